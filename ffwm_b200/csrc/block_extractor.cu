@@ -1,0 +1,245 @@
+// block_extractor: k x k bilinear block extraction around a flow field.
+//
+// Semantics restate cuda/block_extractor/block_extractor_kernel.cu of the
+// reference (K4 :20-85, K5 :89-170): for every flow pixel
+// (yf,xf) and block offset (i,j) the source is sampled bilinearly at
+// (xf + flow_x + j - k/2, yf + flow_y + i - k/2), tap indices clamped after
+// the weights are formed.
+//
+// Execution plan (not the reference's thread-per-element):
+//   forward   one thread per OUTPUT pixel walks a slice of channels: flow and
+//             the four weights/offsets are formed once, stores are coalesced
+//             and streamed, gathers hit L1/L2.
+//   backward  one thread per FLOW pixel x channel slice; loop (i,j) outside,
+//             channels inside, so geometry is formed k*k times per flow pixel
+//             instead of k*k*C times.  grad_source is a scatter (RED.ADD, as in
+//             the reference).  grad_flow — k*k*C contributions per address,
+//             the reference's worst atomic hotspot — is reduced in registers,
+//             then across the CTA's channel slices through shared memory, and
+//             stored once: no atomics, deterministic.
+#include "common.cuh"
+
+namespace ffwm {
+
+template <typename T>
+struct Bilin {
+    int xL, xR, yT, yB;          // clamped indices
+    T xL_P, xR_P, yT_P, yB_P;    // weights from the unclamped coordinate
+};
+
+// block_extractor_kernel.cu:57-76 — same expression order.
+template <typename T>
+__device__ __forceinline__ Bilin<T> block_tap(T flow_x_raw, T flow_y_raw, int xf, int yf,
+                                              int xoff, int yoff, int hs, int ws) {
+    const T flow_y = flow_y_raw + yoff;
+    const T flow_x = flow_x_raw + xoff;
+    const T dy = flow_y + T(yf);
+    const T dx = flow_x + T(xf);
+    const T fdx = floor(dx), fdy = floor(dy);
+    Bilin<T> r;
+    r.xL = clampi(f2i(fdx), ws - 1);
+    r.xR = clampi(f2i(fdx + 1), ws - 1);
+    r.yT = clampi(f2i(fdy), hs - 1);
+    r.yB = clampi(f2i(fdy + 1), hs - 1);
+    r.xL_P = 1 - (dx - fdx);
+    r.xR_P = dx - fdx;
+    r.yT_P = 1 - (dy - fdy);
+    r.yB_P = dy - fdy;
+    return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+block_extractor_fwd_kernel(View<const T> src, View<const T> flow, View<T> out, int k, int c_per_block) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= out.h * out.w) return;
+    const int b = blockIdx.z;
+    const int y = pix / out.w, x = pix - y * out.w;
+    const int yf = y / k, xf = x / k;
+    const int yoff = y - yf * k - k / 2, xoff = x - xf * k - k / 2;
+
+    const T* f = flow.p + b * flow.sb + yf * flow.sh + xf * flow.sw;
+    const Bilin<T> t = block_tap<T>(__ldg(f), __ldg(f + flow.sc), xf, yf, xoff, yoff, src.h, src.w);
+    const int oTL = t.yT * src.sh + t.xL * src.sw, oTR = t.yT * src.sh + t.xR * src.sw;
+    const int oBL = t.yB * src.sh + t.xL * src.sw, oBR = t.yB * src.sh + t.xR * src.sw;
+    const T wTL = t.xL_P * t.yT_P, wTR = t.xR_P * t.yT_P, wBL = t.xL_P * t.yB_P, wBR = t.xR_P * t.yB_P;
+
+    const int c0 = blockIdx.y * c_per_block;
+    const int c1 = min(c0 + c_per_block, out.c);
+    const T* s = src.plane(b, c0);
+    T* d = out.plane(b, c0) + y * out.sh + x * out.sw;
+#pragma unroll 4
+    for (int c = c0; c < c1; ++c, s += src.sc, d += out.sc) {
+        T sample = T(0);
+        sample += wTL * __ldg(s + oTL);
+        sample += wTR * __ldg(s + oTR);
+        sample += wBL * __ldg(s + oBL);
+        sample += wBR * __ldg(s + oBR);
+        st_stream(d, sample);
+    }
+}
+
+template <typename T, int SL>
+__global__ void __launch_bounds__(256)
+block_extractor_bwd_kernel(View<const T> src, View<const T> flow, View<const T> gout,
+                           View<T> gsrc, View<T> gflow, int k) {
+    constexpr int PX = 256 / SL;
+    __shared__ T red[SL > 1 ? SL : 1][2][PX];
+
+    const int lane_px = threadIdx.x, slice = threadIdx.y;
+    const int fpix = blockIdx.x * PX + lane_px;
+    const int b = blockIdx.z;
+    const bool live = fpix < flow.h * flow.w;
+    const bool want_src = gsrc.p != nullptr, want_flow = gflow.p != nullptr;
+
+    T gx = T(0), gy = T(0);
+    int yf = 0, xf = 0;
+    if (live) {
+        yf = fpix / flow.w;
+        xf = fpix - yf * flow.w;
+        const T* f = flow.p + b * flow.sb + yf * flow.sh + xf * flow.sw;
+        const T fx_raw = __ldg(f), fy_raw = __ldg(f + flow.sc);
+        for (int i = 0; i < k; ++i) {
+            for (int j = 0; j < k; ++j) {
+                const Bilin<T> t = block_tap<T>(fx_raw, fy_raw, xf, yf, j - k / 2, i - k / 2, src.h, src.w);
+                const int goff = (yf * k + i) * gout.sh + (xf * k + j) * gout.sw;
+                const int sTL = t.yT * src.sh + t.xL * src.sw, sTR = t.yT * src.sh + t.xR * src.sw;
+                const int sBL = t.yB * src.sh + t.xL * src.sw, sBR = t.yB * src.sh + t.xR * src.sw;
+                const int dTL = t.yT * gsrc.sh + t.xL * gsrc.sw, dTR = t.yT * gsrc.sh + t.xR * gsrc.sw;
+                const int dBL = t.yB * gsrc.sh + t.xL * gsrc.sw, dBR = t.yB * gsrc.sh + t.xR * gsrc.sw;
+#pragma unroll 2
+                for (int c = slice; c < gout.c; c += SL) {
+                    const T grad = ld_stream(gout.plane(b, c) + goff);
+                    if (want_src) {
+                        T* d = gsrc.plane(b, c);
+                        red_add(d + dTL, grad * t.xL_P * t.yT_P);
+                        red_add(d + dTR, grad * t.xR_P * t.yT_P);
+                        red_add(d + dBL, grad * t.xL_P * t.yB_P);
+                        red_add(d + dBR, grad * t.xR_P * t.yB_P);
+                    }
+                    if (want_flow) {
+                        const T* s = src.plane(b, c);
+                        const T xL_yT = __ldg(s + sTL), xR_yT = __ldg(s + sTR);
+                        const T xL_yB = __ldg(s + sBL), xR_yB = __ldg(s + sBR);
+                        gy += grad * (-t.xL_P * xL_yT - t.xR_P * xR_yT + t.xL_P * xL_yB + t.xR_P * xR_yB);
+                        gx += grad * (-t.yT_P * xL_yT - t.yB_P * xL_yB + t.yT_P * xR_yT + t.yB_P * xR_yB);
+                    }
+                }
+            }
+        }
+    }
+
+    if (!want_flow) return;
+    if (SL > 1) {
+        red[slice][0][lane_px] = gx;
+        red[slice][1][lane_px] = gy;
+        __syncthreads();
+        if (slice != 0) return;
+#pragma unroll
+        for (int s = 1; s < SL; ++s) {
+            gx += red[s][0][lane_px];
+            gy += red[s][1][lane_px];
+        }
+    }
+    if (!live) return;
+    T* o = gflow.p + b * gflow.sb + yf * gflow.sh + xf * gflow.sw;
+    o[0] = gx;
+    o[gflow.sc] = gy;
+}
+
+template <typename T, int SL>
+static void launch_bwd_sl(const View<const T>& src, const View<const T>& flow, const View<const T>& gout,
+                          const View<T>& gs, const View<T>& gf, int k, cudaStream_t st) {
+    constexpr int PX = 256 / SL;
+    dim3 grid(ceil_div(flow.h * flow.w, PX), 1, gout.n), block(PX, SL);
+    block_extractor_bwd_kernel<T, SL><<<grid, block, 0, st>>>(src, flow, gout, gs, gf, k);
+}
+
+template <typename T>
+static int block_extractor_forward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, const ffwm_tensor4* o,
+                                     int k, cudaStream_t st) {
+    View<const T> src, flow;
+    View<T> out;
+    int rc;
+    if ((rc = make_view<const T>(a, "source", &src))) return rc;
+    if ((rc = make_view<const T>(b, "flow_field", &flow))) return rc;
+    if ((rc = make_view<T>(o, "output", &out))) return rc;
+    if (k < 1) { set_error("block_extractor: kernel_size=%d", k); return FFWM_ERR_ARG; }
+    if (flow.c != 2) { set_error("block_extractor: flow_field needs 2 channels, got %d", flow.c); return FFWM_ERR_SHAPE; }
+    if (out.n != flow.n || src.n < out.n || out.c != src.c ||
+        (int64_t)out.h != (int64_t)k * flow.h || (int64_t)out.w != (int64_t)k * flow.w) {
+        set_error("block_extractor: output (%d,%d,%d,%d) != (B,C,k*Hf,k*Wf) for k=%d, flow (%d,2,%d,%d), source C=%d",
+                  out.n, out.c, out.h, out.w, k, flow.n, flow.h, flow.w, src.c);
+        return FFWM_ERR_SHAPE;
+    }
+    if ((int64_t)out.n * out.c * out.h * out.w == 0) return FFWM_OK;
+    if (out.n > 65535) { set_error("block_extractor: batch %d > 65535", out.n); return FFWM_ERR_TOO_LARGE; }
+    if (src.h == 0 || src.w == 0) { set_error("block_extractor: empty source plane"); return FFWM_ERR_SHAPE; }
+    const int pix_blocks = ceil_div((int64_t)out.h * out.w, 256);
+    int64_t want = (int64_t)8 * sm_count();
+    int chunks = int((want + (int64_t)pix_blocks * out.n - 1) / ((int64_t)pix_blocks * out.n));
+    chunks = max(1, min(min(chunks, ceil_div(out.c, 4)), 65535));
+    const int c_per_block = ceil_div(out.c, chunks);
+    chunks = ceil_div(out.c, c_per_block);
+    dim3 grid(pix_blocks, chunks, out.n);
+    block_extractor_fwd_kernel<T><<<grid, 256, 0, st>>>(src, flow, out, k, c_per_block);
+    return check_launch("block_extractor_forward");
+}
+
+template <typename T>
+static int block_extractor_backward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, const ffwm_tensor4* go,
+                                      const ffwm_tensor4* ga, const ffwm_tensor4* gb, int k, cudaStream_t st) {
+    View<const T> src, flow, gout;
+    View<T> gs, gf;
+    int rc;
+    if ((rc = make_view<const T>(a, "source", &src))) return rc;
+    if ((rc = make_view<const T>(b, "flow_field", &flow))) return rc;
+    if ((rc = make_view<const T>(go, "grad_output", &gout))) return rc;
+    if ((rc = make_view<T>(ga, "grad_source", &gs, true))) return rc;
+    if ((rc = make_view<T>(gb, "grad_flow_field", &gf, true))) return rc;
+    if (k < 1) { set_error("block_extractor: kernel_size=%d", k); return FFWM_ERR_ARG; }
+    if (flow.c != 2) { set_error("block_extractor: flow_field needs 2 channels, got %d", flow.c); return FFWM_ERR_SHAPE; }
+    if (gout.n != flow.n || src.n < gout.n || gout.c != src.c ||
+        (int64_t)gout.h != (int64_t)k * flow.h || (int64_t)gout.w != (int64_t)k * flow.w) {
+        set_error("block_extractor_backward: grad_output (%d,%d,%d,%d) != (B,C,k*Hf,k*Wf)", gout.n, gout.c, gout.h, gout.w);
+        return FFWM_ERR_SHAPE;
+    }
+    if (gs.p && (gs.n != src.n || gs.c != src.c || gs.h != src.h || gs.w != src.w)) {
+        set_error("block_extractor_backward: grad_source shape differs from source"); return FFWM_ERR_SHAPE;
+    }
+    if (gf.p && (gf.n != flow.n || gf.c != 2 || gf.h != flow.h || gf.w != flow.w)) {
+        set_error("block_extractor_backward: grad_flow_field shape differs from flow_field"); return FFWM_ERR_SHAPE;
+    }
+    if ((int64_t)gout.n * gout.h * gout.w == 0) return FFWM_OK;
+    if (gout.n > 65535) { set_error("block_extractor: batch %d > 65535", gout.n); return FFWM_ERR_TOO_LARGE; }
+    if (src.h == 0 || src.w == 0) { set_error("block_extractor: empty source plane"); return FFWM_ERR_SHAPE; }
+    const int c = gout.c;
+    if (c >= 8) launch_bwd_sl<T, 8>(src, flow, gout, gs, gf, k, st);
+    else if (c >= 4) launch_bwd_sl<T, 4>(src, flow, gout, gs, gf, k, st);
+    else if (c >= 2) launch_bwd_sl<T, 2>(src, flow, gout, gs, gf, k, st);
+    else launch_bwd_sl<T, 1>(src, flow, gout, gs, gf, k, st);
+    return check_launch("block_extractor_backward");
+}
+
+}  // namespace ffwm
+
+extern "C" int ffwm_block_extractor_forward(const ffwm_tensor4* source, const ffwm_tensor4* flow,
+                                            const ffwm_tensor4* output, int kernel_size, int dtype, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == FFWM_F32) return ffwm::block_extractor_forward_t<float>(source, flow, output, kernel_size, st);
+    if (dtype == FFWM_F64) return ffwm::block_extractor_forward_t<double>(source, flow, output, kernel_size, st);
+    ffwm::set_error("block_extractor_forward: unsupported dtype %d", dtype);
+    return FFWM_ERR_ARG;
+}
+
+extern "C" int ffwm_block_extractor_backward(const ffwm_tensor4* source, const ffwm_tensor4* flow,
+                                             const ffwm_tensor4* grad_output, const ffwm_tensor4* grad_source,
+                                             const ffwm_tensor4* grad_flow, int kernel_size, int dtype, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == FFWM_F32)
+        return ffwm::block_extractor_backward_t<float>(source, flow, grad_output, grad_source, grad_flow, kernel_size, st);
+    if (dtype == FFWM_F64)
+        return ffwm::block_extractor_backward_t<double>(source, flow, grad_output, grad_source, grad_flow, kernel_size, st);
+    ffwm::set_error("block_extractor_backward: unsupported dtype %d", dtype);
+    return FFWM_ERR_ARG;
+}

@@ -1,0 +1,501 @@
+// resample2d: GFLA Gaussian-weighted flow resampling, forward + fused backward.
+//
+// Semantics restate cuda/resample2d_package/resample2d_kernel.cu of the
+// reference (K1 :20-95, K2 :98-202, K3 :204-330) including its numerics
+// quirks.  The execution plan is different:
+//
+//   * one thread owns one output PIXEL and walks a slice of the channels, so
+//     (dx,dy,sigma), the 4*(ks/2) double-precision exps, the tap offsets and
+//     the normaliser are computed once per pixel instead of once per element
+//     (the reference redoes them C times, and 3*C times in K3);
+//   * forward: HBM traffic is the algorithmic minimum (flow once, source
+//     through L1/L2 gathers, output streamed with coalesced stores);
+//   * backward: K2 and K3 are ONE pass over grad_output.  The scatter into
+//     grad_input1 uses RED.ADD (as the reference must); the flow gradient is
+//     reduced over channels in registers, across the channel slices of a CTA
+//     through shared memory, and stored once — no atomics, deterministic,
+//     and all three components (dx,dy,sigma) come out of the same pass.
+#include "common.cuh"
+
+namespace ffwm {
+
+// Per-pixel tap geometry shared by forward and backward.
+template <typename T, int HALF>
+struct Taps {
+    int ix[2 * HALF];   // clamped column index: [2*fx] = left, [2*fx+1] = right
+    int iy[2 * HALF];   // clamped row index:    [2*fy] = top,  [2*fy+1] = bottom
+    T dxs[2 * HALF];    // distances xL_, xR_ (resample2d_kernel.cu:70-73)
+    T dys[2 * HALF];    // distances yT_, yB_
+};
+
+template <typename T, int HALF>
+__device__ __forceinline__ void tap_geometry(T xf, T yf, T alpha, T beta, int dil, int ih, int iw,
+                                             Taps<T, HALF>& t) {
+    const T fxf = floor(xf), fyf = floor(yf);
+#pragma unroll
+    for (int f = 0; f < HALF; ++f) {
+        t.iy[2 * f] = clampi(f2i(fyf - f * dil), ih - 1);
+        t.iy[2 * f + 1] = clampi(f2i(fyf + (f + 1) * dil), ih - 1);
+        t.ix[2 * f] = clampi(f2i(fxf - f * dil), iw - 1);
+        t.ix[2 * f + 1] = clampi(f2i(fxf + (f + 1) * dil), iw - 1);
+        t.dxs[2 * f] = T(f * dil) + alpha;
+        t.dxs[2 * f + 1] = T((1. + f) * dil) - alpha;
+        t.dys[2 * f] = T(f * dil) + beta;
+        t.dys[2 * f + 1] = T((1. + f) * dil) - beta;
+    }
+}
+
+// Gaussian weights for the distances above and the reference's normaliser,
+// summed in the reference's order (one 4-term group per (fy,fx)).
+template <typename T, int HALF>
+__device__ __forceinline__ T tap_weights(const T* dxs, const T* dys, T sigma, T* wx, T* wy) {
+#pragma unroll
+    for (int i = 0; i < 2 * HALF; ++i) {
+        wx[i] = gauss<T>(dxs[i], sigma);
+        wy[i] = gauss<T>(dys[i], sigma);
+    }
+    T sum = T(0);
+#pragma unroll
+    for (int fy = 0; fy < HALF; ++fy)
+#pragma unroll
+        for (int fx = 0; fx < HALF; ++fx)
+            sum += (wy[2 * fy] * wx[2 * fx] + wy[2 * fy] * wx[2 * fx + 1] +
+                    wy[2 * fy + 1] * wx[2 * fx] + wy[2 * fy + 1] * wx[2 * fx + 1]);
+    return sum;
+}
+
+// ---------------------------------------------------------------- forward
+template <typename T, int HALF>
+__global__ void __launch_bounds__(256)
+resample2d_fwd_kernel(View<const T> in1, View<const T> in2, View<T> out, int dil, int c_per_block) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= out.h * out.w) return;
+    const int b = blockIdx.z;
+    const int y = pix / out.w, x = pix - y * out.w;
+
+    const T* f = in2.p + b * in2.sb + y * in2.sh + x * in2.sw;
+    const T dx = ld_stream(f), dy = ld_stream(f + in2.sc), sigma = ld_stream(f + 2 * in2.sc);
+    const T xf = T(x) + dx, yf = T(y) + dy;
+
+    Taps<T, HALF> t;
+    tap_geometry<T, HALF>(xf, yf, xf - floor(xf), yf - floor(yf), dil, in1.h, in1.w, t);
+    T wx[2 * HALF], wy[2 * HALF];
+    const T sum = tap_weights<T, HALF>(t.dxs, t.dys, sigma, wx, wy);
+    int ox[2 * HALF], oy[2 * HALF];
+#pragma unroll
+    for (int i = 0; i < 2 * HALF; ++i) { ox[i] = t.ix[i] * in1.sw; oy[i] = t.iy[i] * in1.sh; }
+
+    const int c0 = blockIdx.y * c_per_block;
+    const int c1 = min(c0 + c_per_block, out.c);
+    const T* src = in1.plane(b, c0);
+    T* dst = out.plane(b, c0) + y * out.sh + x * out.sw;
+#pragma unroll 2
+    for (int c = c0; c < c1; ++c, src += in1.sc, dst += out.sc) {
+        T val = T(0);
+#pragma unroll
+        for (int fy = 0; fy < HALF; ++fy)
+#pragma unroll
+            for (int fx = 0; fx < HALF; ++fx) {
+                const T* rt = src + oy[2 * fy];
+                const T* rb = src + oy[2 * fy + 1];
+                val += wy[2 * fy] * wx[2 * fx] * __ldg(rt + ox[2 * fx]);
+                val += wy[2 * fy] * wx[2 * fx + 1] * __ldg(rt + ox[2 * fx + 1]);
+                val += wy[2 * fy + 1] * wx[2 * fx] * __ldg(rb + ox[2 * fx]);
+                val += wy[2 * fy + 1] * wx[2 * fx + 1] * __ldg(rb + ox[2 * fx + 1]);
+            }
+        st_stream(dst, T(safe_div<T>(val, sum)));
+    }
+}
+
+// Any kernel_size (runtime ks/2), no per-pixel arrays: weights are recomputed
+// per tap.  Only reached for kernel_size > 8; kept so that every argument the
+// reference accepts is served by the device path.
+template <typename T>
+__global__ void __launch_bounds__(256)
+resample2d_fwd_generic_kernel(View<const T> in1, View<const T> in2, View<T> out, int half, int dil) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= out.h * out.w) return;
+    const int b = blockIdx.z;
+    const int y = pix / out.w, x = pix - y * out.w;
+    const T* f = in2.p + b * in2.sb + y * in2.sh + x * in2.sw;
+    const T dx = f[0], dy = f[in2.sc], sigma = f[2 * in2.sc];
+    const T xf = T(x) + dx, yf = T(y) + dy;
+    const T alpha = xf - floor(xf), beta = yf - floor(yf);
+    for (int c = blockIdx.y; c < out.c; c += gridDim.y) {
+        const T* src = in1.plane(b, c);
+        T val = T(0), sum = T(0);
+        for (int fy = 0; fy < half; ++fy) {
+            const int yT = clampi(f2i(floor(yf) - fy * dil), in1.h - 1) * in1.sh;
+            const int yB = clampi(f2i(floor(yf) + (fy + 1) * dil), in1.h - 1) * in1.sh;
+            const T yT_P = gauss<T>(T(fy * dil) + beta, sigma);
+            const T yB_P = gauss<T>(T((1. + fy) * dil) - beta, sigma);
+            for (int fx = 0; fx < half; ++fx) {
+                const int xL = clampi(f2i(floor(xf) - fx * dil), in1.w - 1) * in1.sw;
+                const int xR = clampi(f2i(floor(xf) + (fx + 1) * dil), in1.w - 1) * in1.sw;
+                const T xL_P = gauss<T>(T(fx * dil) + alpha, sigma);
+                const T xR_P = gauss<T>(T((1. + fx) * dil) - alpha, sigma);
+                val += yT_P * xL_P * src[yT + xL];
+                val += yT_P * xR_P * src[yT + xR];
+                val += yB_P * xL_P * src[yB + xL];
+                val += yB_P * xR_P * src[yB + xR];
+                sum += (yT_P * xL_P + yT_P * xR_P + yB_P * xL_P + yB_P * xR_P);
+            }
+        }
+        out.plane(b, c)[y * out.sh + x * out.sw] = T(safe_div<T>(val, sum));
+    }
+}
+
+// --------------------------------------------------------------- backward
+// CTA = PX pixels x SL channel slices (PX*SL = 256).  Slice s owns channels
+// s, s+SL, s+2SL, ...  Per channel and tap: one gather of input1, one RED
+// into grad_input1 (skipped when gin1.p == nullptr), three FMAs for the
+// flow-gradient partial sums.
+template <typename T, int HALF, int SL>
+__global__ void __launch_bounds__(256)
+resample2d_bwd_kernel(View<const T> in1, View<const T> in2, View<const T> gout,
+                      View<T> gin1, View<T> gin2, int dil) {
+    constexpr int PX = 256 / SL;
+    constexpr int NT = 2 * HALF;
+    __shared__ T red[SL > 1 ? SL : 1][4][PX];
+
+    const int lane_px = threadIdx.x;          // 0..PX-1
+    const int slice = threadIdx.y;            // 0..SL-1
+    const int pix = blockIdx.x * PX + lane_px;
+    const int b = blockIdx.z;
+    const bool live = pix < gout.h * gout.w;
+
+    T A0 = T(0), A1 = T(0), A2 = T(0), Bs = T(0);
+    T sum = T(0), sigma = T(1);
+    T Wx = T(0), Wy = T(0), AX = T(0), AY = T(0), BX = T(0), BY = T(0);
+    int y = 0, x = 0;
+
+    if (live) {
+        y = pix / gout.w;
+        x = pix - y * gout.w;
+        const T* f = in2.p + b * in2.sb + y * in2.sh + x * in2.sw;
+        const T dx = f[0], dy = f[in2.sc];
+        sigma = f[2 * in2.sc];
+        const T xf = T(x) + dx, yf = T(y) + dy;
+
+        Taps<T, HALF> t;
+        tap_geometry<T, HALF>(xf, yf, xf - floor(xf), yf - floor(yf), dil, in1.h, in1.w, t);
+        T wx[NT], wy[NT];
+        sum = tap_weights<T, HALF>(t.dxs, t.dys, sigma, wx, wy);
+
+        // K2 weights: alpha = xf - int(xf) (truncation).  They only
+        // differ from the floor version for negative non-integer coordinates.
+        T qx[NT], qy[NT], sum2 = sum;
+        const T alpha2 = xf - T(f2i(xf)), beta2 = yf - T(f2i(yf));
+        if (alpha2 != t.dxs[0] || beta2 != t.dys[0]) {
+            T d2x[NT], d2y[NT];
+#pragma unroll
+            for (int k = 0; k < HALF; ++k) {
+                d2x[2 * k] = T(k * dil) + alpha2;
+                d2x[2 * k + 1] = T((1. + k) * dil) - alpha2;
+                d2y[2 * k] = T(k * dil) + beta2;
+                d2y[2 * k + 1] = T((1. + k) * dil) - beta2;
+            }
+            sum2 = tap_weights<T, HALF>(d2x, d2y, sigma, qx, qy);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NT; ++i) { qx[i] = wx[i]; qy[i] = wy[i]; }
+        }
+        // q[i][j] = SAFE_DIV(w, sum) of K2 :195-198, rounded to T.  The product
+        // q*gOut is formed in double by the reference and rounded once; for
+        // T-representable q that equals the T product.  sum2 == 0 implies every
+        // w == 0 (weights are non-negative), so the EPS branch also yields 0.
+        T q[NT][NT];
+#pragma unroll
+        for (int i = 0; i < NT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) q[i][j] = T(safe_div<T>(qy[i] * qx[j], sum2));
+
+        // Separable coefficients of the three flow-gradient numerators
+        // (resample2d_kernel.cu:271-294): sign * distance * weight.
+        T ax[NT], ay[NT], bx[NT], by[NT];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            const T sgn_x = (i & 1) ? T(-1) : T(1);   // +xL_, -xR_
+            const T sgn_y = (i & 1) ? T(-1) : T(1);   // +yT_, -yB_
+            ax[i] = sgn_x * t.dxs[i] * wx[i];
+            ay[i] = sgn_y * t.dys[i] * wy[i];
+            bx[i] = t.dxs[i] * t.dxs[i] * wx[i];
+            by[i] = t.dys[i] * t.dys[i] * wy[i];
+            Wx += wx[i]; Wy += wy[i];
+            AX += ax[i]; AY += ay[i];
+            BX += bx[i]; BY += by[i];
+        }
+
+        const bool want1 = gin1.p != nullptr;
+        const bool want2 = gin2.p != nullptr;
+        const int goff = y * gout.sh + x * gout.sw;
+        for (int c = slice; c < gout.c; c += SL) {
+            const T g = ld_stream(gout.plane(b, c) + goff);
+            const T* src = in1.plane(b, c);
+            T* dst = want1 ? gin1.plane(b, c) : nullptr;
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                T r0 = T(0), rB = T(0), r2 = T(0);
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    if (want2) {
+                        const T s = g * __ldg(src + t.iy[i] * in1.sh + t.ix[j] * in1.sw);
+                        r0 += ax[j] * s;
+                        rB += wx[j] * s;
+                        r2 += bx[j] * s;
+                    }
+                    if (want1) {
+                        // gin1 has in1's geometry but its own strides
+                        red_add(dst + t.iy[i] * gin1.sh + t.ix[j] * gin1.sw, q[i][j] * g);
+                    }
+                }
+                A0 += wy[i] * r0;
+                A1 += ay[i] * rB;
+                A2 += by[i] * rB + wy[i] * r2;
+                Bs += wy[i] * rB;
+            }
+        }
+    }
+
+    if (gin2.p == nullptr) return;   // uniform across the CTA
+    if (SL > 1) {
+        red[slice][0][lane_px] = A0;
+        red[slice][1][lane_px] = A1;
+        red[slice][2][lane_px] = A2;
+        red[slice][3][lane_px] = Bs;
+        __syncthreads();
+        if (slice != 0) return;
+#pragma unroll
+        for (int s = 1; s < SL; ++s) {
+            A0 += red[s][0][lane_px];
+            A1 += red[s][1][lane_px];
+            A2 += red[s][2][lane_px];
+            Bs += red[s][3][lane_px];
+        }
+    }
+    if (!live) return;
+
+    // grad1_c = A_c / div_c ; grad2_c = (sumgrad_c / C) * Bs with
+    // sumgrad_c / C = sum_t coef_t * w_t / div_c   (K3 :271-294,318-328).
+    const T ms2 = -sigma * sigma, s3 = sigma * sigma * sigma;
+    const T G0 = T(safe_div<T>(Wy * AX, ms2));
+    const T G1 = T(safe_div<T>(AY * Wx, ms2));
+    const T G2 = T(safe_div<T>(BY * Wx + Wy * BX, s3));
+    const T g10 = T(safe_div<T>(A0, ms2));
+    const T g11 = T(safe_div<T>(A1, ms2));
+    const T g12 = T(safe_div<T>(A2, s3));
+    const T ss = sum * sum;
+    T* o = gin2.p + b * gin2.sb + y * gin2.sh + x * gin2.sw;
+    o[0] = T(safe_div<T>(g10, sum) - safe_div<T>(G0 * Bs, ss));
+    if (gin2.c > 1) o[gin2.sc] = T(safe_div<T>(g11, sum) - safe_div<T>(G1 * Bs, ss));
+    if (gin2.c > 2) o[2 * gin2.sc] = T(safe_div<T>(g12, sum) - safe_div<T>(G2 * Bs, ss));
+}
+
+// Generic-ks backward (kernel_size > 8): thread per pixel, channels looped,
+// weights recomputed per tap.  Correct for every argument, not tuned.
+template <typename T>
+__global__ void __launch_bounds__(256)
+resample2d_bwd_generic_kernel(View<const T> in1, View<const T> in2, View<const T> gout,
+                              View<T> gin1, View<T> gin2, int half, int dil) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= gout.h * gout.w) return;
+    const int b = blockIdx.z;
+    const int y = pix / gout.w, x = pix - y * gout.w;
+    const T* f = in2.p + b * in2.sb + y * in2.sh + x * in2.sw;
+    const T dx = f[0], dy = f[in2.sc], sigma = f[2 * in2.sc];
+    const T xf = T(x) + dx, yf = T(y) + dy;
+    const T alpha = xf - floor(xf), beta = yf - floor(yf);
+    const T alpha2 = xf - T(f2i(xf)), beta2 = yf - T(f2i(yf));
+    const T ms2 = -sigma * sigma, s3 = sigma * sigma * sigma;
+
+    T sum = T(0), sum2 = T(0), G0 = T(0), G1 = T(0), G2 = T(0);
+    for (int fy = 0; fy < half; ++fy)
+        for (int fx = 0; fx < half; ++fx) {
+            const T xd[2] = {T(fx * dil) + alpha, T((1. + fx) * dil) - alpha};
+            const T yd[2] = {T(fy * dil) + beta, T((1. + fy) * dil) - beta};
+            const T xd2[2] = {T(fx * dil) + alpha2, T((1. + fx) * dil) - alpha2};
+            const T yd2[2] = {T(fy * dil) + beta2, T((1. + fy) * dil) - beta2};
+            for (int i = 0; i < 2; ++i)
+                for (int j = 0; j < 2; ++j) {
+                    const T w = gauss<T>(yd[i], sigma) * gauss<T>(xd[j], sigma);
+                    sum += w;
+                    sum2 += gauss<T>(yd2[i], sigma) * gauss<T>(xd2[j], sigma);
+                    G0 += T(safe_div<T>((j ? -xd[j] : xd[j]) * w, ms2));
+                    G1 += T(safe_div<T>((i ? -yd[i] : yd[i]) * w, ms2));
+                    G2 += T(safe_div<T>((yd[i] * yd[i] + xd[j] * xd[j]) * w, s3));
+                }
+        }
+
+    T A0 = T(0), A1 = T(0), A2 = T(0), Bs = T(0);
+    for (int c = 0; c < gout.c; ++c) {
+        const T g = gout.plane(b, c)[y * gout.sh + x * gout.sw];
+        const T* src = in1.plane(b, c);
+        T* dst = gin1.p ? gin1.plane(b, c) : nullptr;
+        for (int fy = 0; fy < half; ++fy)
+            for (int fx = 0; fx < half; ++fx) {
+                const int yy[2] = {clampi(f2i(floor(yf) - fy * dil), in1.h - 1),
+                                   clampi(f2i(floor(yf) + (fy + 1) * dil), in1.h - 1)};
+                const int xx[2] = {clampi(f2i(floor(xf) - fx * dil), in1.w - 1),
+                                   clampi(f2i(floor(xf) + (fx + 1) * dil), in1.w - 1)};
+                const T xd[2] = {T(fx * dil) + alpha, T((1. + fx) * dil) - alpha};
+                const T yd[2] = {T(fy * dil) + beta, T((1. + fy) * dil) - beta};
+                const T xd2[2] = {T(fx * dil) + alpha2, T((1. + fx) * dil) - alpha2};
+                const T yd2[2] = {T(fy * dil) + beta2, T((1. + fy) * dil) - beta2};
+                for (int i = 0; i < 2; ++i)
+                    for (int j = 0; j < 2; ++j) {
+                        const T w = gauss<T>(yd[i], sigma) * gauss<T>(xd[j], sigma);
+                        const T s = g * src[yy[i] * in1.sh + xx[j] * in1.sw];
+                        A0 += T(safe_div<T>((j ? -xd[j] : xd[j]) * w * s, ms2));
+                        A1 += T(safe_div<T>((i ? -yd[i] : yd[i]) * w * s, ms2));
+                        A2 += T(safe_div<T>((yd[i] * yd[i] + xd[j] * xd[j]) * w * s, s3));
+                        Bs += w * s;
+                        if (dst) {
+                            const T w2 = gauss<T>(yd2[i], sigma) * gauss<T>(xd2[j], sigma);
+                            red_add(dst + yy[i] * gin1.sh + xx[j] * gin1.sw,
+                                    T(safe_div<T>(w2, sum2) * double(g)));
+                        }
+                    }
+            }
+    }
+    if (!gin2.p) return;
+    const T ss = sum * sum;
+    T* o = gin2.p + b * gin2.sb + y * gin2.sh + x * gin2.sw;
+    o[0] = T(safe_div<T>(A0, sum) - safe_div<T>(G0 * Bs, ss));
+    if (gin2.c > 1) o[gin2.sc] = T(safe_div<T>(A1, sum) - safe_div<T>(G1 * Bs, ss));
+    if (gin2.c > 2) o[2 * gin2.sc] = T(safe_div<T>(A2, sum) - safe_div<T>(G2 * Bs, ss));
+}
+
+// ------------------------------------------------------------ host launch
+template <typename T, int HALF>
+static void launch_fwd(const View<const T>& in1, const View<const T>& in2, const View<T>& out,
+                       int dil, cudaStream_t st) {
+    const int hw = out.h * out.w;
+    const int pix_blocks = ceil_div(hw, 256);
+    // enough CTAs for ~8 per SM, but at least 4 channels per CTA so the
+    // per-pixel exps stay amortised
+    int64_t want = (int64_t)8 * sm_count();
+    int chunks = int((want + (int64_t)pix_blocks * out.n - 1) / ((int64_t)pix_blocks * out.n));
+    chunks = max(1, min(chunks, ceil_div(out.c, 4)));
+    chunks = min(chunks, 65535);
+    const int c_per_block = ceil_div(out.c, chunks);
+    chunks = ceil_div(out.c, c_per_block);
+    dim3 grid(pix_blocks, chunks, out.n);
+    resample2d_fwd_kernel<T, HALF><<<grid, 256, 0, st>>>(in1, in2, out, dil, c_per_block);
+}
+
+template <typename T, int HALF, int SL>
+static void launch_bwd_sl(const View<const T>& in1, const View<const T>& in2, const View<const T>& gout,
+                          const View<T>& g1, const View<T>& g2, int dil, cudaStream_t st) {
+    constexpr int PX = 256 / SL;
+    dim3 grid(ceil_div(gout.h * gout.w, PX), 1, gout.n), block(PX, SL);
+    resample2d_bwd_kernel<T, HALF, SL><<<grid, block, 0, st>>>(in1, in2, gout, g1, g2, dil);
+}
+
+template <typename T, int HALF>
+static void launch_bwd(const View<const T>& in1, const View<const T>& in2, const View<const T>& gout,
+                       const View<T>& g1, const View<T>& g2, int dil, cudaStream_t st) {
+    const int c = gout.c;
+    if (c >= 8) launch_bwd_sl<T, HALF, 8>(in1, in2, gout, g1, g2, dil, st);
+    else if (c >= 4) launch_bwd_sl<T, HALF, 4>(in1, in2, gout, g1, g2, dil, st);
+    else if (c >= 2) launch_bwd_sl<T, HALF, 2>(in1, in2, gout, g1, g2, dil, st);
+    else launch_bwd_sl<T, HALF, 1>(in1, in2, gout, g1, g2, dil, st);
+}
+
+template <typename T>
+static int resample2d_forward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, const ffwm_tensor4* o,
+                                int ks, int dil, cudaStream_t st) {
+    View<const T> in1, in2;
+    View<T> out;
+    int rc;
+    if ((rc = make_view<const T>(a, "input1", &in1))) return rc;
+    if ((rc = make_view<const T>(b, "input2", &in2))) return rc;
+    if ((rc = make_view<T>(o, "output", &out))) return rc;
+    if (in2.c < 3) { set_error("resample2d: input2 needs 3 channels (dx,dy,sigma), got %d", in2.c); return FFWM_ERR_SHAPE; }
+    if (out.n != in2.n || out.h != in2.h || out.w != in2.w || out.c != in1.c || in1.n < out.n) {
+        set_error("resample2d: output (%d,%d,%d,%d) inconsistent with input1 C=%d N=%d / input2 (%d,3,%d,%d)",
+                  out.n, out.c, out.h, out.w, in1.c, in1.n, in2.n, in2.h, in2.w);
+        return FFWM_ERR_SHAPE;
+    }
+    if (ks < 0 || dil < 0) { set_error("resample2d: kernel_size=%d dilation=%d", ks, dil); return FFWM_ERR_ARG; }
+    if ((int64_t)out.n * out.c * out.h * out.w == 0) return FFWM_OK;
+    if (out.n > 65535) { set_error("resample2d: batch %d > 65535", out.n); return FFWM_ERR_TOO_LARGE; }
+    if (in1.h == 0 || in1.w == 0) { set_error("resample2d: empty input1 plane"); return FFWM_ERR_SHAPE; }
+    const int half = ks / 2;
+    switch (half) {
+        case 1: launch_fwd<T, 1>(in1, in2, out, dil, st); break;
+        case 2: launch_fwd<T, 2>(in1, in2, out, dil, st); break;
+        case 3: launch_fwd<T, 3>(in1, in2, out, dil, st); break;
+        case 4: launch_fwd<T, 4>(in1, in2, out, dil, st); break;
+        default: {
+            dim3 grid(ceil_div(out.h * out.w, 256), min(out.c, 64), out.n);
+            resample2d_fwd_generic_kernel<T><<<grid, 256, 0, st>>>(in1, in2, out, half, dil);
+        }
+    }
+    return check_launch("resample2d_forward");
+}
+
+template <typename T>
+static int resample2d_backward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, const ffwm_tensor4* go,
+                                 const ffwm_tensor4* ga, const ffwm_tensor4* gb,
+                                 int ks, int dil, cudaStream_t st) {
+    View<const T> in1, in2, gout;
+    View<T> g1, g2;
+    int rc;
+    if ((rc = make_view<const T>(a, "input1", &in1))) return rc;
+    if ((rc = make_view<const T>(b, "input2", &in2))) return rc;
+    if ((rc = make_view<const T>(go, "grad_output", &gout))) return rc;
+    if ((rc = make_view<T>(ga, "grad_input1", &g1, true))) return rc;
+    if ((rc = make_view<T>(gb, "grad_input2", &g2, true))) return rc;
+    if (in2.c < 3) { set_error("resample2d: input2 needs 3 channels"); return FFWM_ERR_SHAPE; }
+    if (gout.n != in2.n || gout.h != in2.h || gout.w != in2.w || gout.c != in1.c || in1.n < gout.n) {
+        set_error("resample2d_backward: grad_output (%d,%d,%d,%d) inconsistent with inputs", gout.n, gout.c, gout.h, gout.w);
+        return FFWM_ERR_SHAPE;
+    }
+    if (g1.p && (g1.n != in1.n || g1.c != in1.c || g1.h != in1.h || g1.w != in1.w)) {
+        set_error("resample2d_backward: grad_input1 shape differs from input1"); return FFWM_ERR_SHAPE;
+    }
+    if (g2.p && (g2.n != in2.n || g2.h != in2.h || g2.w != in2.w || g2.c < 1 || g2.c > 3)) {
+        set_error("resample2d_backward: grad_input2 shape differs from input2"); return FFWM_ERR_SHAPE;
+    }
+    if (ks < 0 || dil < 0) { set_error("resample2d: kernel_size=%d dilation=%d", ks, dil); return FFWM_ERR_ARG; }
+    if ((int64_t)gout.n * gout.h * gout.w == 0) return FFWM_OK;
+    if (gout.n > 65535) { set_error("resample2d: batch %d > 65535", gout.n); return FFWM_ERR_TOO_LARGE; }
+    if (in1.h == 0 || in1.w == 0) { set_error("resample2d: empty input1 plane"); return FFWM_ERR_SHAPE; }
+    const int half = ks / 2;
+    switch (half) {
+        case 1: launch_bwd<T, 1>(in1, in2, gout, g1, g2, dil, st); break;
+        case 2: launch_bwd<T, 2>(in1, in2, gout, g1, g2, dil, st); break;
+        case 3: launch_bwd<T, 3>(in1, in2, gout, g1, g2, dil, st); break;
+        case 4: launch_bwd<T, 4>(in1, in2, gout, g1, g2, dil, st); break;
+        default: {
+            dim3 grid(ceil_div(gout.h * gout.w, 256), 1, gout.n);
+            resample2d_bwd_generic_kernel<T><<<grid, 256, 0, st>>>(in1, in2, gout, g1, g2, half, dil);
+        }
+    }
+    return check_launch("resample2d_backward");
+}
+
+}  // namespace ffwm
+
+extern "C" int ffwm_resample2d_forward(const ffwm_tensor4* input1, const ffwm_tensor4* input2,
+                                       const ffwm_tensor4* output, int kernel_size, int dilation,
+                                       int dtype, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == FFWM_F32) return ffwm::resample2d_forward_t<float>(input1, input2, output, kernel_size, dilation, st);
+    if (dtype == FFWM_F64) return ffwm::resample2d_forward_t<double>(input1, input2, output, kernel_size, dilation, st);
+    ffwm::set_error("resample2d_forward: unsupported dtype %d", dtype);
+    return FFWM_ERR_ARG;
+}
+
+extern "C" int ffwm_resample2d_backward(const ffwm_tensor4* input1, const ffwm_tensor4* input2,
+                                        const ffwm_tensor4* grad_output, const ffwm_tensor4* grad_input1,
+                                        const ffwm_tensor4* grad_input2, int kernel_size, int dilation,
+                                        int dtype, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == FFWM_F32)
+        return ffwm::resample2d_backward_t<float>(input1, input2, grad_output, grad_input1, grad_input2, kernel_size, dilation, st);
+    if (dtype == FFWM_F64)
+        return ffwm::resample2d_backward_t<double>(input1, input2, grad_output, grad_input1, grad_input2, kernel_size, dilation, st);
+    ffwm::set_error("resample2d_backward: unsupported dtype %d", dtype);
+    return FFWM_ERR_ARG;
+}

@@ -1,0 +1,53 @@
+"""Thin tensor-level wrappers over the C ABI (one function per entry point).
+
+These take and fill caller-allocated CUDA tensors exactly like the reference's
+pybind functions do; autograd lives in external_function.py.
+"""
+from . import _lib as L
+
+
+def resample2d_forward(input1, input2, output, kernel_size, dilation):
+    dev = L.require_cuda(input1, input2, output)
+    L.call("ffwm_resample2d_forward", dev, L.t4(input1), L.t4(input2), L.t4(output),
+           int(kernel_size), int(dilation), L.dtype_code(input1))
+
+
+def resample2d_backward(input1, input2, grad_output, grad_input1, grad_input2, kernel_size, dilation):
+    dev = L.require_cuda(input1, input2, grad_output, grad_input1, grad_input2)
+    L.call("ffwm_resample2d_backward", dev, L.t4(input1), L.t4(input2), L.t4(grad_output),
+           L.t4(grad_input1), L.t4(grad_input2), int(kernel_size), int(dilation), L.dtype_code(input1))
+
+
+def block_extractor_forward(source, flow_field, output, kernel_size):
+    dev = L.require_cuda(source, flow_field, output)
+    L.call("ffwm_block_extractor_forward", dev, L.t4(source), L.t4(flow_field), L.t4(output),
+           int(kernel_size), L.dtype_code(source))
+
+
+def block_extractor_backward(source, flow_field, grad_output, grad_source, grad_flow_field, kernel_size):
+    dev = L.require_cuda(source, flow_field, grad_output, grad_source, grad_flow_field)
+    L.call("ffwm_block_extractor_backward", dev, L.t4(source), L.t4(flow_field), L.t4(grad_output),
+           L.t4(grad_source), L.t4(grad_flow_field), int(kernel_size), L.dtype_code(source))
+
+
+def local_attn_reshape_forward(inputs, output, kernel_size):
+    dev = L.require_cuda(inputs, output)
+    L.call("ffwm_local_attn_reshape_forward", dev, L.t4(inputs), L.t4(output),
+           int(kernel_size), L.dtype_code(inputs))
+
+
+def local_attn_reshape_backward(grad_output, grad_inputs, kernel_size):
+    dev = L.require_cuda(grad_output, grad_inputs)
+    L.call("ffwm_local_attn_reshape_backward", dev, L.t4(grad_output), L.t4(grad_inputs),
+           int(kernel_size), L.dtype_code(grad_inputs))
+
+
+def grid_warp_forward(images, flow, output):
+    dev = L.require_cuda(images, flow, output)
+    L.call("ffwm_grid_warp_forward", dev, L.t4(images), L.t4(flow), L.t4(output), L.dtype_code(images))
+
+
+def grid_warp_backward(images, flow, grad_output, grad_images, grad_flow):
+    dev = L.require_cuda(images, flow, grad_output, grad_images, grad_flow)
+    L.call("ffwm_grid_warp_backward", dev, L.t4(images), L.t4(flow), L.t4(grad_output),
+           L.t4(grad_images), L.t4(grad_flow), L.dtype_code(images))

@@ -1,0 +1,124 @@
+/*
+ * ffwm_b200 — C ABI of the B200-native FFWM flow-warping hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces
+ * one function a reference pybind module exports; the Python shims in
+ * ffwm_b200/dropin/ re-export them under the reference's module names
+ * (resample2d_cuda, block_extractor_cuda, local_attn_reshape_cuda) with the
+ * reference's signatures, so models/external_function.py runs unmodified.
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions (identical for every call):
+ *   - tensors are 4-D (N,C,H,W), described by ffwm_tensor4: raw DEVICE
+ *     pointer, sizes and ELEMENT strides (the reference kernels take long4
+ *     size/stride pairs and honour arbitrary strides; so do these);
+ *   - dtype is FFWM_F32 or FFWM_F64 (AT_DISPATCH_FLOATING_TYPES);
+ *   - the caller owns and allocates everything, the callee writes in place
+ *     and never allocates, frees or synchronises;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL is
+ *     the legacy default stream) of the CURRENT device;
+ *   - return 0 on success, FFWM_ERR_* (<0) for a rejected argument, or a
+ *     positive cudaError_t from the launch; ffwm_last_error() describes the
+ *     last failure of the calling thread.  (The reference returns 1 and
+ *     never checks; the Python shims translate 0 -> 1 / raise RuntimeError.)
+ *
+ * Output initialisation: the reference's callers zero-fill every output and
+ * gradient buffer and the reference kernels atomicAdd into them.  Here only
+ * the true scatter targets ACCUMULATE and therefore must be zero-filled by
+ * the caller, exactly as the reference requires:
+ *       grad_input1 (resample2d), grad_source (block_extractor),
+ *       grad_images (grid_warp).
+ * Every other output is OVERWRITTEN (each element is produced exactly once,
+ * deterministically), which is indistinguishable from accumulate-into-zero.
+ */
+#ifndef FFWM_B200_H_
+#define FFWM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFWM_ABI_VERSION 1
+
+enum { FFWM_F32 = 0, FFWM_F64 = 1 };
+
+enum {
+    FFWM_OK = 0,
+    FFWM_ERR_NULL = -1,      /* null tensor / data pointer with non-zero numel   */
+    FFWM_ERR_SHAPE = -2,     /* inconsistent sizes                               */
+    FFWM_ERR_ARG = -3,       /* bad kernel_size / dilation / dtype               */
+    FFWM_ERR_TOO_LARGE = -4  /* a single (H,W) plane spans more than 2^31 elems  */
+};
+
+typedef struct ffwm_tensor4 {
+    void* data;          /* device pointer */
+    int64_t size[4];     /* N, C, H, W */
+    int64_t stride[4];   /* in elements */
+} ffwm_tensor4;
+
+int ffwm_abi_version(void);
+const char* ffwm_last_error(void);
+
+/* resample2d_cuda.forward   (cuda/resample2d_package/resample2d_cuda.cc:6-15,
+ *                            resample2d_kernel.cu:20-95,335-375)
+ * input1 (B,C,Hi,Wi); input2 (B,3,H,W) = (dx, dy, sigma); output (B,C,H,W). */
+int ffwm_resample2d_forward(const ffwm_tensor4* input1, const ffwm_tensor4* input2,
+                            const ffwm_tensor4* output,
+                            int kernel_size, int dilation, int dtype, void* stream);
+
+/* resample2d_cuda.backward  (resample2d_cuda.cc:17-28, resample2d_kernel.cu:98-330,377-454)
+ * grad_input1 (B,C,Hi,Wi) accumulates (zero-fill it); grad_input2 (B,3,H,W) is overwritten.
+ * One fused pass over grad_output instead of the reference's two kernels.    */
+int ffwm_resample2d_backward(const ffwm_tensor4* input1, const ffwm_tensor4* input2,
+                             const ffwm_tensor4* grad_output,
+                             const ffwm_tensor4* grad_input1, const ffwm_tensor4* grad_input2,
+                             int kernel_size, int dilation, int dtype, void* stream);
+
+/* block_extractor_cuda.forward  (cuda/block_extractor/block_extractor_cuda.cc:5-12,
+ *                                block_extractor_kernel.cu:20-85,172-217)
+ * source (B,C,Hs,Ws); flow (B,2,Hf,Wf); output (B,C,k*Hf,k*Wf).              */
+int ffwm_block_extractor_forward(const ffwm_tensor4* source, const ffwm_tensor4* flow,
+                                 const ffwm_tensor4* output,
+                                 int kernel_size, int dtype, void* stream);
+
+/* block_extractor_cuda.backward (block_extractor_cuda.cc:14-27, block_extractor_kernel.cu:89-170,222-278)
+ * grad_source accumulates (zero-fill it); grad_flow is overwritten (no atomics).  */
+int ffwm_block_extractor_backward(const ffwm_tensor4* source, const ffwm_tensor4* flow,
+                                  const ffwm_tensor4* grad_output,
+                                  const ffwm_tensor4* grad_source, const ffwm_tensor4* grad_flow,
+                                  int kernel_size, int dtype, void* stream);
+
+/* local_attn_reshape_cuda.forward  (cuda/local_attn_reshape/local_attn_reshape_cuda.cc:5-11,
+ *                                   local_attn_reshape_kernel.cu:20-61,110-148)
+ * inputs (B,k*k,H,W) -> output (B,1,k*H,k*W).                                 */
+int ffwm_local_attn_reshape_forward(const ffwm_tensor4* inputs, const ffwm_tensor4* output,
+                                    int kernel_size, int dtype, void* stream);
+
+/* local_attn_reshape_cuda.backward (local_attn_reshape_cuda.cc:13-23, local_attn_reshape_kernel.cu:65-108,153-195)
+ * grad_output (B,Cg,k*H,k*W) -> grad_inputs (B,k*k,H,W), overwritten with the
+ * sum over Cg (Cg is 1 for every caller in the reference).                    */
+int ffwm_local_attn_reshape_backward(const ffwm_tensor4* grad_output, const ffwm_tensor4* grad_inputs,
+                                     int kernel_size, int dtype, void* stream);
+
+/* WarpNet.forward (models/base_networks.py:168-173) and
+ * PerceptualCorrectness.bilinear_warp (models/losses.py:392-396):
+ *   F.grid_sample(images, flow.permute(0,2,3,1)), bilinear, zeros padding,
+ *   align_corners=False.  flow stays in the network's (B,2,H,W) layout:
+ *   channel 0 = x, channel 1 = y, both in [-1,1]; no permuted copy is made.
+ * images (B,C,Hi,Wi); flow (B,2,H,W); output (B,C,H,W).                       */
+int ffwm_grid_warp_forward(const ffwm_tensor4* images, const ffwm_tensor4* flow,
+                           const ffwm_tensor4* output, int dtype, void* stream);
+
+/* grad_images accumulates (zero-fill it); grad_flow (B,2,H,W) is overwritten.
+ * grad_images->data or grad_flow->data may be NULL to skip that gradient.     */
+int ffwm_grid_warp_backward(const ffwm_tensor4* images, const ffwm_tensor4* flow,
+                            const ffwm_tensor4* grad_output,
+                            const ffwm_tensor4* grad_images, const ffwm_tensor4* grad_flow,
+                            int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFWM_B200_H_ */

@@ -1,0 +1,100 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU,
+exports every symbol include/ffwm_b200.h declares, the ctypes binding covers
+each of them, and argument validation fails cleanly (no kernel is launched)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "ffwm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ffwm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ffwm_b200 import _lib
+    lib = _lib.lib()
+    names = _header_functions()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), "libffwm_b200.so does not export %s" % n
+    assert sorted(_lib.SIGNATURES) == names, "ctypes binding and header disagree"
+    assert lib.ffwm_abi_version() == _lib.ABI_VERSION
+
+
+def test_header_cites_reference_interfaces():
+    text = open(os.path.join(ROOT, "include", "ffwm_b200.h")).read()
+    for cite in ("resample2d_cuda.cc", "block_extractor_cuda.cc", "local_attn_reshape_cuda.cc", "base_networks.py:168-173"):
+        assert cite in text
+
+
+def test_argument_validation_without_gpu():
+    from ffwm_b200 import _lib
+    lib = _lib.lib()
+    a = torch.zeros(1, 3, 4, 4)
+    flow3 = torch.zeros(1, 3, 4, 4)
+    out = torch.zeros(1, 3, 4, 4)
+    null = ctypes.c_void_p(0)
+    # wrong channel count on the flow
+    rc = lib.ffwm_block_extractor_forward(_lib.t4(a), _lib.t4(flow3), _lib.t4(out), 3, 0, null)
+    assert rc == -2 and b"2 channels" in lib.ffwm_last_error()
+    # bad dtype code
+    rc = lib.ffwm_resample2d_forward(_lib.t4(a), _lib.t4(flow3), _lib.t4(out), 2, 1, 7, null)
+    assert rc == -3
+    # negative kernel size
+    rc = lib.ffwm_resample2d_forward(_lib.t4(a), _lib.t4(flow3), _lib.t4(out), -2, 1, 0, null)
+    assert rc == -3
+    # k*k channel rule of local_attn_reshape (external_function.py:77)
+    rc = lib.ffwm_local_attn_reshape_forward(_lib.t4(a), _lib.t4(torch.zeros(1, 1, 12, 12)), 3, 0, null)
+    assert rc == -2
+    # null data pointer
+    d = _lib.t4(a)
+    d.data = None
+    rc = lib.ffwm_grid_warp_forward(d, _lib.t4(torch.zeros(1, 2, 4, 4)), _lib.t4(out), 0, null)
+    assert rc == -1
+    # empty tensors are a successful no-op (no launch)
+    e = torch.zeros(0, 3, 4, 4)
+    rc = lib.ffwm_grid_warp_forward(_lib.t4(e), _lib.t4(torch.zeros(0, 2, 4, 4)), _lib.t4(e), 0, null)
+    assert rc == 0
+
+
+def test_python_surface_mirrors_reference_errors():
+    from ffwm_b200 import external_function as E
+    with pytest.raises(NotImplementedError):                       # external_function.py:37-38
+        E.BlockExtractor(3)(torch.rand(1, 1, 8, 8), torch.zeros(1, 2, 6, 6))
+    with pytest.raises(NotImplementedError):                       # :84-85
+        E.LocalAttnReshape()(torch.rand(1, 9, 4, 4), 3)
+    with pytest.raises(AssertionError):                            # :77  ds == k*k
+        E.LocalAttnReshape()(torch.rand(1, 8, 4, 4), 3)
+    with pytest.raises(AssertionError):                            # :31  df == 2
+        E.BlockExtractor(3)(torch.rand(1, 1, 8, 8), torch.zeros(1, 3, 6, 6))
+    with pytest.raises(TypeError):
+        from ffwm_b200 import _lib
+        _lib.dtype_code(torch.zeros(1, dtype=torch.float16))
+
+
+def test_dropin_modules_expose_reference_surface():
+    import sys
+    import ffwm_b200
+    ffwm_b200.install_dropin()
+    for n in ("resample2d_cuda", "block_extractor_cuda", "local_attn_reshape_cuda"):
+        m = sys.modules[n]
+        assert callable(m.forward) and callable(m.backward)
+    import inspect
+    import resample2d_cuda
+    assert list(inspect.signature(resample2d_cuda.backward).parameters) == [
+        "input1", "input2", "gradOutput", "gradInput1", "gradInput2", "kernel_size", "dilation"]
+
+
+def test_guided_filter_box_sums():
+    from ffwm_b200.external_function import BoxFilter
+    x = torch.rand(2, 3, 40, 37, dtype=torch.float64)
+    r = 5
+    ref = torch.nn.functional.avg_pool2d(torch.nn.functional.pad(x, (r, r, r, r)), 2 * r + 1, 1, divisor_override=1)
+    assert torch.allclose(BoxFilter(r)(x), ref, atol=1e-9)
