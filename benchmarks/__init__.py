@@ -1,0 +1,17 @@
+"""Benchmark workloads for bench.py (measurement harness, not product code)."""
+
+
+def get_workload(name):
+    if name in ("default",):
+        name = DEFAULT
+    if name == "warp":
+        from .warp import WarpWorkload
+        return WarpWorkload
+    if name == "train_step":
+        from .train_step import TrainStepWorkload
+        return TrainStepWorkload
+    raise SystemExit("bench.py: unknown workload %r (warp, train_step)" % name)
+
+
+# The workload BASELINE.json's metric is quoted on.
+DEFAULT = "warp"

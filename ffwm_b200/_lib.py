@@ -41,6 +41,7 @@ SIGNATURES = {
 }
 
 _lib = None
+LAUNCHES = 0   # kernels enqueued through the C ABI by this process (each entry point launches exactly one)
 
 
 def lib():
@@ -104,7 +105,9 @@ def require_cuda(*tensors):
 
 def call(name, dev, *args):
     """Invoke one entry point on `dev`'s current stream and raise on failure."""
+    global LAUNCHES
     l = lib()
+    LAUNCHES += 1
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream().cuda_stream
         rc = getattr(l, name)(*args, ctypes.c_void_p(stream))
