@@ -6,10 +6,11 @@
 One JSON line on stdout (rank 0).  Workloads live in benchmarks/*.py; each is
 "one pass of the hot path over one batch of synthetic input":
 
+    train_step   FFWM train step (BASELINE config 3; batch 8/GPU, 128x128; config 4 under torchrun)
+                 [default].  At N=1 the flow-warp microbench below is attached as `warp_microbench`.
     warp         flow-warp microbench (BASELINE config 5): resample2d, block_extractor,
                  local_attn_reshape and the bilinear grid-warp, forward+backward, on feature
                  maps far larger than L2
-    train_step   FFWM train step (BASELINE config 3; batch 8/GPU, 128x128)   [default once built]
 
 `--impl reference` times the CPU restatement of the same path (oracle/) on the
 host cores — the only place besides tests/ and smoke() that executes oracle/.
@@ -98,6 +99,30 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def warp_microbench(local_rank, pk, steps=10, warmup=3):
+    """BASELINE's second metric (resample2d / block_extractor HBM GB/s): the `warp` workload's
+    device leg, attached to the train-step line at N=1."""
+    import torch
+    from benchmarks.warp import WarpWorkload
+    from ffwm_b200 import _lib
+    wl = WarpWorkload(device=torch.device("cuda", local_rank))
+    wl.setup()
+    for _ in range(warmup):
+        wl.step(timed=False)
+    torch.cuda.synchronize()
+    n0 = _lib.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        wl.step(timed=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"metric": wl.METRIC, "value": wl.units_per_step() / (ms * 1e-3), "unit": wl.UNIT, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms, "config": wl.config(), "gpu_launches": _lib.LAUNCHES - n0,
+            "roofline": wl.roofline(pk), "kernels": wl.kernel_table(pk)}
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -111,6 +136,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("FFWM_BENCH_WORKLOAD", "default"))
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--no-warp", action="store_true", help="train_step: skip the attached flow-warp microbench")
     args = ap.parse_args()
 
     from benchmarks import get_workload
@@ -199,8 +225,11 @@ def main():
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": wl.DTYPE, "data": "synthetic", "config": wl.config(),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "roofline": wl.roofline(pk), "kernels": wl.kernel_table(pk),
+            "roofline": (wl.step_roofline(pk, ms_per_step) if hasattr(wl, "step_roofline") else wl.roofline(pk)),
+            "kernels": wl.kernel_table(pk),
         }
+        if args.workload in ("default", "train_step") and world == 1 and not args.no_warp:
+            line["warp_microbench"] = warp_microbench(local_rank, pk)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = wl_cls.cpu_baseline()
         print(json.dumps(line), flush=True)

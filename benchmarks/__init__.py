@@ -14,4 +14,4 @@ def get_workload(name):
 
 
 # The workload BASELINE.json's metric is quoted on.
-DEFAULT = "warp"
+DEFAULT = "train_step"

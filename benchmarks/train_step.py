@@ -1,0 +1,145 @@
+"""FFWM train step (BASELINE config 3 on one GPU, config 4 under torchrun: batch 8 per GPU).
+
+One step = one `optimize_parameters()` of the full model — flowNetF + flowNetB + netG forward,
+guided filter, 8 facial-part crops, discriminator step, generator/flow step with VGG19 perceptual,
+L1, illumination, LightCNN identity, adversarial and facial-part losses, three Adam updates, and
+(N>1) the NCCL gradient all-reduce — on the SURVEY 8(d) cfg3 synthetic batch: 8 images of
+128x128 per rank, titers=30000 (steady-state branch), random-init weights of the reference
+architectures (no checkpoints or ImageNet weights are reachable offline).
+
+Algorithmic work: 461.5 GFLOP per image as executed (SURVEY 6 [probe], conv + matmul, forward +
+backward).  Convolutions run in strict fp32 (`cudnn.allow_tf32 = False`) unless
+FFWM_BENCH_TF32=1, because the parity target of the path is 1e-4 relative.
+"""
+import os
+import time
+
+import torch
+
+GFLOP_PER_IMAGE = 461.5
+BATCH = 8
+
+
+def make_batch(b, seed, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    batch = {
+        'img_S': torch.rand(b, 3, 128, 128, generator=g), 'img_F': torch.rand(b, 3, 128, 128, generator=g),
+        'mask_F': (torch.rand(b, 1, 128, 128, generator=g) > 0.3).float(),
+        'mask_S': (torch.rand(b, 1, 128, 128, generator=g) > 0.3).float(),
+        'lm_F': torch.randint(20, 108, (b, 1000, 2), generator=g),
+    }
+    if pin:
+        batch = {k: v.pin_memory() for k, v in batch.items()}
+    batch.update(titers=30000, epoch=0)
+    return batch
+
+
+class TrainStepWorkload:
+    METRIC = "FFWM train-step images/sec (128x128)"
+    UNIT = "images/s"
+    DTYPE = "f32"
+    STEPS, WARMUP = 20, 5
+    E2E_STEPS = 10
+    REF_STEPS, REF_WARMUP = 2, 1
+
+    def __init__(self, device, rank=0, world=1):
+        self.dev, self.rank, self.world = device, rank, world
+        self.tf32 = os.environ.get("FFWM_BENCH_TF32", "0") == "1"
+
+    def setup(self):
+        torch.backends.cudnn.allow_tf32 = self.tf32
+        torch.backends.cuda.matmul.allow_tf32 = self.tf32
+        torch.backends.cudnn.benchmark = True            # as the reference (models/base_model.py:38-39)
+        from ffwm_b200.train_step import FFWMTrainer
+        from ffwm_b200.parallel import Distributed
+        torch.manual_seed(0)                              # identical weights on every rank
+        dist = Distributed() if self.world > 1 else None
+        self.trainer = FFWMTrainer(self.dev, distributed=dist)
+        self.dev_batch = {k: (v.to(self.dev) if torch.is_tensor(v) else v)
+                          for k, v in make_batch(BATCH, 1000 + self.rank).items()}
+        self.host_batch = make_batch(BATCH, 2000 + self.rank, pin=True)
+        self.t_warp = 0.0
+
+    def step(self, timed):
+        self.trainer.set_input(self.dev_batch)
+        self.trainer.optimize_parameters()
+
+    def step_e2e(self):
+        """What a user of the reference does per iteration (train_ffwm.py:72-83): set_input from host
+        tensors (H2D inside), optimize_parameters, get_current_losses (8 float() reads, D2H)."""
+        self.trainer.set_input(self.host_batch)
+        self.trainer.optimize_parameters()
+        self.losses = self.trainer.get_current_losses()
+
+    def e2e_bytes(self):
+        h2d = sum(v.numel() * v.element_size() for v in self.host_batch.values() if torch.is_tensor(v))
+        return h2d, 8 * 4
+
+    def extra_launches(self):
+        return 0
+
+    def units_per_step(self):
+        return BATCH
+
+    def config(self):
+        return {"workload": "ffwm_model train step (BASELINE cfg3; cfg4 when n_gpus>1)", "batch_per_gpu": BATCH,
+                "global_batch": BATCH * self.world, "image": "128x128", "titers": 30000,
+                "nets": "netG(FFWM sn) + flowNetF + flowNetB + netD(MSDiscriminator) + LightCNN-29 + VGG19",
+                "parallelism": "dp%d (NCCL grad all-reduce, per-rank BN)" % self.world,
+                "conv_math": "tf32" if self.tf32 else "fp32 (cudnn.allow_tf32=False)",
+                "l2": "activations of one step (several GB) exceed L2; weights 488 MB", "weights": "random init"}
+
+    def roofline(self, pk):
+        return None      # filled by bench.py from the measured step time (see step_roofline)
+
+    def step_roofline(self, pk, ms_per_step):
+        tflops = GFLOP_PER_IMAGE * BATCH / 1e3 / (ms_per_step * 1e-3)
+        return {"kernel": "whole step (cuDNN implicit-GEMM convolutions dominate: ~99% of the FLOPs)", "bound": "tensor",
+                "achieved": tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": tflops / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"],
+                "note": "algorithmic 461.5 GFLOP/image (conv+matmul fwd+bwd as executed) / measured step time; "
+                        "peak is the measured sustained bf16 tensor rate, the math here is %s" % ("tf32" if self.tf32 else "fp32")}
+
+    def kernel_table(self, pk):
+        return None
+
+    # ------------------------------------------------------------------ CPU arm
+    CPU_BATCH = 2
+
+    @classmethod
+    def _cpu_time(cls, steps, warmup):
+        from oracle import train_cpu
+        from ffwm_b200.train_step import FFWMTrainer
+        torch.set_num_threads(os.cpu_count())
+        torch.manual_seed(0)
+        with train_cpu.cpu_ops():
+            tr = FFWMTrainer("cpu")
+            batch = make_batch(cls.CPU_BATCH, 3000)
+            for _ in range(warmup):
+                tr.set_input(batch)
+                tr.optimize_parameters()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                tr.set_input(batch)
+                tr.optimize_parameters()
+            dt = (time.perf_counter() - t0) / steps
+        sample = ("the same train step on the host CPU at batch %d, %d step(s): PyTorch CPU (oneDNN) convolutions and "
+                  "F.grid_sample warps, i.e. what the reference's own CPU path executes (oracle/train_cpu.py)"
+                  % (cls.CPU_BATCH, steps))
+        return cls.CPU_BATCH / dt, dt, sample
+
+    @classmethod
+    def cpu_baseline(cls):
+        v, dt, sample = cls._cpu_time(steps=2, warmup=1)
+        return {"value": v, "unit": cls.UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample, "s_per_step": dt}
+
+    @classmethod
+    def run_reference(cls, steps, warmup, n_gpus):
+        v, dt, sample = cls._cpu_time(steps=max(1, steps), warmup=warmup)
+        w = cls(device=None)
+        return {"impl": "reference", "metric": cls.METRIC, "value": v, "unit": cls.UNIT, "n_gpus": n_gpus,
+                "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": cls.DTYPE, "data": "synthetic",
+                "config": dict(w.config(), sample=sample, parallelism="cpu"),
+                "cpu_baseline": {"value": v, "unit": cls.UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+                "e2e": {"value": v, "unit": cls.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

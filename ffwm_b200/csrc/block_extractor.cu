@@ -79,6 +79,107 @@ block_extractor_fwd_kernel(View<const T> src, View<const T> flow, View<T> out, i
     }
 }
 
+// ---- forward, tiled: k is a template parameter -----------------------------------------
+// A warp owns 32 consecutive flow pixels of one flow row and walks a slice of channels.
+// The k*k samples of one flow pixel share a (k+1)x(k+1) source window (same fractional
+// part, integer offsets 0..k-1), so the window is loaded once into registers — (k+1)^2
+// gathers instead of 4*k*k — and every output row is interleaved through a private
+// shared-memory row so that the k*Wf-wide output rows leave as full 128-byte stores
+// (the output is k*k times larger than the source: this kernel is store-bound).
+// Geometry (weights, clamped indices) is formed per tap with the reference's expressions
+// (block_tap); the shared window is only used when the clamped tap indices really are
+// consecutive, otherwise that pixel gathers its four taps directly.
+constexpr int BE_WARPS = 8;
+
+template <typename T, int K>
+__global__ void __launch_bounds__(32 * BE_WARPS, 2)
+block_extractor_fwd_tiled_kernel(View<const T> src, View<const T> flow, View<T> out, int chunks, int c_per_block) {
+    __shared__ T stage[BE_WARPS][K * 32];
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    const int xf0 = blockIdx.x * 32, xf = xf0 + lane;
+    const int yf = blockIdx.y * BE_WARPS + warp;
+    const int b = blockIdx.z / chunks, chunk = blockIdx.z - b * chunks;
+    if (yf >= flow.h) return;                      // whole warp
+    const int nx = min(32, flow.w - xf0);
+    const bool live = lane < nx;
+    T* row = stage[warp];
+
+    // Separable tap geometry: column part depends on j only, row part on i only.
+    int cx[K + 1], cy[K + 1];       // element offsets of the shared window's columns / rows
+    T xLP[K], xRP[K], yTP[K], yBP[K];
+    bool shared_window = true;
+    T fx_raw = T(0), fy_raw = T(0);
+    if (live) {
+        const T* f = flow.p + b * flow.sb + yf * flow.sh + xf * flow.sw;
+        fx_raw = __ldg(f);
+        fy_raw = __ldg(f + flow.sc);
+        int prev_xR = 0, prev_yB = 0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const Bilin<T> t = block_tap<T>(fx_raw, fy_raw, xf, yf, j - K / 2, j - K / 2, src.h, src.w);
+            xLP[j] = t.xL_P; xRP[j] = t.xR_P; yTP[j] = t.yT_P; yBP[j] = t.yB_P;
+            cx[j] = t.xL * src.sw; cy[j] = t.yT * src.sh;
+            if (j > 0) shared_window = shared_window && prev_xR == t.xL && prev_yB == t.yT;
+            prev_xR = t.xR; prev_yB = t.yB;
+        }
+        cx[K] = prev_xR * src.sw;
+        cy[K] = prev_yB * src.sh;
+    }
+
+    const int c0 = chunk * c_per_block;
+    const int c1 = min(c0 + c_per_block, out.c);
+    const T* s = src.plane(b, c0);
+    T* obase = out.plane(b, c0) + (yf * K) * out.sh + (xf0 * K) * out.sw;
+    for (int c = c0; c < c1; ++c, s += src.sc, obase += out.sc) {
+        T top[K + 1];
+        if (live && shared_window) {
+#pragma unroll
+            for (int m = 0; m <= K; ++m) top[m] = __ldg(s + cy[0] + cx[m]);
+        }
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            if (live) {
+                if (shared_window) {
+                    T bot[K + 1];
+#pragma unroll
+                    for (int m = 0; m <= K; ++m) bot[m] = __ldg(s + cy[i + 1] + cx[m]);
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        T sample = T(0);
+                        sample += xLP[j] * yTP[i] * top[j];
+                        sample += xRP[j] * yTP[i] * top[j + 1];
+                        sample += xLP[j] * yBP[i] * bot[j];
+                        sample += xRP[j] * yBP[i] * bot[j + 1];
+                        row[lane * K + j] = sample;
+                    }
+#pragma unroll
+                    for (int m = 0; m <= K; ++m) top[m] = bot[m];
+                } else {
+                    // rare: the clamped taps of this pixel are not consecutive (float rounding at an
+                    // integer boundary); gather the four taps of every sample directly
+#pragma unroll 1
+                    for (int j = 0; j < K; ++j) {
+                        const Bilin<T> t = block_tap<T>(fx_raw, fy_raw, xf, yf, j - K / 2, i - K / 2, src.h, src.w);
+                        T sample = T(0);
+                        sample += t.xL_P * t.yT_P * __ldg(s + t.yT * src.sh + t.xL * src.sw);
+                        sample += t.xR_P * t.yT_P * __ldg(s + t.yT * src.sh + t.xR * src.sw);
+                        sample += t.xL_P * t.yB_P * __ldg(s + t.yB * src.sh + t.xL * src.sw);
+                        sample += t.xR_P * t.yB_P * __ldg(s + t.yB * src.sh + t.xR * src.sw);
+                        row[lane * K + j] = sample;
+                    }
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int m = 0; m < K; ++m) {
+                const int idx = m * 32 + lane;
+                if (idx < nx * K) st_stream(obase + i * out.sh + idx * out.sw, row[idx]);
+            }
+            __syncwarp();
+        }
+    }
+}
+
 template <typename T, int SL>
 __global__ void __launch_bounds__(256)
 block_extractor_bwd_kernel(View<const T> src, View<const T> flow, View<const T> gout,
@@ -175,6 +276,25 @@ static int block_extractor_forward_t(const ffwm_tensor4* a, const ffwm_tensor4* 
     if ((int64_t)out.n * out.c * out.h * out.w == 0) return FFWM_OK;
     if (out.n > 65535) { set_error("block_extractor: batch %d > 65535", out.n); return FFWM_ERR_TOO_LARGE; }
     if (src.h == 0 || src.w == 0) { set_error("block_extractor: empty source plane"); return FFWM_ERR_SHAPE; }
+    if constexpr (sizeof(T) == 4) if (k == 2 || k == 3) {
+        const int tx = ceil_div(flow.w, 32), ty = ceil_div(flow.h, BE_WARPS);
+        // ~8 CTAs per SM overall, at least 4 channels per CTA so the per-pixel geometry stays amortised
+        int64_t want = (int64_t)8 * sm_count();
+        int64_t tiles = (int64_t)tx * ty * out.n;
+        int chunks = int((want + tiles - 1) / tiles);
+        chunks = max(1, min(chunks, ceil_div(out.c, 4)));
+        chunks = min(chunks, max(1, 65535 / out.n));
+        const int c_per_block = ceil_div(out.c, chunks);
+        chunks = ceil_div(out.c, c_per_block);
+        if (ty <= 65535 && (int64_t)out.n * chunks <= 65535) {
+            dim3 grid(tx, ty, out.n * chunks), block(32, BE_WARPS);
+            switch (k) {
+                case 2: block_extractor_fwd_tiled_kernel<T, 2><<<grid, block, 0, st>>>(src, flow, out, chunks, c_per_block); break;
+                default: block_extractor_fwd_tiled_kernel<T, 3><<<grid, block, 0, st>>>(src, flow, out, chunks, c_per_block); break;
+            }
+            return check_launch("block_extractor_forward");
+        }
+    }
     const int pix_blocks = ceil_div((int64_t)out.h * out.w, 256);
     int64_t want = (int64_t)8 * sm_count();
     int chunks = int((want + (int64_t)pix_blocks * out.n - 1) / ((int64_t)pix_blocks * out.n));

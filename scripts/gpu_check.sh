@@ -1,18 +1,24 @@
 #!/bin/bash
-# One GPU-box pass: parity tests, smoke, bench, cfg5 sweep, ncu launch list + full capture.
-# Usage (from the repo root, under gpurun): bash scripts/gpu_check.sh [tag]
+# One GPU-box pass: parity tests, smoke, bench (train step + warp microbench), cfg5 sweep, ncu.
+# Usage (from the repo root, under gpurun): bash scripts/gpu_check.sh [tag] [skip-list]
 TAG=${1:-r01}
+SKIP=${2:-}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/nvsmi_$TAG.csv
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"
-tail -3 gpurun_out/pytest_gpu_$TAG.log
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"
+tail -15 gpurun_out/pytest_gpu_$TAG.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke_$TAG.log
-timeout 900 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"; cat gpurun_out/bench_$TAG.json; tail -5 gpurun_out/bench_$TAG.err
-timeout 300 python bench.py --impl reference > gpurun_out/bench_ref_$TAG.json 2>> gpurun_out/bench_$TAG.err; echo "bench ref rc=$?"
-timeout 1200 python -m benchmarks.sweep --out gpurun_out/sweep_$TAG.json > gpurun_out/sweep_$TAG.txt 2>&1; echo "sweep rc=$?"; cat gpurun_out/sweep_$TAG.txt
-KR='regex:resample2d|block_extractor|local_attn|grid_warp'
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$TAG.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launches_$TAG.log 2>&1; echo "ncu launches rc=$?"
+timeout 1200 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"; cat gpurun_out/bench_$TAG.json; tail -5 gpurun_out/bench_$TAG.err
+[[ $SKIP == *tf32* ]] || { FFWM_BENCH_TF32=1 timeout 600 python bench.py --no-cpu-baseline --no-warp > gpurun_out/bench_tf32_$TAG.json 2>> gpurun_out/bench_$TAG.err; echo "bench tf32 rc=$?"; cat gpurun_out/bench_tf32_$TAG.json; }
+[[ $SKIP == *warpbench* ]] || { timeout 600 python bench.py --workload warp > gpurun_out/bench_warp_$TAG.json 2>> gpurun_out/bench_$TAG.err; echo "bench warp rc=$?"; }
+[[ $SKIP == *sweep* ]] || { timeout 1200 python -m benchmarks.sweep --out gpurun_out/sweep_$TAG.json > gpurun_out/sweep_$TAG.txt 2>&1; echo "sweep rc=$?"; cat gpurun_out/sweep_$TAG.txt; }
+KR='regex:resample2d|block_extractor|lar_tiled|local_attn|grid_warp'
+[[ $SKIP == *ncu* ]] || {
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_warp_$TAG.csv \
+    python bench.py --workload warp --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launches_$TAG.log 2>&1; echo "ncu launches rc=$?"
 timeout 1500 ncu --set full --clock-control none --import-source on -k "$KR" -s 8 -c 8 -f -o gpurun_out/prof_$TAG \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
-ls -la gpurun_out
+    python bench.py --workload warp --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
+timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 40000 --csv --log-file gpurun_out/launches_train_$TAG.csv \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-warp > gpurun_out/ncu_launches_train_$TAG.log 2>&1; echo "ncu train launches rc=$?"
+}
+ls -la gpurun_out | tail -30
