@@ -182,11 +182,16 @@ def main():
     launches0 = _lib.LAUNCHES + wl.extra_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
+    ncu_range = os.environ.get("FFWM_BENCH_NCU_RANGE") == "1"     # `ncu --profile-from-start off`
+    if ncu_range:
+        torch.cuda.profiler.start()
     ev0.record()
     for _ in range(steps):
         wl.step(timed=True)
     ev1.record()
     barrier()
+    if ncu_range:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop()
     launches = _lib.LAUNCHES + wl.extra_launches() - launches0
     ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)

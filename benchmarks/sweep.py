@@ -16,7 +16,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from benchmarks.warp import alg_bytes  # noqa: E402
+from benchmarks.warp import alg_bytes, _identity_grid  # noqa: E402
 
 
 def load_ref():
@@ -79,7 +79,7 @@ def main():
         feat = torch.rand(B, c, r, r, device=dev) * 2 - 1
         gout = torch.randn(B, c, r, r, device=dev)
         out, g1 = torch.empty_like(feat), torch.empty_like(feat)
-        grid = torch.rand(B, 2, r, r, device=dev) * 2 - 1
+        grid = (_identity_grid(B, r).to(dev) + torch.randn(B, 2, r, r, device=dev) * (2 * 2.0 / r)).contiguous()
         gfl = torch.empty_like(grid)
         for ks in (2, 4):
             disp = torch.cat([torch.randn(B, 2, r, r, device=dev) * 2, torch.full((B, 1, r, r), 2.0, device=dev)], 1)

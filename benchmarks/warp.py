@@ -56,6 +56,12 @@ def alg_bytes(op, **s):
     raise KeyError(op)
 
 
+def _identity_grid(b, r):
+    lin = (torch.arange(r, dtype=torch.float32) * 2 + 1) / r - 1          # pixel centres, align_corners=False
+    gy, gx = torch.meshgrid(lin, lin, indexing="ij")
+    return torch.stack((gx, gy), 0).unsqueeze(0).expand(b, 2, r, r)
+
+
 def make_inputs(shapes, device, seed, pin=False):
     """Synthetic inputs of one step, seeded; `shapes` = dict(B, Bb, B2, C, R)."""
     g = torch.Generator(device="cpu").manual_seed(seed)
@@ -69,7 +75,8 @@ def make_inputs(shapes, device, seed, pin=False):
         "feat": rnd(B, c, r, r) * 2 - 1,
         "disp": torch.cat([rnd(B, 2, r, r, fn=torch.randn) * 2, torch.full((B, 1, r, r), 2.0)], 1),
         "gout": rnd(B, c, r, r, fn=torch.randn),
-        "grid": (rnd(B, 2, r, r) * 2 - 1),
+        # WarpNet's absolute sampling grid: identity + the same 2 px noise as resample2d
+        "grid": _identity_grid(B, r) + rnd(B, 2, r, r, fn=torch.randn) * (2 * 2.0 / r),
         "be_src": rnd(Bb, c, r, r),
         "be_flow": rnd(Bb, 2, r, r) * 1.8,
         "be_gout": rnd(Bb, c, K_BLOCK * r, K_BLOCK * r, fn=torch.randn),

@@ -130,7 +130,13 @@ block_extractor_fwd_tiled_kernel(View<const T> src, View<const T> flow, View<T> 
     const int c1 = min(c0 + c_per_block, out.c);
     const T* s = src.plane(b, c0);
     T* obase = out.plane(b, c0) + (yf * K) * out.sh + (xf0 * K) * out.sw;
+    constexpr int PF = 4;     // channels of look-ahead: first touch of a source row is a DRAM round trip
     for (int c = c0; c < c1; ++c, s += src.sc, obase += out.sc) {
+        if (live && c + PF < c1) {
+            const T* ps = s + (int64_t)PF * src.sc + cx[0];
+#pragma unroll
+            for (int n = 0; n <= K; ++n) asm volatile("prefetch.global.L1 [%0];" ::"l"(ps + cy[n]));
+        }
         T top[K + 1];
         if (live && shared_window) {
 #pragma unroll

@@ -17,6 +17,8 @@
 // shared memory and stored once (ATen does the same per-pixel reduction but
 // serially over all C in one thread).
 #include "common.cuh"
+#include "gather_tiled.cuh"
+#include "scatter_tiled.cuh"
 
 namespace ffwm {
 
@@ -56,6 +58,25 @@ __device__ __forceinline__ void corner_offsets(const Corner<T>& c, int sh, int s
     o[3] = c.v[3] ? y1 * sh + x1 * sw : 0;
 }
 
+// Tap list of one output pixel for the tiled scatter (scatter_tiled.cuh): the four bilinear
+// corners; corners outside the image are skipped (zeros padding).
+struct GridWarpScatterGeo {
+    static constexpr int NT = 4;
+    View<const float> flow;
+    int hi, wi;
+    __device__ __forceinline__ void taps(int b, int y, int x, int* iy, int* ix, float* w) const {
+        const float* f = flow.p + b * flow.sb + y * flow.sh + x * flow.sw;
+        const Corner<float> cr = corners<float>(__ldg(f), __ldg(f + flow.sc), hi, wi);
+        const int y0 = cr.o[0], x0 = cr.o[1], y1 = cr.o[2], x1 = cr.o[3];
+        iy[0] = cr.v[0] ? y0 : -1; ix[0] = x0;
+        iy[1] = cr.v[1] ? y0 : -1; ix[1] = x1;
+        iy[2] = cr.v[2] ? y1 : -1; ix[2] = x0;
+        iy[3] = cr.v[3] ? y1 : -1; ix[3] = x1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] = cr.w[k];
+    }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 grid_warp_fwd_kernel(View<const T> img, View<const T> flow, View<T> out, int c_per_block) {
@@ -84,6 +105,124 @@ grid_warp_fwd_kernel(View<const T> img, View<const T> flow, View<T> out, int c_p
         v += __ldg(s + o[3]) * w3;
         st_stream(d, v);
     }
+}
+
+// ---- tiled gathers (gather_tiled.cuh): lanes are channels, the image's halo region in a slab ----
+// MODE 0: forward.  MODE 1: flow gradient (grad_images comes from the tiled scatter).
+// Per-pixel parameters: 4 tap offsets (INT_MIN for a corner outside the image: zeros padding) and
+// either the 4 bilinear weights (forward) or the d/dix, d/diy coefficient of each corner (gradient).
+constexpr int GW_PW = 12;
+
+template <int MODE>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+grid_warp_tiled_kernel(View<const float> img, View<const float> flow, View<const float> gout, View<float> dst) {
+    extern __shared__ __align__(16) unsigned char gt_smem_raw[];
+    float* slab = reinterpret_cast<float*>(gt_smem_raw);               // [32][961]
+    float* prm = slab + 32 * GT_RPX;                                   // [256][12]
+    float* aux = prm + GT_NPX * GW_PW;                                 // fwd: staging [16][32][17]; grad: G [32][257]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx0 = blockIdx.x * GT_TW, ty0 = blockIdx.y * GT_TH, b = blockIdx.z;
+    const int rx0 = tx0 - 7, ry0 = ty0 - 7;
+    const int oh = MODE == 0 ? dst.h : gout.h, ow = MODE == 0 ? dst.w : gout.w;
+    const int nc = MODE == 0 ? dst.c : gout.c;
+
+    if (tid < GT_NPX) {
+        const int y = ty0 + tid / GT_TW, x = tx0 + tid % GT_TW;
+        if (y < oh && x < ow) {
+            const float* f = flow.p + b * flow.sb + y * flow.sh + x * flow.sw;
+            const Corner<float> cr = corners<float>(__ldg(f), __ldg(f + flow.sc), img.h, img.w);
+            const int y0 = cr.o[0], x0 = cr.o[1], y1 = cr.o[2], x1 = cr.o[3];
+            float* P = prm + tid * GW_PW;
+            int* Pi = reinterpret_cast<int*>(P);
+            Pi[0] = cr.v[0] ? gt_tap_offset(y0, x0, ry0, rx0, img.sh, img.sw) : INT_MIN;
+            Pi[1] = cr.v[1] ? gt_tap_offset(y0, x1, ry0, rx0, img.sh, img.sw) : INT_MIN;
+            Pi[2] = cr.v[2] ? gt_tap_offset(y1, x0, ry0, rx0, img.sh, img.sw) : INT_MIN;
+            Pi[3] = cr.v[3] ? gt_tap_offset(y1, x1, ry0, rx0, img.sh, img.sw) : INT_MIN;
+            if (MODE == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) P[4 + k] = cr.v[k] ? cr.w[k] : 0.f;
+            } else {
+                P[4] = -cr.wy1; P[5] = cr.wy1; P[6] = -cr.wy0; P[7] = cr.wy0;      // d out / d ix per corner
+                P[8] = -cr.wx1; P[9] = -cr.wx0; P[10] = cr.wx1; P[11] = cr.wx0;    // d out / d iy per corner
+            }
+        }
+    }
+    float gix[GT_TW], giy[GT_TW];
+#pragma unroll
+    for (int px = 0; px < GT_TW; ++px) gix[px] = giy[px] = 0.f;
+    const int y = ty0 + warp;
+    for (int c0 = 0; c0 < nc; c0 += 32) {
+        const int nch = min(32, nc - c0);
+        __syncthreads();
+        gt_fill_slab(slab, img, b, c0, nch, ry0, rx0, warp, lane);
+        if (MODE == 1) gt_fill_tile(aux, gout, b, c0, nch, ty0, tx0, tid);
+        __syncthreads();
+        if (y < oh) {
+            const float* slab_lane = slab + lane * GT_RPX;
+            const float* plane_lane = img.p + b * img.sb + (int64_t)(c0 + min(lane, nch - 1)) * img.sc;
+            float* stage = aux + warp * (32 * GT_SPITCH);
+            const float* G_lane = aux + lane * GT_GPITCH + warp * GT_TW;
+#pragma unroll
+            for (int px = 0; px < GT_TW; ++px) {
+                if (tx0 + px < ow) {
+                    const float4* P4 = reinterpret_cast<const float4*>(prm + (warp * GT_TW + px) * GW_PW);
+                    const float4 o4 = P4[0], w4 = P4[1];
+                    const int off[4] = {__float_as_int(o4.x), __float_as_int(o4.y), __float_as_int(o4.z), __float_as_int(o4.w)};
+                    float v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[k] = off[k] == INT_MIN ? 0.f : gt_load(slab_lane, plane_lane, off[k]);
+                    if (MODE == 0) {
+                        float r = 0.f;
+                        r += v[0] * w4.x;
+                        r += v[1] * w4.y;
+                        r += v[2] * w4.z;
+                        r += v[3] * w4.w;
+                        stage[lane * GT_SPITCH + px] = r;
+                    } else {
+                        const float4 y4 = P4[2];
+                        const float g = lane < nch ? G_lane[px] : 0.f;
+                        gix[px] += v[0] * w4.x * g; giy[px] += v[0] * y4.x * g;
+                        gix[px] += v[1] * w4.y * g; giy[px] += v[1] * y4.y * g;
+                        gix[px] += v[2] * w4.z * g; giy[px] += v[2] * y4.z * g;
+                        gix[px] += v[3] * w4.w * g; giy[px] += v[3] * y4.w * g;
+                    }
+                }
+            }
+            if (MODE == 0) {
+                __syncwarp();
+                gt_store_row(stage, dst, b, c0, nch, y, tx0, lane);
+                __syncwarp();
+            }
+        }
+    }
+    if (MODE == 0 || y >= oh) return;
+    float sx = 0.f, sy = 0.f;
+#pragma unroll
+    for (int px = 0; px < GT_TW; ++px) {
+        float v0 = gix[px], v1 = giy[px];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, d);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, d);
+        }
+        if (lane == px) { sx = v0; sy = v1; }
+    }
+    const int x = tx0 + lane;
+    if (lane >= GT_TW || x >= ow) return;
+    float* o = dst.p + b * dst.sb + y * dst.sh + x * dst.sw;
+    o[0] = (float(img.w) / 2) * sx;
+    o[dst.sc] = (float(img.h) / 2) * sy;
+}
+
+template <int MODE>
+static int launch_grid_warp_tiled(const View<const float>& img, const View<const float>& flow,
+                                  const View<const float>& gout, const View<float>& dst, int n, int h, int w, cudaStream_t st) {
+    const size_t smem = sizeof(float) * (32 * GT_RPX + GT_NPX * GW_PW + (MODE == 0 ? GT_WARPS * 32 * GT_SPITCH : 32 * GT_GPITCH));
+    cudaError_t e = cudaFuncSetAttribute(grid_warp_tiled_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("grid_warp_tiled: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
+    dim3 grid(ceil_div(w, GT_TW), ceil_div(h, GT_TH), n);
+    grid_warp_tiled_kernel<MODE><<<grid, GT_THREADS, smem, st>>>(img, flow, gout, dst);
+    return FFWM_OK;
 }
 
 template <typename T, int SL>
@@ -176,6 +315,14 @@ static int grid_warp_forward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, con
     }
     if ((int64_t)out.n * out.c * out.h * out.w == 0) return FFWM_OK;
     if (out.n > 65535) { set_error("grid_warp: batch %d > 65535", out.n); return FFWM_ERR_TOO_LARGE; }
+    if constexpr (sizeof(T) == 4) {
+        if (img.h == out.h && img.w == out.w && (int64_t)(img.h - 1) * img.sh + (int64_t)(img.w - 1) * img.sw < (1 << 30) &&
+            gather_tiled_applicable(out.n, out.c, out.h, out.w, img)) {
+            const int rc2 = launch_grid_warp_tiled<0>(img, flow, View<const float>{}, out, out.n, out.h, out.w, st);
+            if (rc2) return rc2;
+            return check_launch("grid_warp_forward(tiled)");
+        }
+    }
     const int pix_blocks = ceil_div((int64_t)out.h * out.w, 256);
     int64_t want = (int64_t)8 * sm_count();
     int chunks = int((want + (int64_t)pix_blocks * out.n - 1) / ((int64_t)pix_blocks * out.n));
@@ -211,6 +358,24 @@ static int grid_warp_backward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, co
     }
     if ((!gi.p && !gf.p) || (int64_t)gout.n * gout.h * gout.w == 0) return FFWM_OK;
     if (gout.n > 65535) { set_error("grid_warp: batch %d > 65535", gout.n); return FFWM_ERR_TOO_LARGE; }
+    if constexpr (sizeof(T) == 4) {
+        // grad_images through the tiled scatter when the maps are large and of equal size (a flow
+        // that is a perturbed identity then lands inside the tile's halo)
+        if (gi.p && img.h == gout.h && img.w == gout.w && scatter_tiled_applicable(gout, gi)) {
+            int rc2 = launch_scatter_tiled(GridWarpScatterGeo{flow, img.h, img.w}, gout, gi, 7, st);
+            if (rc2) return rc2;
+            if ((rc2 = check_launch("grid_warp_backward(tiled scatter)"))) return rc2;
+            if (!gf.p) return FFWM_OK;
+            gi.p = nullptr;
+        }
+        if (!gi.p && gf.p && img.h == gout.h && img.w == gout.w && !getenv("FFWM_DISABLE_TILED_GFLOW") &&
+            (int64_t)(img.h - 1) * img.sh + (int64_t)(img.w - 1) * img.sw < (1 << 30) &&
+            gather_tiled_applicable(gout.n, gout.c, gout.h, gout.w, img)) {
+            const int rc2 = launch_grid_warp_tiled<1>(img, flow, gout, gf, gout.n, gout.h, gout.w, st);
+            if (rc2) return rc2;
+            return check_launch("grid_warp_backward(tiled flow gradient)");
+        }
+    }
     const int c = gout.c;
     if (c >= 8) launch_bwd_sl<T, 8>(img, flow, gout, gi, gf, st);
     else if (c >= 4) launch_bwd_sl<T, 4>(img, flow, gout, gi, gf, st);

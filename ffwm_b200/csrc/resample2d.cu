@@ -16,6 +16,8 @@
 //     through shared memory, and stored once — no atomics, deterministic,
 //     and all three components (dx,dy,sigma) come out of the same pass.
 #include "common.cuh"
+#include "gather_tiled.cuh"
+#include "scatter_tiled.cuh"
 
 namespace ffwm {
 
@@ -64,6 +66,42 @@ __device__ __forceinline__ T tap_weights(const T* dxs, const T* dys, T sigma, T*
     return sum;
 }
 
+// Tap list of one pixel for the tiled scatter (scatter_tiled.cuh): destinations are the clamped
+// tap indices, weights are K2's SAFE_DIV(w, sum) with the truncation quirk of SURVEY N2 —
+// exactly the values the direct kernel below REDs.
+template <int HALF>
+struct Resample2dScatterGeo {
+    static constexpr int NT = 4 * HALF * HALF;
+    View<const float> in2;
+    int dil, ih, iw;
+    __device__ __forceinline__ void taps(int b, int y, int x, int* iy, int* ix, float* w) const {
+        constexpr int N2 = 2 * HALF;
+        const float* f = in2.p + b * in2.sb + y * in2.sh + x * in2.sw;
+        const float dx = f[0], dy = f[in2.sc], sigma = f[2 * in2.sc];
+        const float xf = float(x) + dx, yf = float(y) + dy;
+        Taps<float, HALF> t;
+        tap_geometry<float, HALF>(xf, yf, xf - floorf(xf), yf - floorf(yf), dil, ih, iw, t);
+        const float alpha2 = xf - float(f2i(xf)), beta2 = yf - float(f2i(yf));
+        float d2x[N2], d2y[N2], qx[N2], qy[N2];
+#pragma unroll
+        for (int k = 0; k < HALF; ++k) {
+            d2x[2 * k] = float(k * dil) + alpha2;
+            d2x[2 * k + 1] = float((1. + k) * dil) - alpha2;
+            d2y[2 * k] = float(k * dil) + beta2;
+            d2y[2 * k + 1] = float((1. + k) * dil) - beta2;
+        }
+        const float sum2 = tap_weights<float, HALF>(d2x, d2y, sigma, qx, qy);
+#pragma unroll
+        for (int i = 0; i < N2; ++i)
+#pragma unroll
+            for (int j = 0; j < N2; ++j) {
+                iy[i * N2 + j] = t.iy[i];
+                ix[i * N2 + j] = t.ix[j];
+                w[i * N2 + j] = float(safe_div<float>(qy[i] * qx[j], sum2));
+            }
+    }
+};
+
 // ---------------------------------------------------------------- forward
 template <typename T, int HALF>
 __global__ void __launch_bounds__(256)
@@ -107,6 +145,111 @@ resample2d_fwd_kernel(View<const T> in1, View<const T> in2, View<T> out, int dil
     }
 }
 
+// ---------------------------------------------------------------- forward, tiled
+// gather_tiled.cuh explains the plan: lanes are channels, taps come from a shared-memory slab.
+// Per-pixel parameters (formed once per tile, read by broadcast): NT tap offsets, the 2*HALF
+// column and row weights, the normaliser.  The arithmetic is the direct kernel's, term by term.
+template <int HALF>
+struct RsFwdParams {
+    static constexpr int N2 = 2 * HALF, NT = N2 * N2;
+    static constexpr int PW = ((NT + 2 * N2 + 1 + 3) / 4) * 4;     // words per pixel, 16-byte rows
+};
+
+template <int HALF>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+resample2d_fwd_tiled_kernel(View<const float> in1, View<const float> in2, View<float> out, int dil, int ml) {
+    using PP = RsFwdParams<HALF>;
+    constexpr int N2 = PP::N2, NT = PP::NT, PW = PP::PW;
+    extern __shared__ __align__(16) unsigned char gt_smem_raw[];
+    float* slab = reinterpret_cast<float*>(gt_smem_raw);               // [32][961]
+    float* prm = slab + 32 * GT_RPX;                                   // [256][PW]
+    float* stage_all = prm + GT_NPX * PW;                              // [16 warps][32][17]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx0 = blockIdx.x * GT_TW, ty0 = blockIdx.y * GT_TH, b = blockIdx.z;
+    const int rx0 = tx0 - ml, ry0 = ty0 - ml;
+
+    if (tid < GT_NPX) {
+        const int y = ty0 + tid / GT_TW, x = tx0 + tid % GT_TW;
+        if (y < out.h && x < out.w) {
+            const float* f = in2.p + b * in2.sb + y * in2.sh + x * in2.sw;
+            const float dx = ld_stream(f), dy = ld_stream(f + in2.sc), sigma = ld_stream(f + 2 * in2.sc);
+            const float xf = float(x) + dx, yf = float(y) + dy;
+            Taps<float, HALF> t;
+            tap_geometry<float, HALF>(xf, yf, xf - floorf(xf), yf - floorf(yf), dil, in1.h, in1.w, t);
+            float wx[N2], wy[N2];
+            const float sum = tap_weights<float, HALF>(t.dxs, t.dys, sigma, wx, wy);
+            float* P = prm + tid * PW;
+            int* Pi = reinterpret_cast<int*>(P);
+#pragma unroll
+            for (int i = 0; i < N2; ++i)
+#pragma unroll
+                for (int j = 0; j < N2; ++j) Pi[i * N2 + j] = gt_tap_offset(t.iy[i], t.ix[j], ry0, rx0, in1.sh, in1.sw);
+#pragma unroll
+            for (int i = 0; i < N2; ++i) { P[NT + i] = wx[i]; P[NT + N2 + i] = wy[i]; }
+            P[NT + 2 * N2] = sum;
+        }
+    }
+    float* stage = stage_all + warp * (32 * GT_SPITCH);
+    const int y = ty0 + warp;                        // this warp's tile row
+    for (int c0 = 0; c0 < out.c; c0 += 32) {
+        const int nch = min(32, out.c - c0);
+        __syncthreads();                             // parameters written / previous group's slab consumed
+        gt_fill_slab(slab, in1, b, c0, nch, ry0, rx0, warp, lane);
+        __syncthreads();
+        if (y < out.h) {
+            const float* slab_lane = slab + lane * GT_RPX;
+            const float* plane_lane = in1.p + b * in1.sb + (int64_t)(c0 + min(lane, nch - 1)) * in1.sc;
+#pragma unroll 2
+            for (int px = 0; px < GT_TW; ++px) {
+                if (tx0 + px >= out.w) break;        // warp-uniform
+                const float4* P4 = reinterpret_cast<const float4*>(prm + (warp * GT_TW + px) * PW);
+                int off[NT];
+                float w[2 * N2 + 4];
+#pragma unroll
+                for (int q = 0; q < NT / 4; ++q) {
+                    const float4 v = P4[q];
+                    off[4 * q] = __float_as_int(v.x); off[4 * q + 1] = __float_as_int(v.y);
+                    off[4 * q + 2] = __float_as_int(v.z); off[4 * q + 3] = __float_as_int(v.w);
+                }
+#pragma unroll
+                for (int q = 0; q < (2 * N2 + 1 + 3) / 4; ++q) {
+                    const float4 v = P4[NT / 4 + q];
+                    w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+                }
+                const float* wx = w;
+                const float* wy = w + N2;
+                const float sum = w[2 * N2];
+                float val = 0.f;
+#pragma unroll
+                for (int fy = 0; fy < HALF; ++fy)
+#pragma unroll
+                    for (int fx = 0; fx < HALF; ++fx) {
+                        val += wy[2 * fy] * wx[2 * fx] * gt_load(slab_lane, plane_lane, off[(2 * fy) * N2 + 2 * fx]);
+                        val += wy[2 * fy] * wx[2 * fx + 1] * gt_load(slab_lane, plane_lane, off[(2 * fy) * N2 + 2 * fx + 1]);
+                        val += wy[2 * fy + 1] * wx[2 * fx] * gt_load(slab_lane, plane_lane, off[(2 * fy + 1) * N2 + 2 * fx]);
+                        val += wy[2 * fy + 1] * wx[2 * fx + 1] * gt_load(slab_lane, plane_lane, off[(2 * fy + 1) * N2 + 2 * fx + 1]);
+                    }
+                stage[lane * GT_SPITCH + px] = float(safe_div<float>(val, sum));
+            }
+            __syncwarp();
+            gt_store_row(stage, out, b, c0, nch, y, tx0, lane);
+            __syncwarp();
+        }
+    }
+}
+
+template <int HALF>
+static int launch_fwd_tiled(const View<const float>& in1, const View<const float>& in2, const View<float>& out,
+                            int dil, int ml, cudaStream_t st) {
+    using PP = RsFwdParams<HALF>;
+    const size_t smem = sizeof(float) * (32 * GT_RPX + GT_NPX * PP::PW + GT_WARPS * 32 * GT_SPITCH);
+    cudaError_t e = cudaFuncSetAttribute(resample2d_fwd_tiled_kernel<HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("resample2d_fwd_tiled: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
+    dim3 grid(ceil_div(out.w, GT_TW), ceil_div(out.h, GT_TH), out.n);
+    resample2d_fwd_tiled_kernel<HALF><<<grid, GT_THREADS, smem, st>>>(in1, in2, out, dil, ml);
+    return FFWM_OK;
+}
+
 // Any kernel_size (runtime ks/2), no per-pixel arrays: weights are recomputed
 // per tap.  Only reached for kernel_size > 8; kept so that every argument the
 // reference accepts is served by the device path.
@@ -143,6 +286,166 @@ resample2d_fwd_generic_kernel(View<const T> in1, View<const T> in2, View<T> out,
         }
         out.plane(b, c)[y * out.sh + x * out.sw] = T(safe_div<T>(val, sum));
     }
+}
+
+// --------------------------------------------------------------- flow gradient, tiled
+// K3 as a tiled gather (gather_tiled.cuh): lanes are channels, input1's halo region sits in a
+// shared-memory slab, grad_output's tile beside it.  Each lane accumulates the four partial sums
+// of the direct kernel (A0, A1, A2, Bs) for the 16 pixels of its warp's tile row over all channel
+// groups; one butterfly reduction over the lanes at the end gives the channel sums, and lanes
+// 0..15 finish one pixel each.  grad_input1 is produced separately by the tiled scatter.
+template <int HALF>
+struct RsGradParams {
+    static constexpr int N2 = 2 * HALF, NT = N2 * N2;
+    static constexpr int PW = ((NT + 6 * N2 + 2 + 3) / 4) * 4;   // offsets, wx wy ax ay bx by, sum, sigma
+};
+
+template <int HALF>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+resample2d_gflow_tiled_kernel(View<const float> in1, View<const float> in2, View<const float> gout,
+                              View<float> gin2, int dil, int ml) {
+    using PP = RsGradParams<HALF>;
+    constexpr int N2 = PP::N2, NT = PP::NT, PW = PP::PW;
+    extern __shared__ __align__(16) unsigned char gt_smem_raw[];
+    float* slab = reinterpret_cast<float*>(gt_smem_raw);               // [32][961]
+    float* G = slab + 32 * GT_RPX;                                     // [32][257]
+    float* prm = G + 32 * GT_GPITCH;                                   // [256][PW]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx0 = blockIdx.x * GT_TW, ty0 = blockIdx.y * GT_TH, b = blockIdx.z;
+    const int rx0 = tx0 - ml, ry0 = ty0 - ml;
+
+    if (tid < GT_NPX) {
+        const int y = ty0 + tid / GT_TW, x = tx0 + tid % GT_TW;
+        if (y < gout.h && x < gout.w) {
+            const float* f = in2.p + b * in2.sb + y * in2.sh + x * in2.sw;
+            const float dx = f[0], dy = f[in2.sc], sigma = f[2 * in2.sc];
+            const float xf = float(x) + dx, yf = float(y) + dy;
+            Taps<float, HALF> t;
+            tap_geometry<float, HALF>(xf, yf, xf - floorf(xf), yf - floorf(yf), dil, in1.h, in1.w, t);
+            float wx[N2], wy[N2];
+            const float sum = tap_weights<float, HALF>(t.dxs, t.dys, sigma, wx, wy);
+            float* P = prm + tid * PW;
+            int* Pi = reinterpret_cast<int*>(P);
+#pragma unroll
+            for (int i = 0; i < N2; ++i)
+#pragma unroll
+                for (int j = 0; j < N2; ++j) Pi[i * N2 + j] = gt_tap_offset(t.iy[i], t.ix[j], ry0, rx0, in1.sh, in1.sw);
+#pragma unroll
+            for (int i = 0; i < N2; ++i) {
+                const float sgn = (i & 1) ? -1.f : 1.f;            // +xL_, -xR_ / +yT_, -yB_
+                P[NT + i] = wx[i];
+                P[NT + N2 + i] = wy[i];
+                P[NT + 2 * N2 + i] = sgn * t.dxs[i] * wx[i];
+                P[NT + 3 * N2 + i] = sgn * t.dys[i] * wy[i];
+                P[NT + 4 * N2 + i] = t.dxs[i] * t.dxs[i] * wx[i];
+                P[NT + 5 * N2 + i] = t.dys[i] * t.dys[i] * wy[i];
+            }
+            P[NT + 6 * N2] = sum;
+            P[NT + 6 * N2 + 1] = sigma;
+        }
+    }
+    float A0[GT_TW], A1[GT_TW], A2[GT_TW], Bs[GT_TW];
+#pragma unroll
+    for (int px = 0; px < GT_TW; ++px) A0[px] = A1[px] = A2[px] = Bs[px] = 0.f;
+    const int y = ty0 + warp;
+    for (int c0 = 0; c0 < gout.c; c0 += 32) {
+        const int nch = min(32, gout.c - c0);
+        __syncthreads();
+        gt_fill_slab(slab, in1, b, c0, nch, ry0, rx0, warp, lane);
+        gt_fill_tile(G, gout, b, c0, nch, ty0, tx0, tid);
+        __syncthreads();
+        if (y < gout.h && lane < nch) {
+            const float* slab_lane = slab + lane * GT_RPX;
+            const float* plane_lane = in1.p + b * in1.sb + (int64_t)(c0 + lane) * in1.sc;
+            const float* G_lane = G + lane * GT_GPITCH + warp * GT_TW;
+#pragma unroll
+            for (int px = 0; px < GT_TW; ++px) {
+                if (tx0 + px < gout.w) {
+                    const float4* P4 = reinterpret_cast<const float4*>(prm + (warp * GT_TW + px) * PW);
+                    int off[NT];
+                    float w[6 * N2];
+#pragma unroll
+                    for (int q = 0; q < NT / 4; ++q) {
+                        const float4 v = P4[q];
+                        off[4 * q] = __float_as_int(v.x); off[4 * q + 1] = __float_as_int(v.y);
+                        off[4 * q + 2] = __float_as_int(v.z); off[4 * q + 3] = __float_as_int(v.w);
+                    }
+#pragma unroll
+                    for (int q = 0; q < (6 * N2) / 4; ++q) {
+                        const float4 v = P4[NT / 4 + q];
+                        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+                    }
+                    const float *wx = w, *wy = w + N2, *ax = w + 2 * N2, *ay = w + 3 * N2, *bx = w + 4 * N2, *by = w + 5 * N2;
+                    const float g = G_lane[px];
+#pragma unroll
+                    for (int i = 0; i < N2; ++i) {
+                        float r0 = 0.f, rB = 0.f, r2 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < N2; ++j) {
+                            const float s = g * gt_load(slab_lane, plane_lane, off[i * N2 + j]);
+                            r0 += ax[j] * s;
+                            rB += wx[j] * s;
+                            r2 += bx[j] * s;
+                        }
+                        A0[px] += wy[i] * r0;
+                        A1[px] += ay[i] * rB;
+                        A2[px] += by[i] * rB + wy[i] * r2;
+                        Bs[px] += wy[i] * rB;
+                    }
+                }
+            }
+        }
+    }
+    if (y >= gout.h) return;                          // whole warp; no barrier follows
+    // channel sums: butterfly over the 32 lanes, then lane px keeps pixel px
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, bs = 0.f;
+#pragma unroll
+    for (int px = 0; px < GT_TW; ++px) {
+        float v0 = A0[px], v1 = A1[px], v2 = A2[px], v3 = Bs[px];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, d);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, d);
+            v2 += __shfl_xor_sync(0xffffffffu, v2, d);
+            v3 += __shfl_xor_sync(0xffffffffu, v3, d);
+        }
+        if (lane == px) { a0 = v0; a1 = v1; a2 = v2; bs = v3; }
+    }
+    const int x = tx0 + lane;
+    if (lane >= GT_TW || x >= gout.w) return;
+    const float* P = prm + (warp * GT_TW + lane) * PW;
+    float Wx = 0.f, Wy = 0.f, AX = 0.f, AY = 0.f, BX = 0.f, BY = 0.f;
+#pragma unroll
+    for (int i = 0; i < N2; ++i) {
+        Wx += P[NT + i]; Wy += P[NT + N2 + i];
+        AX += P[NT + 2 * N2 + i]; AY += P[NT + 3 * N2 + i];
+        BX += P[NT + 4 * N2 + i]; BY += P[NT + 5 * N2 + i];
+    }
+    const float sum = P[NT + 6 * N2], sigma = P[NT + 6 * N2 + 1];
+    const float ms2 = -sigma * sigma, s3 = sigma * sigma * sigma;
+    const float G0 = float(safe_div<float>(Wy * AX, ms2));
+    const float G1 = float(safe_div<float>(AY * Wx, ms2));
+    const float G2 = float(safe_div<float>(BY * Wx + Wy * BX, s3));
+    const float g10 = float(safe_div<float>(a0, ms2));
+    const float g11 = float(safe_div<float>(a1, ms2));
+    const float g12 = float(safe_div<float>(a2, s3));
+    const float ss = sum * sum;
+    float* o = gin2.p + b * gin2.sb + y * gin2.sh + x * gin2.sw;
+    o[0] = float(safe_div<float>(g10, sum) - safe_div<float>(G0 * bs, ss));
+    if (gin2.c > 1) o[gin2.sc] = float(safe_div<float>(g11, sum) - safe_div<float>(G1 * bs, ss));
+    if (gin2.c > 2) o[2 * gin2.sc] = float(safe_div<float>(g12, sum) - safe_div<float>(G2 * bs, ss));
+}
+
+template <int HALF>
+static int launch_gflow_tiled(const View<const float>& in1, const View<const float>& in2, const View<const float>& gout,
+                              const View<float>& g2, int dil, int ml, cudaStream_t st) {
+    using PP = RsGradParams<HALF>;
+    const size_t smem = sizeof(float) * (32 * GT_RPX + 32 * GT_GPITCH + GT_NPX * PP::PW);
+    cudaError_t e = cudaFuncSetAttribute(resample2d_gflow_tiled_kernel<HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("resample2d_gflow_tiled: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
+    dim3 grid(ceil_div(gout.w, GT_TW), ceil_div(gout.h, GT_TH), gout.n);
+    resample2d_gflow_tiled_kernel<HALF><<<grid, GT_THREADS, smem, st>>>(in1, in2, gout, g2, dil, ml);
+    return FFWM_OK;
 }
 
 // --------------------------------------------------------------- backward
@@ -421,6 +724,17 @@ static int resample2d_forward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, co
     if (out.n > 65535) { set_error("resample2d: batch %d > 65535", out.n); return FFWM_ERR_TOO_LARGE; }
     if (in1.h == 0 || in1.w == 0) { set_error("resample2d: empty input1 plane"); return FFWM_ERR_SHAPE; }
     const int half = ks / 2;
+    if constexpr (sizeof(T) == 4) {
+        const int hmax = (15 - (2 * half - 1) * dil) / 2;
+        if ((half == 1 || half == 2) && dil >= 1 && hmax >= 2 && in1.n >= out.n &&
+            (int64_t)(in1.h - 1) * in1.sh + (int64_t)(in1.w - 1) * in1.sw < (1 << 30) &&
+            gather_tiled_applicable(out.n, out.c, out.h, out.w, in1)) {
+            const int ml = hmax + (half - 1) * dil;
+            const int rc2 = half == 1 ? launch_fwd_tiled<1>(in1, in2, out, dil, ml, st) : launch_fwd_tiled<2>(in1, in2, out, dil, ml, st);
+            if (rc2) return rc2;
+            return check_launch("resample2d_forward(tiled)");
+        }
+    }
     switch (half) {
         case 1: launch_fwd<T, 1>(in1, in2, out, dil, st); break;
         case 2: launch_fwd<T, 2>(in1, in2, out, dil, st); break;
@@ -462,6 +776,31 @@ static int resample2d_backward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, c
     if (gout.n > 65535) { set_error("resample2d: batch %d > 65535", gout.n); return FFWM_ERR_TOO_LARGE; }
     if (in1.h == 0 || in1.w == 0) { set_error("resample2d: empty input1 plane"); return FFWM_ERR_SHAPE; }
     const int half = ks / 2;
+    if constexpr (sizeof(T) == 4) {
+        // grad_input1 through the tiled scatter when the problem is large enough; the fused kernel
+        // below then only produces the flow gradient
+        const int hmax = (15 - (2 * half - 1) * dil) / 2;
+        if (g1.p && (half == 1 || half == 2) && dil >= 1 && hmax >= 2 && scatter_tiled_applicable(gout, g1)) {
+            const int ml = hmax + (half - 1) * dil;
+            int rc2;
+            if (half == 1) rc2 = launch_scatter_tiled(Resample2dScatterGeo<1>{in2, dil, in1.h, in1.w}, gout, g1, ml, st);
+            else rc2 = launch_scatter_tiled(Resample2dScatterGeo<2>{in2, dil, in1.h, in1.w}, gout, g1, ml, st);
+            if (rc2) return rc2;
+            if ((rc2 = check_launch("resample2d_backward(tiled scatter)"))) return rc2;
+            if (!g2.p) return FFWM_OK;
+            g1.p = nullptr;
+        }
+        // flow gradient through the tiled gather
+        if (!g1.p && g2.p && (half == 1 || half == 2) && dil >= 1 && hmax >= 2 &&
+            (int64_t)(in1.h - 1) * in1.sh + (int64_t)(in1.w - 1) * in1.sw < (1 << 30) &&
+            gather_tiled_applicable(gout.n, gout.c, gout.h, gout.w, in1) && !getenv("FFWM_DISABLE_TILED_GFLOW")) {
+            const int ml = hmax + (half - 1) * dil;
+            const int rc2 = half == 1 ? launch_gflow_tiled<1>(in1, in2, gout, g2, dil, ml, st)
+                                      : launch_gflow_tiled<2>(in1, in2, gout, g2, dil, ml, st);
+            if (rc2) return rc2;
+            return check_launch("resample2d_backward(tiled flow gradient)");
+        }
+    }
     switch (half) {
         case 1: launch_bwd<T, 1>(in1, in2, gout, g1, g2, dil, st); break;
         case 2: launch_bwd<T, 2>(in1, in2, gout, g1, g2, dil, st); break;

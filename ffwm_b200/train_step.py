@@ -35,8 +35,9 @@ class FFWMTrainer:
     loss_names = ['loss_G', 'loss_D', 'loss_l1', 'loss_iden', 'loss_illu', 'loss_adv', 'loss_prc', 'loss_fc']
 
     def __init__(self, device, crop=False, lightcnn_state=None, flownetf_state=None, flownetb_state=None,
-                 vgg_weights=None, distributed=None):
+                 vgg_weights=None, distributed=None, graph=False):
         self.device = torch.device(device)
+        self._capturable = bool(graph)
         dev = self.device
         self.flowNetF = base_networks.FlowNet(64).to(dev)
         self.flowNetB = base_networks.FlowNet(64).to(dev)
@@ -58,9 +59,10 @@ class FFWMTrainer:
         self.criterionGAN = losses.GANLoss('lsgan').to(dev)
 
         flow_params = itertools.chain(self.flowNetF.parameters(), self.flowNetB.parameters())
-        self.optimizer_F = torch.optim.Adam(flow_params, lr=0.00005, betas=(0.5, 0.999))
-        self.optimizer_G = torch.optim.Adam(self.netG.parameters(), lr=0.0004, betas=(0.5, 0.999))
-        self.optimizer_D = torch.optim.Adam(self.netD.parameters(), lr=0.0004, betas=(0.5, 0.999))
+        adam = dict(betas=(0.5, 0.999), capturable=self._capturable)
+        self.optimizer_F = torch.optim.Adam(flow_params, lr=0.00005, **adam)
+        self.optimizer_G = torch.optim.Adam(self.netG.parameters(), lr=0.0004, **adam)
+        self.optimizer_D = torch.optim.Adam(self.netD.parameters(), lr=0.0004, **adam)
         self.optimizers = [self.optimizer_G, self.optimizer_F, self.optimizer_D]
         self.optimizers_G = [self.optimizer_G, self.optimizer_F]
         self.optimizers_D = [self.optimizer_D]
@@ -152,6 +154,54 @@ class FFWMTrainer:
         if self.avg_G is not None:
             self.avg_G.average()
         self._step(self.optimizers_G)
+
+    # ------------------------------------------------------------------ CUDA graph
+    def enable_cuda_graph(self, example_batch, warmup=3):
+        """Capture one whole `optimize_parameters()` — ~10^4 kernel launches — into a CUDA graph and
+        replay it from then on (`set_input` copies into the captured input buffers).  The step is
+        launch-bound when issued from Python; replaying removes the CPU from the loop.  Requires the
+        optimisers to be built with `capturable=True` (constructor argument `graph=True`)."""
+        assert self.device.type == "cuda" and self._capturable, "construct the trainer with graph=True"
+        self._static = {k: (v.to(self.device).clone() if torch.is_tensor(v) else v) for k, v in example_batch.items()}
+        self._graph = None
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):              # cudnn autotuning, allocator warm-up, averager plans
+                self._bind(self._static)
+                self.optimize_parameters()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self._zero(self.optimizers)
+        from . import _lib
+        graph = torch.cuda.CUDAGraph()
+        self._bind(self._static)
+        n0 = _lib.LAUNCHES
+        with torch.cuda.graph(graph):
+            self.optimize_parameters()
+        self.graph_kernel_nodes = _lib.LAUNCHES - n0     # ffwm_b200 kernels recorded in the graph
+        self.graph_replays = 0
+        self._graph = graph
+
+    def _bind(self, batch):
+        self.img_S, self.img_F, self.lm_F = batch['img_S'], batch['img_F'], batch['lm_F']
+        self.mask_F, self.mask_S = batch['mask_F'].float(), batch['mask_S'].float()
+        self.titers = batch['titers']
+        self.epoch = batch.get('epoch', 0)
+
+    def step(self, batch):
+        """set_input + optimize_parameters; replays the captured graph when there is one."""
+        if getattr(self, "_graph", None) is None:
+            self.set_input(batch)
+            self.optimize_parameters()
+            return
+        if batch is not self._static:
+            assert (batch['titers'] < 20000) == (self._static['titers'] < 20000), "warm-up branch is baked into the graph"
+            for k, v in self._static.items():
+                if torch.is_tensor(v):
+                    v.copy_(batch[k], non_blocking=True)
+        self._graph.replay()
+        self.graph_replays += 1
 
     @staticmethod
     def _zero(opts):

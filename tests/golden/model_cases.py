@@ -106,7 +106,7 @@ def run_netg(net):
     for i, f in enumerate(flows):
         res["grad/flow%d" % i] = sub(f.grad)
     params = dict(net.named_parameters())
-    for k in ("e0.0.weight_orig", "dres2.1.blocks.3.weight_orig", "att1.0.0.bias"):
+    for k in ("e0.0.weight_orig", "dres2.1.blocks.3.weight_orig", "rec1.0.bias"):
         res["grad/" + k] = sub(params[k].grad)
     res["sn_u/e1.0.weight_u"] = sub(net.state_dict()["e1.0.weight_u"])
     return res

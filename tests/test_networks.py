@@ -77,11 +77,19 @@ def test_generator_refuses_cpu_tensors(nets):
 
 
 # ------------------------------------------------------------------ GPU: every net, f64 and f32
+# fp32 tolerances (relative to max|ref|, reference = float64 CPU): plain conv stacks 2e-3; LightCNN's
+# max-feature-map is piecewise linear, so rounding flips a few max selections and reroutes their
+# gradient (2e-2); the generator's flow gradients pass through ~60 conv+BN(batch of 2) layers (3e-2).
+# The float64 runs are the tight check (1e-8).
+F32_TOL = {"flownet16": 2e-3, "netD": 2e-3, "lightcnn": 2e-2, "netG": 3e-2}
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("dt,rtol", [(torch.float64, 1e-8), (torch.float32, 2e-3)])
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
 @pytest.mark.parametrize("which", ["flownet16", "netD", "lightcnn", "netG"])
-def test_networks_match_reference_on_gpu(nets, which, dt, rtol):
+def test_networks_match_reference_on_gpu(nets, which, dt):
     B, L = nets
+    rtol = 1e-8 if dt == torch.float64 else F32_TOL[which]
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     dev = torch.device("cuda", 0)

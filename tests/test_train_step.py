@@ -71,3 +71,30 @@ def test_train_step_matches_reference_on_gpu():
     got = run_two_steps(tr)
     assert _lib.LAUNCHES - n0 >= 2 * 16          # 16 grid warps per step went through the C ABI
     compare(tr, got, 5e-3)
+
+
+@pytest.mark.gpu
+def test_cuda_graph_replay_matches_eager_launches():
+    """The captured step (benchmarks use it) must compute what the eager step computes."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from ffwm_b200.train_step import FFWMTrainer
+    from oracle.train_cpu import synthetic_batch
+    batches = [synthetic_batch(2, seed=900 + i) for i in range(3)]
+    torch.manual_seed(3)
+    eager = FFWMTrainer("cuda:0")
+    torch.manual_seed(3)
+    graphed = FFWMTrainer("cuda:0", graph=True)
+    for a, b in zip(eager.netG.state_dict().values(), graphed.netG.state_dict().values()):
+        assert torch.equal(a, b)
+    # the capture warm-up runs 3 real optimisation steps on batches[0]: do the same eagerly
+    for _ in range(3):
+        eager.step(batches[0])
+    graphed.enable_cuda_graph(batches[0], warmup=3)
+    assert graphed.graph_kernel_nodes >= 16
+    for b in batches[1:]:
+        eager.step(b)
+        graphed.step(b)
+        le, lg = eager.get_current_losses(), graphed.get_current_losses()
+        for k in le:
+            assert abs(le[k] - lg[k]) <= 2e-3 * max(abs(le[k]), 1e-3), (k, le[k], lg[k])
