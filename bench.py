@@ -110,7 +110,7 @@ def warp_microbench(local_rank, pk, steps=10, warmup=3):
     for _ in range(warmup):
         wl.step(timed=False)
     torch.cuda.synchronize()
-    n0 = _lib.LAUNCHES
+    n0 = _lib.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -119,7 +119,7 @@ def warp_microbench(local_rank, pk, steps=10, warmup=3):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     return {"metric": wl.METRIC, "value": wl.units_per_step() / (ms * 1e-3), "unit": wl.UNIT, "steps": steps,
-            "warmup": warmup, "ms_per_step": ms, "config": wl.config(), "gpu_launches": _lib.LAUNCHES - n0,
+            "warmup": warmup, "ms_per_step": ms, "config": wl.config(), "gpu_launches": _lib.kernel_launches() - n0,
             "roofline": wl.roofline(pk), "kernels": wl.kernel_table(pk)}
 
 
@@ -179,7 +179,7 @@ def main():
         wl.step(timed=False)
     barrier()
     sampler = ClockSampler(local_rank)
-    launches0 = _lib.LAUNCHES + wl.extra_launches()
+    launches0 = _lib.kernel_launches() + wl.extra_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
     ncu_range = os.environ.get("FFWM_BENCH_NCU_RANGE") == "1"     # `ncu --profile-from-start off`
@@ -193,7 +193,7 @@ def main():
     if ncu_range:
         torch.cuda.profiler.stop()
     clocks = sampler.stop()
-    launches = _lib.LAUNCHES + wl.extra_launches() - launches0
+    launches = _lib.kernel_launches() + wl.extra_launches() - launches0
     ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)

@@ -30,6 +30,7 @@ _I, _VP = ctypes.c_int, ctypes.c_void_p
 SIGNATURES = {
     "ffwm_abi_version": [],
     "ffwm_last_error": [],
+    "ffwm_kernel_launches": [],
     "ffwm_resample2d_forward": [_T4P, _T4P, _T4P, _I, _I, _I, _VP],
     "ffwm_resample2d_backward": [_T4P, _T4P, _T4P, _T4P, _T4P, _I, _I, _I, _VP],
     "ffwm_block_extractor_forward": [_T4P, _T4P, _T4P, _I, _I, _VP],
@@ -41,7 +42,12 @@ SIGNATURES = {
 }
 
 _lib = None
-LAUNCHES = 0   # kernels enqueued through the C ABI by this process (each entry point launches exactly one)
+LAUNCHES = 0   # C-ABI entry-point calls made by this process (kernel launches: kernel_launches())
+
+
+def kernel_launches():
+    """Kernels enqueued by libffwm_b200 in this process (an entry point may launch more than one)."""
+    return int(lib().ffwm_kernel_launches())
 
 
 def lib():
@@ -56,7 +62,7 @@ def lib():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(l, name)          # AttributeError if the symbol is not exported
             fn.argtypes = argtypes
-            fn.restype = ctypes.c_char_p if name == "ffwm_last_error" else ctypes.c_int
+            fn.restype = {"ffwm_last_error": ctypes.c_char_p, "ffwm_kernel_launches": ctypes.c_ulonglong}.get(name, ctypes.c_int)
         if l.ffwm_abi_version() != ABI_VERSION:
             raise ImportError("ffwm_b200: ABI version mismatch (library %d, binding %d)"
                               % (l.ffwm_abi_version(), ABI_VERSION))

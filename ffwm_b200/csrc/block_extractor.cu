@@ -18,6 +18,7 @@
 //             then across the CTA's channel slices through shared memory, and
 //             stored once: no atomics, deterministic.
 #include "common.cuh"
+#include "scatter_tiled.cuh"
 
 namespace ffwm {
 
@@ -186,6 +187,29 @@ block_extractor_fwd_tiled_kernel(View<const T> src, View<const T> flow, View<T> 
     }
 }
 
+// Tap list of one OUTPUT pixel (y,x) of the k*Hf x k*Wf map for the tiled scatter
+// (scatter_tiled.cuh): the four bilinear taps of block_tap, weights in K5's product order.
+// A 16x16 output tile covers ~(16/k)^2 flow pixels, so its taps land in a small neighbourhood of
+// (ty0/k, tx0/k) of the source plane.
+struct BlockExtractorScatterGeo {
+    static constexpr int NT = 4;
+    View<const float> flow;
+    int k, hs, ws;
+    __device__ __forceinline__ void region_origin(int tx0, int ty0, int ml, int& rx0, int& ry0) const {
+        rx0 = tx0 / k - ml;
+        ry0 = ty0 / k - ml;
+    }
+    __device__ __forceinline__ void taps(int b, int y, int x, int* iy, int* ix, float* w) const {
+        const int yf = y / k, xf = x / k;
+        const float* f = flow.p + b * flow.sb + yf * flow.sh + xf * flow.sw;
+        const Bilin<float> t = block_tap<float>(__ldg(f), __ldg(f + flow.sc), xf, yf, x - xf * k - k / 2, y - yf * k - k / 2, hs, ws);
+        iy[0] = t.yT; ix[0] = t.xL; w[0] = t.xL_P * t.yT_P;
+        iy[1] = t.yT; ix[1] = t.xR; w[1] = t.xR_P * t.yT_P;
+        iy[2] = t.yB; ix[2] = t.xL; w[2] = t.xL_P * t.yB_P;
+        iy[3] = t.yB; ix[3] = t.xR; w[3] = t.xR_P * t.yB_P;
+    }
+};
+
 template <typename T, int SL>
 __global__ void __launch_bounds__(256)
 block_extractor_bwd_kernel(View<const T> src, View<const T> flow, View<const T> gout,
@@ -339,6 +363,16 @@ static int block_extractor_backward_t(const ffwm_tensor4* a, const ffwm_tensor4*
     if ((int64_t)gout.n * gout.h * gout.w == 0) return FFWM_OK;
     if (gout.n > 65535) { set_error("block_extractor: batch %d > 65535", gout.n); return FFWM_ERR_TOO_LARGE; }
     if (src.h == 0 || src.w == 0) { set_error("block_extractor: empty source plane"); return FFWM_ERR_SHAPE; }
+    if constexpr (sizeof(T) == 4) {
+        // grad_source through the tiled scatter; the fused kernel below then only reduces the flow gradient
+        if (gs.p && scatter_tiled_applicable(gout, gs)) {
+            int rc2 = launch_scatter_tiled(BlockExtractorScatterGeo{flow, k, src.h, src.w}, gout, gs, 12, st);
+            if (rc2) return rc2;
+            if ((rc2 = check_launch("block_extractor_backward(tiled scatter)"))) return rc2;
+            if (!gf.p) return FFWM_OK;
+            gs.p = nullptr;
+        }
+    }
     const int c = gout.c;
     if (c >= 8) launch_bwd_sl<T, 8>(src, flow, gout, gs, gf, k, st);
     else if (c >= 4) launch_bwd_sl<T, 4>(src, flow, gout, gs, gf, k, st);

@@ -61,7 +61,10 @@ template int make_view<double>(const ffwm_tensor4*, const char*, View<double>*, 
 template int make_view<const float>(const ffwm_tensor4*, const char*, View<const float>*, bool);
 template int make_view<const double>(const ffwm_tensor4*, const char*, View<const double>*, bool);
 
+static unsigned long long g_launches = 0;   // kernels enqueued by this process (diagnostic, not synchronised)
+
 int check_launch(const char* what) {
+    __atomic_add_fetch(&g_launches, 1ULL, __ATOMIC_RELAXED);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("%s: %s", what, cudaGetErrorString(e));
@@ -87,3 +90,4 @@ int sm_count() {
 
 extern "C" int ffwm_abi_version(void) { return FFWM_ABI_VERSION; }
 extern "C" const char* ffwm_last_error(void) { return ffwm::g_err; }
+extern "C" unsigned long long ffwm_kernel_launches(void) { return __atomic_load_n(&ffwm::g_launches, __ATOMIC_RELAXED); }

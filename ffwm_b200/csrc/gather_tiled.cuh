@@ -39,20 +39,26 @@ __device__ __forceinline__ float gt_load(const float* slab_lane, const float* pl
 }
 
 // slab[c][31*31] <- src[b, c0+c, ry0.., rx0..] for the part of the region inside the image.
-// One warp per (channel, region row): 31 lanes read 124 contiguous bytes.
+// One warp per (channel, region row): 31 lanes copy 124 contiguous bytes with cp.async (LDGSTS), so
+// all ~62 row copies of a warp are in flight at once and nothing is staged in registers.
+// Complete with gt_fill_wait() + __syncthreads().
 __device__ __forceinline__ void gt_fill_slab(float* slab, const View<const float>& src, int b, int c0, int nch,
                                              int ry0, int rx0, int warp, int lane) {
     const int gx = rx0 + lane;
     const bool col_ok = lane < GT_RW && (unsigned)gx < (unsigned)src.w;
     const float* base = src.p + b * src.sb + (int64_t)c0 * src.sc + gx * src.sw;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(slab) + 4u * lane;
 #pragma unroll 4
     for (int pr = warp; pr < 32 * GT_RW; pr += GT_WARPS) {
         const int c = pr / GT_RW, row = pr - c * GT_RW;
         const int gy = ry0 + row;
         if (col_ok && c < nch && (unsigned)gy < (unsigned)src.h)
-            slab[c * GT_RPX + row * GT_RW + lane] = __ldg(base + (int64_t)c * src.sc + gy * src.sh);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sbase + 4u * (c * GT_RPX + row * GT_RW)),
+                         "l"(base + (int64_t)c * src.sc + gy * src.sh) : "memory");
     }
 }
+
+__device__ __forceinline__ void gt_fill_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // G[c][256] <- t[b, c0+c, tile]; thread -> (channel tid/16, column tid%16), 16 rows.
 __device__ __forceinline__ void gt_fill_tile(float* G, const View<const float>& t, int b, int c0, int nch,
@@ -78,6 +84,30 @@ __device__ __forceinline__ void gt_store_row(const float* stage, const View<floa
         const int c = it * 2 + half;
         if (c < nch) st_stream(op + (int64_t)c * out.sc, stage[c * GT_SPITCH + x]);
     }
+}
+
+// Sum N per-lane values over the 32 lanes of a warp with N + log-ish shuffles instead of 5*N:
+// every butterfly step halves the number of live values (each lane keeps the half selected by
+// one bit of its lane id).  On return v[0] of lane l holds the warp total of value index l >> (5 - log2 N)...
+// for N = 16: index l >> 1; for N = 8: index l >> 2.  Lanes sharing an index hold the same total.
+template <int N>
+__device__ __forceinline__ float gt_packed_reduce(float (&v)[N], int lane) {
+    static_assert(N == 8 || N == 16, "N must be 8 or 16");
+    int offset = 16;
+#pragma unroll
+    for (int n = N / 2; n >= 1; n >>= 1, offset >>= 1) {
+        const bool hi = (lane & offset) != 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float send = hi ? v[i] : v[i + n];
+            const float keep = hi ? v[i + n] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, offset);
+        }
+    }
+    float r = v[0];
+#pragma unroll
+    for (; offset >= 1; offset >>= 1) r += __shfl_xor_sync(0xffffffffu, r, offset);
+    return r;
 }
 
 inline bool gather_tiled_applicable(int n, int c, int h, int w, const View<const float>& src) {

@@ -64,6 +64,10 @@ struct GridWarpScatterGeo {
     static constexpr int NT = 4;
     View<const float> flow;
     int hi, wi;
+    __device__ __forceinline__ void region_origin(int tx0, int ty0, int ml, int& rx0, int& ry0) const {
+        rx0 = tx0 - ml;
+        ry0 = ty0 - ml;
+    }
     __device__ __forceinline__ void taps(int b, int y, int x, int* iy, int* ix, float* w) const {
         const float* f = flow.p + b * flow.sb + y * flow.sh + x * flow.sw;
         const Corner<float> cr = corners<float>(__ldg(f), __ldg(f + flow.sc), hi, wi);
@@ -111,21 +115,23 @@ grid_warp_fwd_kernel(View<const T> img, View<const T> flow, View<T> out, int c_p
 // MODE 0: forward.  MODE 1: flow gradient (grad_images comes from the tiled scatter).
 // Per-pixel parameters: 4 tap offsets (INT_MIN for a corner outside the image: zeros padding) and
 // either the 4 bilinear weights (forward) or the d/dix, d/diy coefficient of each corner (gradient).
-constexpr int GW_PW = 12;
+constexpr int GW_PW = 16;     // 4 offsets | 4 weights or d/dix coefficients | 4 d/diy coefficients | far flag, pad
 
 template <int MODE>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 grid_warp_tiled_kernel(View<const float> img, View<const float> flow, View<const float> gout, View<float> dst) {
     extern __shared__ __align__(16) unsigned char gt_smem_raw[];
     float* slab = reinterpret_cast<float*>(gt_smem_raw);               // [32][961]
-    float* prm = slab + 32 * GT_RPX;                                   // [256][12]
-    float* aux = prm + GT_NPX * GW_PW;                                 // fwd: staging [16][32][17]; grad: G [32][257]
+    float* prm = slab + 32 * GT_RPX;                                   // [256][16]
+    float* accs = prm + GT_NPX * GW_PW;                                // grad: [16 warps][16 px][2]
+    float* aux = accs + GT_WARPS * GT_TW * 2;                          // fwd: staging [16][32][17]; grad: G [32][257]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx0 = blockIdx.x * GT_TW, ty0 = blockIdx.y * GT_TH, b = blockIdx.z;
     const int rx0 = tx0 - 7, ry0 = ty0 - 7;
     const int oh = MODE == 0 ? dst.h : gout.h, ow = MODE == 0 ? dst.w : gout.w;
     const int nc = MODE == 0 ? dst.c : gout.c;
 
+    for (int i = tid; i < GT_WARPS * GT_TW * 2; i += GT_THREADS) accs[i] = 0.f;
     if (tid < GT_NPX) {
         const int y = ty0 + tid / GT_TW, x = tx0 + tid % GT_TW;
         if (y < oh && x < ow) {
@@ -138,6 +144,9 @@ grid_warp_tiled_kernel(View<const float> img, View<const float> flow, View<const
             Pi[1] = cr.v[1] ? gt_tap_offset(y0, x1, ry0, rx0, img.sh, img.sw) : INT_MIN;
             Pi[2] = cr.v[2] ? gt_tap_offset(y1, x0, ry0, rx0, img.sh, img.sw) : INT_MIN;
             Pi[3] = cr.v[3] ? gt_tap_offset(y1, x1, ry0, rx0, img.sh, img.sw) : INT_MIN;
+            int anyfar = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) anyfar |= (Pi[k] < 0 && Pi[k] != INT_MIN);
             if (MODE == 0) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) P[4 + k] = cr.v[k] ? cr.w[k] : 0.f;
@@ -145,47 +154,64 @@ grid_warp_tiled_kernel(View<const float> img, View<const float> flow, View<const
                 P[4] = -cr.wy1; P[5] = cr.wy1; P[6] = -cr.wy0; P[7] = cr.wy0;      // d out / d ix per corner
                 P[8] = -cr.wx1; P[9] = -cr.wx0; P[10] = cr.wx1; P[11] = cr.wx0;    // d out / d iy per corner
             }
+            Pi[12] = anyfar;
         }
     }
-    float gix[GT_TW], giy[GT_TW];
-#pragma unroll
-    for (int px = 0; px < GT_TW; ++px) gix[px] = giy[px] = 0.f;
+    float* acc = accs + warp * (GT_TW * 2);
     const int y = ty0 + warp;
     for (int c0 = 0; c0 < nc; c0 += 32) {
         const int nch = min(32, nc - c0);
         __syncthreads();
         gt_fill_slab(slab, img, b, c0, nch, ry0, rx0, warp, lane);
         if (MODE == 1) gt_fill_tile(aux, gout, b, c0, nch, ty0, tx0, tid);
+        gt_fill_wait();
         __syncthreads();
         if (y < oh) {
             const float* slab_lane = slab + lane * GT_RPX;
             const float* plane_lane = img.p + b * img.sb + (int64_t)(c0 + min(lane, nch - 1)) * img.sc;
             float* stage = aux + warp * (32 * GT_SPITCH);
             const float* G_lane = aux + lane * GT_GPITCH + warp * GT_TW;
+#pragma unroll 1
+            for (int p4 = 0; p4 < GT_TW / 4; ++p4) {
+                float red[8];
 #pragma unroll
-            for (int px = 0; px < GT_TW; ++px) {
-                if (tx0 + px < ow) {
-                    const float4* P4 = reinterpret_cast<const float4*>(prm + (warp * GT_TW + px) * GW_PW);
-                    const float4 o4 = P4[0], w4 = P4[1];
-                    const int off[4] = {__float_as_int(o4.x), __float_as_int(o4.y), __float_as_int(o4.z), __float_as_int(o4.w)};
-                    float v[4];
+                for (int k = 0; k < 4; ++k) {
+                    const int px = p4 * 4 + k;
+                    red[2 * k] = red[2 * k + 1] = 0.f;
+                    if (tx0 + px < ow) {                                    // warp-uniform
+                        const float4* P4 = reinterpret_cast<const float4*>(prm + (warp * GT_TW + px) * GW_PW);
+                        const float4 o4 = P4[0], w4 = P4[1];
+                        const int off[4] = {__float_as_int(o4.x), __float_as_int(o4.y), __float_as_int(o4.z), __float_as_int(o4.w)};
+                        float v[4];
+                        if (reinterpret_cast<const int*>(P4)[12] == 0) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) v[k] = off[k] == INT_MIN ? 0.f : gt_load(slab_lane, plane_lane, off[k]);
-                    if (MODE == 0) {
-                        float r = 0.f;
-                        r += v[0] * w4.x;
-                        r += v[1] * w4.y;
-                        r += v[2] * w4.z;
-                        r += v[3] * w4.w;
-                        stage[lane * GT_SPITCH + px] = r;
-                    } else {
-                        const float4 y4 = P4[2];
-                        const float g = lane < nch ? G_lane[px] : 0.f;
-                        gix[px] += v[0] * w4.x * g; giy[px] += v[0] * y4.x * g;
-                        gix[px] += v[1] * w4.y * g; giy[px] += v[1] * y4.y * g;
-                        gix[px] += v[2] * w4.z * g; giy[px] += v[2] * y4.z * g;
-                        gix[px] += v[3] * w4.w * g; giy[px] += v[3] * y4.w * g;
+                            for (int t = 0; t < 4; ++t) v[t] = off[t] == INT_MIN ? 0.f : slab_lane[off[t]];
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) v[t] = off[t] == INT_MIN ? 0.f : gt_load(slab_lane, plane_lane, off[t]);
+                        }
+                        if (MODE == 0) {
+                            float r = 0.f;
+                            r += v[0] * w4.x;
+                            r += v[1] * w4.y;
+                            r += v[2] * w4.z;
+                            r += v[3] * w4.w;
+                            stage[lane * GT_SPITCH + px] = r;
+                        } else {
+                            const float4 y4 = P4[2];
+                            const float g = lane < nch ? G_lane[px] : 0.f;
+                            float gx = 0.f, gy = 0.f;
+                            gx += v[0] * w4.x * g; gy += v[0] * y4.x * g;
+                            gx += v[1] * w4.y * g; gy += v[1] * y4.y * g;
+                            gx += v[2] * w4.z * g; gy += v[2] * y4.z * g;
+                            gx += v[3] * w4.w * g; gy += v[3] * y4.w * g;
+                            red[2 * k] = gx; red[2 * k + 1] = gy;
+                        }
                     }
+                }
+                if (MODE == 1) {
+                    const float tot = gt_packed_reduce<8>(red, lane);        // lane l: value index l >> 2
+                    if ((lane & 3) == 0) acc[p4 * 8 + (lane >> 2)] += tot;
                 }
             }
             if (MODE == 0) {
@@ -196,28 +222,18 @@ grid_warp_tiled_kernel(View<const float> img, View<const float> flow, View<const
         }
     }
     if (MODE == 0 || y >= oh) return;
-    float sx = 0.f, sy = 0.f;
-#pragma unroll
-    for (int px = 0; px < GT_TW; ++px) {
-        float v0 = gix[px], v1 = giy[px];
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-            v0 += __shfl_xor_sync(0xffffffffu, v0, d);
-            v1 += __shfl_xor_sync(0xffffffffu, v1, d);
-        }
-        if (lane == px) { sx = v0; sy = v1; }
-    }
+    __syncwarp();
     const int x = tx0 + lane;
     if (lane >= GT_TW || x >= ow) return;
     float* o = dst.p + b * dst.sb + y * dst.sh + x * dst.sw;
-    o[0] = (float(img.w) / 2) * sx;
-    o[dst.sc] = (float(img.h) / 2) * sy;
+    o[0] = (float(img.w) / 2) * acc[lane * 2];
+    o[dst.sc] = (float(img.h) / 2) * acc[lane * 2 + 1];
 }
 
 template <int MODE>
 static int launch_grid_warp_tiled(const View<const float>& img, const View<const float>& flow,
                                   const View<const float>& gout, const View<float>& dst, int n, int h, int w, cudaStream_t st) {
-    const size_t smem = sizeof(float) * (32 * GT_RPX + GT_NPX * GW_PW + (MODE == 0 ? GT_WARPS * 32 * GT_SPITCH : 32 * GT_GPITCH));
+    const size_t smem = sizeof(float) * (32 * GT_RPX + GT_NPX * GW_PW + GT_WARPS * GT_TW * 2 + (MODE == 0 ? GT_WARPS * 32 * GT_SPITCH : 32 * GT_GPITCH));
     cudaError_t e = cudaFuncSetAttribute(grid_warp_tiled_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("grid_warp_tiled: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
     dim3 grid(ceil_div(w, GT_TW), ceil_div(h, GT_TH), n);

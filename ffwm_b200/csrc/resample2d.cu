@@ -74,6 +74,10 @@ struct Resample2dScatterGeo {
     static constexpr int NT = 4 * HALF * HALF;
     View<const float> in2;
     int dil, ih, iw;
+    __device__ __forceinline__ void region_origin(int tx0, int ty0, int ml, int& rx0, int& ry0) const {
+        rx0 = tx0 - ml;
+        ry0 = ty0 - ml;
+    }
     __device__ __forceinline__ void taps(int b, int y, int x, int* iy, int* ix, float* w) const {
         constexpr int N2 = 2 * HALF;
         const float* f = in2.p + b * in2.sb + y * in2.sh + x * in2.sw;
@@ -152,7 +156,7 @@ resample2d_fwd_kernel(View<const T> in1, View<const T> in2, View<T> out, int dil
 template <int HALF>
 struct RsFwdParams {
     static constexpr int N2 = 2 * HALF, NT = N2 * N2;
-    static constexpr int PW = ((NT + 2 * N2 + 1 + 3) / 4) * 4;     // words per pixel, 16-byte rows
+    static constexpr int PW = ((NT + 2 * N2 + 2 + 3) / 4) * 4;     // offsets, wx, wy, sum, far flag; 16-byte rows
 };
 
 template <int HALF>
@@ -180,13 +184,19 @@ resample2d_fwd_tiled_kernel(View<const float> in1, View<const float> in2, View<f
             const float sum = tap_weights<float, HALF>(t.dxs, t.dys, sigma, wx, wy);
             float* P = prm + tid * PW;
             int* Pi = reinterpret_cast<int*>(P);
+            int anyfar = 0;
 #pragma unroll
             for (int i = 0; i < N2; ++i)
 #pragma unroll
-                for (int j = 0; j < N2; ++j) Pi[i * N2 + j] = gt_tap_offset(t.iy[i], t.ix[j], ry0, rx0, in1.sh, in1.sw);
+                for (int j = 0; j < N2; ++j) {
+                    const int o = gt_tap_offset(t.iy[i], t.ix[j], ry0, rx0, in1.sh, in1.sw);
+                    Pi[i * N2 + j] = o;
+                    anyfar |= o < 0;
+                }
 #pragma unroll
             for (int i = 0; i < N2; ++i) { P[NT + i] = wx[i]; P[NT + N2 + i] = wy[i]; }
             P[NT + 2 * N2] = sum;
+            Pi[NT + 2 * N2 + 1] = anyfar;
         }
     }
     float* stage = stage_all + warp * (32 * GT_SPITCH);
@@ -195,6 +205,7 @@ resample2d_fwd_tiled_kernel(View<const float> in1, View<const float> in2, View<f
         const int nch = min(32, out.c - c0);
         __syncthreads();                             // parameters written / previous group's slab consumed
         gt_fill_slab(slab, in1, b, c0, nch, ry0, rx0, warp, lane);
+        gt_fill_wait();
         __syncthreads();
         if (y < out.h) {
             const float* slab_lane = slab + lane * GT_RPX;
@@ -202,17 +213,11 @@ resample2d_fwd_tiled_kernel(View<const float> in1, View<const float> in2, View<f
 #pragma unroll 2
             for (int px = 0; px < GT_TW; ++px) {
                 if (tx0 + px >= out.w) break;        // warp-uniform
-                const float4* P4 = reinterpret_cast<const float4*>(prm + (warp * GT_TW + px) * PW);
-                int off[NT];
+                const float* P = prm + (warp * GT_TW + px) * PW;
+                const float4* P4 = reinterpret_cast<const float4*>(P);
                 float w[2 * N2 + 4];
 #pragma unroll
-                for (int q = 0; q < NT / 4; ++q) {
-                    const float4 v = P4[q];
-                    off[4 * q] = __float_as_int(v.x); off[4 * q + 1] = __float_as_int(v.y);
-                    off[4 * q + 2] = __float_as_int(v.z); off[4 * q + 3] = __float_as_int(v.w);
-                }
-#pragma unroll
-                for (int q = 0; q < (2 * N2 + 1 + 3) / 4; ++q) {
+                for (int q = 0; q < (2 * N2 + 2 + 3) / 4; ++q) {
                     const float4 v = P4[NT / 4 + q];
                     w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
                 }
@@ -220,15 +225,38 @@ resample2d_fwd_tiled_kernel(View<const float> in1, View<const float> in2, View<f
                 const float* wy = w + N2;
                 const float sum = w[2 * N2];
                 float val = 0.f;
+                if (__float_as_int(w[2 * N2 + 1]) == 0) {
+                    // every tap inside the slab: one conflict-free shared load per tap, nothing else
+                    int off[NT];
 #pragma unroll
-                for (int fy = 0; fy < HALF; ++fy)
-#pragma unroll
-                    for (int fx = 0; fx < HALF; ++fx) {
-                        val += wy[2 * fy] * wx[2 * fx] * gt_load(slab_lane, plane_lane, off[(2 * fy) * N2 + 2 * fx]);
-                        val += wy[2 * fy] * wx[2 * fx + 1] * gt_load(slab_lane, plane_lane, off[(2 * fy) * N2 + 2 * fx + 1]);
-                        val += wy[2 * fy + 1] * wx[2 * fx] * gt_load(slab_lane, plane_lane, off[(2 * fy + 1) * N2 + 2 * fx]);
-                        val += wy[2 * fy + 1] * wx[2 * fx + 1] * gt_load(slab_lane, plane_lane, off[(2 * fy + 1) * N2 + 2 * fx + 1]);
+                    for (int q = 0; q < NT / 4; ++q) {
+                        const float4 v = P4[q];
+                        off[4 * q] = __float_as_int(v.x); off[4 * q + 1] = __float_as_int(v.y);
+                        off[4 * q + 2] = __float_as_int(v.z); off[4 * q + 3] = __float_as_int(v.w);
                     }
+#pragma unroll
+                    for (int fy = 0; fy < HALF; ++fy)
+#pragma unroll
+                        for (int fx = 0; fx < HALF; ++fx) {
+                            val += wy[2 * fy] * wx[2 * fx] * slab_lane[off[(2 * fy) * N2 + 2 * fx]];
+                            val += wy[2 * fy] * wx[2 * fx + 1] * slab_lane[off[(2 * fy) * N2 + 2 * fx + 1]];
+                            val += wy[2 * fy + 1] * wx[2 * fx] * slab_lane[off[(2 * fy + 1) * N2 + 2 * fx]];
+                            val += wy[2 * fy + 1] * wx[2 * fx + 1] * slab_lane[off[(2 * fy + 1) * N2 + 2 * fx + 1]];
+                        }
+                } else {
+                    // some tap left the halo: same sum, taps fetched one by one (slab or global)
+                    const int* Pi = reinterpret_cast<const int*>(P);
+#pragma unroll 1
+                    for (int f = 0; f < HALF * HALF; ++f) {
+                        const int fy = f / HALF, fx = f - fy * HALF;
+                        const float wyt = P[NT + N2 + 2 * fy], wyb = P[NT + N2 + 2 * fy + 1];
+                        const float wxl = P[NT + 2 * fx], wxr = P[NT + 2 * fx + 1];
+                        val += wyt * wxl * gt_load(slab_lane, plane_lane, Pi[(2 * fy) * N2 + 2 * fx]);
+                        val += wyt * wxr * gt_load(slab_lane, plane_lane, Pi[(2 * fy) * N2 + 2 * fx + 1]);
+                        val += wyb * wxl * gt_load(slab_lane, plane_lane, Pi[(2 * fy + 1) * N2 + 2 * fx]);
+                        val += wyb * wxr * gt_load(slab_lane, plane_lane, Pi[(2 * fy + 1) * N2 + 2 * fx + 1]);
+                    }
+                }
                 stage[lane * GT_SPITCH + px] = float(safe_div<float>(val, sum));
             }
             __syncwarp();
@@ -297,8 +325,35 @@ resample2d_fwd_generic_kernel(View<const T> in1, View<const T> in2, View<T> out,
 template <int HALF>
 struct RsGradParams {
     static constexpr int N2 = 2 * HALF, NT = N2 * N2;
-    static constexpr int PW = ((NT + 6 * N2 + 2 + 3) / 4) * 4;   // offsets, wx wy ax ay bx by, sum, sigma
+    static constexpr int PW = ((NT + 6 * N2 + 3 + 3) / 4) * 4;   // offsets, wx wy ax ay bx by, sum, sigma, far flag
 };
+
+// One pixel of the flow-gradient sums with at least one tap outside the slab (rare): loops are
+// kept rolled and read the parameters straight from shared memory.
+template <int HALF>
+__device__ __noinline__ void rs_gflow_pixel_slow(const float* P, const float* slab_lane, const float* plane_lane,
+                                                 float g, float* out4) {
+    constexpr int N2 = 2 * HALF, NT = N2 * N2;
+    const int* Pi = reinterpret_cast<const int*>(P);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, bs = 0.f;
+#pragma unroll 1
+    for (int i = 0; i < N2; ++i) {
+        float r0 = 0.f, rB = 0.f, r2 = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < N2; ++j) {
+            const float s = g * gt_load(slab_lane, plane_lane, Pi[i * N2 + j]);
+            r0 += P[NT + 2 * N2 + j] * s;
+            rB += P[NT + j] * s;
+            r2 += P[NT + 4 * N2 + j] * s;
+        }
+        const float wyi = P[NT + N2 + i];
+        a0 += wyi * r0;
+        a1 += P[NT + 3 * N2 + i] * rB;
+        a2 += P[NT + 5 * N2 + i] * rB + wyi * r2;
+        bs += wyi * rB;
+    }
+    out4[0] = a0; out4[1] = a1; out4[2] = a2; out4[3] = bs;
+}
 
 template <int HALF>
 __global__ void __launch_bounds__(GT_THREADS, 1)
@@ -310,10 +365,12 @@ resample2d_gflow_tiled_kernel(View<const float> in1, View<const float> in2, View
     float* slab = reinterpret_cast<float*>(gt_smem_raw);               // [32][961]
     float* G = slab + 32 * GT_RPX;                                     // [32][257]
     float* prm = G + 32 * GT_GPITCH;                                   // [256][PW]
+    float* accs = prm + GT_NPX * PW;                                   // [16 warps][16 px][4]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx0 = blockIdx.x * GT_TW, ty0 = blockIdx.y * GT_TH, b = blockIdx.z;
     const int rx0 = tx0 - ml, ry0 = ty0 - ml;
 
+    for (int i = tid; i < GT_WARPS * GT_TW * 4; i += GT_THREADS) accs[i] = 0.f;
     if (tid < GT_NPX) {
         const int y = ty0 + tid / GT_TW, x = tx0 + tid % GT_TW;
         if (y < gout.h && x < gout.w) {
@@ -326,10 +383,15 @@ resample2d_gflow_tiled_kernel(View<const float> in1, View<const float> in2, View
             const float sum = tap_weights<float, HALF>(t.dxs, t.dys, sigma, wx, wy);
             float* P = prm + tid * PW;
             int* Pi = reinterpret_cast<int*>(P);
+            int anyfar = 0;
 #pragma unroll
             for (int i = 0; i < N2; ++i)
 #pragma unroll
-                for (int j = 0; j < N2; ++j) Pi[i * N2 + j] = gt_tap_offset(t.iy[i], t.ix[j], ry0, rx0, in1.sh, in1.sw);
+                for (int j = 0; j < N2; ++j) {
+                    const int o = gt_tap_offset(t.iy[i], t.ix[j], ry0, rx0, in1.sh, in1.sw);
+                    Pi[i * N2 + j] = o;
+                    anyfar |= o < 0;
+                }
 #pragma unroll
             for (int i = 0; i < N2; ++i) {
                 const float sgn = (i & 1) ? -1.f : 1.f;            // +xL_, -xR_ / +yT_, -yB_
@@ -342,77 +404,79 @@ resample2d_gflow_tiled_kernel(View<const float> in1, View<const float> in2, View
             }
             P[NT + 6 * N2] = sum;
             P[NT + 6 * N2 + 1] = sigma;
+            Pi[NT + 6 * N2 + 2] = anyfar;
         }
     }
-    float A0[GT_TW], A1[GT_TW], A2[GT_TW], Bs[GT_TW];
-#pragma unroll
-    for (int px = 0; px < GT_TW; ++px) A0[px] = A1[px] = A2[px] = Bs[px] = 0.f;
+    float* acc = accs + warp * (GT_TW * 4);
     const int y = ty0 + warp;
     for (int c0 = 0; c0 < gout.c; c0 += 32) {
         const int nch = min(32, gout.c - c0);
         __syncthreads();
         gt_fill_slab(slab, in1, b, c0, nch, ry0, rx0, warp, lane);
         gt_fill_tile(G, gout, b, c0, nch, ty0, tx0, tid);
+        gt_fill_wait();
         __syncthreads();
-        if (y < gout.h && lane < nch) {
+        if (y < gout.h) {
             const float* slab_lane = slab + lane * GT_RPX;
-            const float* plane_lane = in1.p + b * in1.sb + (int64_t)(c0 + lane) * in1.sc;
+            const float* plane_lane = in1.p + b * in1.sb + (int64_t)(c0 + min(lane, nch - 1)) * in1.sc;
             const float* G_lane = G + lane * GT_GPITCH + warp * GT_TW;
+#pragma unroll 1
+            for (int p4 = 0; p4 < GT_TW / 4; ++p4) {
+                float v[16];
 #pragma unroll
-            for (int px = 0; px < GT_TW; ++px) {
-                if (tx0 + px < gout.w) {
-                    const float4* P4 = reinterpret_cast<const float4*>(prm + (warp * GT_TW + px) * PW);
-                    int off[NT];
-                    float w[6 * N2];
+                for (int k = 0; k < 4; ++k) {
+                    const int px = p4 * 4 + k;
+                    float r4[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (tx0 + px < gout.w) {                      // warp-uniform
+                        const float* P = prm + (warp * GT_TW + px) * PW;
+                        const float g = lane < nch ? G_lane[px] : 0.f;
+                        if (reinterpret_cast<const int*>(P)[NT + 6 * N2 + 2] == 0) {
+                            const float4* P4 = reinterpret_cast<const float4*>(P);
+                            int off[NT];
+                            float w[6 * N2];
 #pragma unroll
-                    for (int q = 0; q < NT / 4; ++q) {
-                        const float4 v = P4[q];
-                        off[4 * q] = __float_as_int(v.x); off[4 * q + 1] = __float_as_int(v.y);
-                        off[4 * q + 2] = __float_as_int(v.z); off[4 * q + 3] = __float_as_int(v.w);
-                    }
+                            for (int q = 0; q < NT / 4; ++q) {
+                                const float4 u = P4[q];
+                                off[4 * q] = __float_as_int(u.x); off[4 * q + 1] = __float_as_int(u.y);
+                                off[4 * q + 2] = __float_as_int(u.z); off[4 * q + 3] = __float_as_int(u.w);
+                            }
 #pragma unroll
-                    for (int q = 0; q < (6 * N2) / 4; ++q) {
-                        const float4 v = P4[NT / 4 + q];
-                        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
-                    }
-                    const float *wx = w, *wy = w + N2, *ax = w + 2 * N2, *ay = w + 3 * N2, *bx = w + 4 * N2, *by = w + 5 * N2;
-                    const float g = G_lane[px];
+                            for (int q = 0; q < (6 * N2) / 4; ++q) {
+                                const float4 u = P4[NT / 4 + q];
+                                w[4 * q] = u.x; w[4 * q + 1] = u.y; w[4 * q + 2] = u.z; w[4 * q + 3] = u.w;
+                            }
+                            const float *wx = w, *wy = w + N2, *ax = w + 2 * N2, *ay = w + 3 * N2, *bx = w + 4 * N2, *by = w + 5 * N2;
 #pragma unroll
-                    for (int i = 0; i < N2; ++i) {
-                        float r0 = 0.f, rB = 0.f, r2 = 0.f;
+                            for (int i = 0; i < N2; ++i) {
+                                float r0 = 0.f, rB = 0.f, r2 = 0.f;
 #pragma unroll
-                        for (int j = 0; j < N2; ++j) {
-                            const float s = g * gt_load(slab_lane, plane_lane, off[i * N2 + j]);
-                            r0 += ax[j] * s;
-                            rB += wx[j] * s;
-                            r2 += bx[j] * s;
+                                for (int j = 0; j < N2; ++j) {
+                                    const float s = g * slab_lane[off[i * N2 + j]];
+                                    r0 += ax[j] * s;
+                                    rB += wx[j] * s;
+                                    r2 += bx[j] * s;
+                                }
+                                r4[0] += wy[i] * r0;
+                                r4[1] += ay[i] * rB;
+                                r4[2] += by[i] * rB + wy[i] * r2;
+                                r4[3] += wy[i] * rB;
+                            }
+                        } else {
+                            rs_gflow_pixel_slow<HALF>(P, slab_lane, plane_lane, g, r4);
                         }
-                        A0[px] += wy[i] * r0;
-                        A1[px] += ay[i] * rB;
-                        A2[px] += by[i] * rB + wy[i] * r2;
-                        Bs[px] += wy[i] * rB;
                     }
+                    v[4 * k] = r4[0]; v[4 * k + 1] = r4[1]; v[4 * k + 2] = r4[2]; v[4 * k + 3] = r4[3];
                 }
+                const float tot = gt_packed_reduce<16>(v, lane);       // lane l: value index l >> 1
+                if ((lane & 1) == 0) acc[p4 * 16 + (lane >> 1)] += tot;
             }
         }
     }
-    if (y >= gout.h) return;                          // whole warp; no barrier follows
-    // channel sums: butterfly over the 32 lanes, then lane px keeps pixel px
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, bs = 0.f;
-#pragma unroll
-    for (int px = 0; px < GT_TW; ++px) {
-        float v0 = A0[px], v1 = A1[px], v2 = A2[px], v3 = Bs[px];
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-            v0 += __shfl_xor_sync(0xffffffffu, v0, d);
-            v1 += __shfl_xor_sync(0xffffffffu, v1, d);
-            v2 += __shfl_xor_sync(0xffffffffu, v2, d);
-            v3 += __shfl_xor_sync(0xffffffffu, v3, d);
-        }
-        if (lane == px) { a0 = v0; a1 = v1; a2 = v2; bs = v3; }
-    }
+    if (y >= gout.h) return;                          // whole warp; no block barrier follows
+    __syncwarp();
     const int x = tx0 + lane;
     if (lane >= GT_TW || x >= gout.w) return;
+    const float a0 = acc[lane * 4], a1 = acc[lane * 4 + 1], a2 = acc[lane * 4 + 2], bs = acc[lane * 4 + 3];
     const float* P = prm + (warp * GT_TW + lane) * PW;
     float Wx = 0.f, Wy = 0.f, AX = 0.f, AY = 0.f, BX = 0.f, BY = 0.f;
 #pragma unroll
@@ -440,7 +504,7 @@ template <int HALF>
 static int launch_gflow_tiled(const View<const float>& in1, const View<const float>& in2, const View<const float>& gout,
                               const View<float>& g2, int dil, int ml, cudaStream_t st) {
     using PP = RsGradParams<HALF>;
-    const size_t smem = sizeof(float) * (32 * GT_RPX + 32 * GT_GPITCH + GT_NPX * PP::PW);
+    const size_t smem = sizeof(float) * (32 * GT_RPX + 32 * GT_GPITCH + GT_NPX * PP::PW + GT_WARPS * GT_TW * 4);
     cudaError_t e = cudaFuncSetAttribute(resample2d_gflow_tiled_kernel<HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("resample2d_gflow_tiled: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
     dim3 grid(ceil_div(gout.w, GT_TW), ceil_div(gout.h, GT_TH), gout.n);

@@ -50,6 +50,7 @@ struct StSmem {
     }
 };
 
+// Geo::region_origin(tx0,ty0,ml,&rx0,&ry0)  where the tile's taps are expected to land
 // Geo::NT                       taps per pixel
 // Geo::taps(b, y, x, iy[], ix[], w[]) -> fills clamped/valid destination coords and weights;
 //                                        w == 0 entries with iy < 0 are skipped (invalid taps)
@@ -67,7 +68,8 @@ scatter_tiled_kernel(Geo geo, View<const float> gout, View<float> gsrc, int ml) 
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx0 = blockIdx.x * ST_TW, ty0 = blockIdx.y * ST_TH, b = blockIdx.z;
-    const int rx0 = tx0 - ml, ry0 = ty0 - ml;
+    int rx0, ry0;                            // origin of the 31x31 destination region in the source plane
+    geo.region_origin(tx0, ty0, ml, rx0, ry0);
 
     for (int i = tid; i < ST_RPX + 1; i += ST_THREADS) cnt[i] = 0;
     if (tid == 0) misc[0] = 0;
@@ -147,6 +149,23 @@ scatter_tiled_kernel(Geo geo, View<const float> gout, View<float> gsrc, int ml) 
     }
     __syncthreads();
     const int nfar = misc[0];
+    // split the destinations into ST_WARPS contiguous ranges with (nearly) equal entry counts
+    int q_beg, q_end, e_beg, e_end;
+    {
+        const int total = off[ST_RPX];
+        auto first_dest_at = [&](int target) {           // smallest q with off[q] >= target
+            int lo = 0, hi = ST_RPX;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (off[mid] < target) lo = mid + 1; else hi = mid;
+            }
+            return lo;
+        };
+        q_beg = warp == 0 ? 0 : first_dest_at((int)(((long long)total * warp) / ST_WARPS));
+        q_end = warp == ST_WARPS - 1 ? ST_RPX : first_dest_at((int)(((long long)total * (warp + 1)) / ST_WARPS));
+        e_beg = off[q_beg];
+        e_end = off[q_end];
+    }
 
     // ---- 2. channel groups -------------------------------------------------------------------
     for (int c0 = 0; c0 < gout.c; c0 += 32) {
@@ -163,17 +182,42 @@ scatter_tiled_kernel(Geo geo, View<const float> gout, View<float> gsrc, int ml) 
             }
         }
         __syncthreads();
-        // destinations owned by this warp
+        // destinations owned by this warp: a contiguous range, so its entries are one contiguous
+        // stream that can be read ahead (4 entries in flight) instead of one dependent
+        // entry -> tile-value -> fma chain per entry
         const float* Gl = G + lane * ST_GPITCH;
         float* Rl = R + lane * ST_RPX;
-        for (int q = warp; q < ST_RPX; q += ST_WARPS) {
-            const int beg = off[q], end = off[q + 1];
+        {
+            int q = q_beg, e = e_beg;
+            int nb = off[q + 1];
             float acc = 0.f;
-            for (int e = beg; e < end; ++e) {
-                const StEntry en = ent[e];
-                acc = fmaf(en.w, Gl[en.p], acc);
+            for (; e < e_end; e += 4) {
+                StEntry en[4];
+                float gv[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    en[k].p = 0; en[k].w = 0.f;
+                    if (e + k < e_end) en[k] = ent[e + k];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) gv[k] = Gl[en[k].p];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (e + k < e_end) {
+                        while (e + k >= nb) {            // warp-uniform: close finished (or empty) destinations
+                            Rl[q] = acc;
+                            acc = 0.f;
+                            ++q;
+                            nb = off[q + 1];
+                        }
+                        acc = fmaf(en[k].w, gv[k], acc);
+                    }
+                }
             }
-            Rl[q] = acc;
+            for (; q < q_end; ++q) {                     // the open destination, then trailing empty ones
+                Rl[q] = acc;
+                acc = 0.f;
+            }
         }
         // far entries: direct REDs, lanes are channels
         for (int k = warp; k < nfar; k += ST_WARPS) {

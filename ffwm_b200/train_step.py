@@ -176,10 +176,10 @@ class FFWMTrainer:
         from . import _lib
         graph = torch.cuda.CUDAGraph()
         self._bind(self._static)
-        n0 = _lib.LAUNCHES
+        n0 = _lib.kernel_launches()
         with torch.cuda.graph(graph):
             self.optimize_parameters()
-        self.graph_kernel_nodes = _lib.LAUNCHES - n0     # ffwm_b200 kernels recorded in the graph
+        self.graph_kernel_nodes = _lib.kernel_launches() - n0     # ffwm_b200 kernels recorded in the graph
         self.graph_replays = 0
         self._graph = graph
 

@@ -60,6 +60,9 @@ typedef struct ffwm_tensor4 {
 
 int ffwm_abi_version(void);
 const char* ffwm_last_error(void);
+/* Number of kernels this process has enqueued through the library (diagnostic counter used by
+ * bench.py's `gpu_launches`; the reference has no equivalent). */
+unsigned long long ffwm_kernel_launches(void);
 
 /* resample2d_cuda.forward   (cuda/resample2d_package/resample2d_cuda.cc:6-15,
  *                            resample2d_kernel.cu:20-95,335-375)

@@ -66,10 +66,10 @@ def test_train_step_matches_reference_on_gpu():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     from ffwm_b200 import _lib
-    n0 = _lib.LAUNCHES
+    n0 = _lib.kernel_launches()
     tr = build_trainer("cuda:0")
     got = run_two_steps(tr)
-    assert _lib.LAUNCHES - n0 >= 2 * 16          # 16 grid warps per step went through the C ABI
+    assert _lib.kernel_launches() - n0 >= 2 * 16          # 16 grid warps per step went through the C ABI
     compare(tr, got, 5e-3)
 
 

@@ -442,3 +442,29 @@ def test_grid_warp_tiled_scatter_matches_direct_and_torch(ops, noise):
     torch.nn.functional.grid_sample(x, gr.permute(0, 2, 3, 1), align_corners=False).backward(go.double())
     assert rel_err(gi_t.cpu().double(), x.grad) <= 1e-5
     assert rel_err(gf_t.cpu().double(), gr.grad) <= 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,mode", [(3, "rand1.8"), (3, "wild"), (2, "rand1.8"), (5, "rand1.8")])
+def test_block_extractor_tiled_paths_match_direct_and_oracle(ops, oracle_warp, k, mode):
+    """Large enough for the tiled forward (k=2,3) and the tiled grad_source scatter."""
+    g = torch.Generator().manual_seed(31 + k)
+    b, c, h, w = 2, 24, 40, 37
+    src = torch.rand(b, c, h, w, generator=g)
+    flow = torch.rand(b, 2, h, w, generator=g) * 1.8 if mode == "rand1.8" else torch.randn(b, 2, h, w, generator=g) * 9
+    go = torch.randn(b, c, k * h, k * w, generator=g)
+    d = [t.to(DEV) for t in (src, flow, go)]
+    out = torch.empty_like(d[2])
+    ops.block_extractor_forward(d[0], d[1], out, k)
+    assert rel_err(out.cpu(), oracle_warp.block_extractor_forward(src, flow, k)) <= 1e-6
+    gs_t, gf_t = torch.zeros_like(d[0]), torch.empty_like(d[1])
+    ops.block_extractor_backward(d[0], d[1], d[2], gs_t, gf_t, k)
+    os.environ["FFWM_DISABLE_TILED"] = "1"
+    try:
+        gs_d, gf_d = torch.zeros_like(d[0]), torch.empty_like(d[1])
+        ops.block_extractor_backward(d[0], d[1], d[2], gs_d, gf_d, k)
+    finally:
+        del os.environ["FFWM_DISABLE_TILED"]
+    assert rel_err(gs_t, gs_d) <= 2e-5 and rel_err(gf_t, gf_d) <= 5e-5
+    ws, wf = oracle_warp.block_extractor_backward(src, flow, go, k)
+    assert rel_err(gs_t.cpu(), ws) <= 1e-4 and rel_err(gf_t.cpu(), wf) <= 1e-4
