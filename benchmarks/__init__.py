@@ -10,7 +10,10 @@ def get_workload(name):
     if name == "train_step":
         from .train_step import TrainStepWorkload
         return TrainStepWorkload
-    raise SystemExit("bench.py: unknown workload %r (warp, train_step)" % name)
+    if name == "flownet":
+        from .flownet import FlowNetWorkload
+        return FlowNetWorkload
+    raise SystemExit("bench.py: unknown workload %r (train_step, warp, flownet)" % name)
 
 
 # The workload BASELINE.json's metric is quoted on.

@@ -1,0 +1,108 @@
+"""FlowNetF forward+backward (BASELINE config 2): batch 6, 128x128 synthetic pairs, one GPU.
+
+One step = forward of `FlowNet(64)` in train mode + backward of sum(out_i * cotangent_i) over the
+three flow scales (13.05 GFLOP per image).  Not the default bench line; run with
+`python bench.py --workload flownet`.
+"""
+import os
+import time
+
+import torch
+
+BATCH = 6
+GFLOP_PER_IMAGE = 13.05
+
+
+class FlowNetWorkload:
+    METRIC = "FlowNetF forward+backward images/sec (128x128, batch 6)"
+    UNIT = "images/s"
+    DTYPE = "f32"
+    STEPS, WARMUP = 30, 5
+    E2E_STEPS = 10
+    REF_STEPS, REF_WARMUP = 2, 1
+
+    def __init__(self, device, rank=0, world=1):
+        self.dev, self.rank, self.world = device, rank, world
+
+    def _build(self, dev):
+        from ffwm_b200.base_networks import FlowNet
+        torch.manual_seed(0)
+        net = FlowNet(64).to(dev).train()
+        g = torch.Generator().manual_seed(1)
+        x = torch.rand(BATCH, 3, 128, 128, generator=g)
+        cots = [torch.randn(BATCH, 2, s, s, generator=g) for s in (128, 64, 32)]
+        return net, x, cots
+
+    def setup(self):
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.benchmark = True
+        self.net, x, cots = self._build(self.dev)
+        self.x, self.cots = x.to(self.dev), [c.to(self.dev) for c in cots]
+        self.host_x = x.pin_memory()
+
+    def _fb(self, x):
+        self.net.zero_grad(set_to_none=True)
+        outs = self.net(x)
+        loss = sum((o * c).sum() for o, c in zip(outs, self.cots))
+        loss.backward()
+        return loss
+
+    def step(self, timed):
+        self._fb(self.x)
+
+    def step_e2e(self):
+        self.loss_value = float(self._fb(self.host_x.to(self.dev, non_blocking=True)).detach())
+
+    def e2e_bytes(self):
+        return self.host_x.numel() * 4, 4
+
+    def extra_launches(self):
+        return 0
+
+    def units_per_step(self):
+        return BATCH
+
+    def config(self):
+        return {"workload": "FlowNetF fwd+bwd (BASELINE cfg2)", "batch": BATCH, "image": "128x128",
+                "conv_math": "fp32 (cudnn.allow_tf32=False)", "weights": "random init (MSRA)"}
+
+    def step_roofline(self, pk, ms_per_step):
+        tflops = GFLOP_PER_IMAGE * BATCH / 1e3 / (ms_per_step * 1e-3)
+        return {"kernel": "whole step (cuDNN convolutions; the net is launch/weight-bandwidth bound)", "bound": "tensor",
+                "achieved": tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": tflops / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"]}
+
+    def roofline(self, pk):
+        return None
+
+    def kernel_table(self, pk):
+        return None
+
+    @classmethod
+    def _cpu_time(cls, steps, warmup):
+        torch.set_num_threads(os.cpu_count())
+        w = cls(device=None)
+        net, x, cots = w._build("cpu")
+        w.net, w.cots = net, cots
+        for _ in range(warmup):
+            w._fb(x)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            w._fb(x)
+        dt = (time.perf_counter() - t0) / steps
+        return BATCH / dt, dt, "the same FlowNet(64) fwd+bwd on the host CPU (PyTorch CPU kernels), batch %d, %d step(s)" % (BATCH, steps)
+
+    @classmethod
+    def cpu_baseline(cls):
+        v, dt, sample = cls._cpu_time(2, 1)
+        return {"value": v, "unit": cls.UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample}
+
+    @classmethod
+    def run_reference(cls, steps, warmup, n_gpus):
+        v, dt, sample = cls._cpu_time(max(1, steps), warmup)
+        return {"impl": "reference", "metric": cls.METRIC, "value": v, "unit": cls.UNIT, "n_gpus": n_gpus, "steps": steps,
+                "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": cls.DTYPE, "data": "synthetic", "config": dict(cls(device=None).config(), sample=sample),
+                "cpu_baseline": {"value": v, "unit": cls.UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+                "e2e": {"value": v, "unit": cls.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

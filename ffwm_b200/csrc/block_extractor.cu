@@ -193,6 +193,7 @@ block_extractor_fwd_tiled_kernel(View<const T> src, View<const T> flow, View<T> 
 // (ty0/k, tx0/k) of the source plane.
 struct BlockExtractorScatterGeo {
     static constexpr int NT = 4;
+    static constexpr int RW = 15;      // a 16x16 output tile covers ~6x6 flow pixels (k>=3)
     View<const float> flow;
     int k, hs, ws;
     __device__ __forceinline__ void region_origin(int tx0, int ty0, int ml, int& rx0, int& ry0) const {
@@ -366,7 +367,7 @@ static int block_extractor_backward_t(const ffwm_tensor4* a, const ffwm_tensor4*
     if constexpr (sizeof(T) == 4) {
         // grad_source through the tiled scatter; the fused kernel below then only reduces the flow gradient
         if (gs.p && scatter_tiled_applicable(gout, gs)) {
-            int rc2 = launch_scatter_tiled(BlockExtractorScatterGeo{flow, k, src.h, src.w}, gout, gs, 12, st);
+            int rc2 = launch_scatter_tiled(BlockExtractorScatterGeo{flow, k, src.h, src.w}, gout, gs, k >= 3 ? 4 : 2, st);
             if (rc2) return rc2;
             if ((rc2 = check_launch("block_extractor_backward(tiled scatter)"))) return rc2;
             if (!gf.p) return FFWM_OK;

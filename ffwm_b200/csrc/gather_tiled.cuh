@@ -39,22 +39,24 @@ __device__ __forceinline__ float gt_load(const float* slab_lane, const float* pl
 }
 
 // slab[c][31*31] <- src[b, c0+c, ry0.., rx0..] for the part of the region inside the image.
-// One warp per (channel, region row): 31 lanes copy 124 contiguous bytes with cp.async (LDGSTS), so
-// all ~62 row copies of a warp are in flight at once and nothing is staged in registers.
+// Warp w copies channels 2w and 2w+1: per region row, 31 lanes issue one 4-byte cp.async (LDGSTS)
+// covering 124 contiguous bytes; all row copies of a warp are in flight at once and nothing is
+// staged in registers.  The loop only advances one global and one shared pointer.
 // Complete with gt_fill_wait() + __syncthreads().
 __device__ __forceinline__ void gt_fill_slab(float* slab, const View<const float>& src, int b, int c0, int nch,
                                              int ry0, int rx0, int warp, int lane) {
     const int gx = rx0 + lane;
-    const bool col_ok = lane < GT_RW && (unsigned)gx < (unsigned)src.w;
-    const float* base = src.p + b * src.sb + (int64_t)c0 * src.sc + gx * src.sw;
-    const unsigned sbase = (unsigned)__cvta_generic_to_shared(slab) + 4u * lane;
+    if (lane >= GT_RW || (unsigned)gx >= (unsigned)src.w) return;
+    const int r_lo = max(0, -ry0), r_hi = min(GT_RW, src.h - ry0);      // region rows inside the image
+#pragma unroll
+    for (int cc = 0; cc < 32 / GT_WARPS; ++cc) {
+        const int c = warp * (32 / GT_WARPS) + cc;
+        if (c >= nch) break;
+        const float* gp = src.p + b * src.sb + (int64_t)(c0 + c) * src.sc + (int64_t)(ry0 + r_lo) * src.sh + gx * src.sw;
+        unsigned sp = (unsigned)__cvta_generic_to_shared(slab) + 4u * (c * GT_RPX + r_lo * GT_RW + lane);
 #pragma unroll 4
-    for (int pr = warp; pr < 32 * GT_RW; pr += GT_WARPS) {
-        const int c = pr / GT_RW, row = pr - c * GT_RW;
-        const int gy = ry0 + row;
-        if (col_ok && c < nch && (unsigned)gy < (unsigned)src.h)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sbase + 4u * (c * GT_RPX + row * GT_RW)),
-                         "l"(base + (int64_t)c * src.sc + gy * src.sh) : "memory");
+        for (int row = r_lo; row < r_hi; ++row, gp += src.sh, sp += 4u * GT_RW)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sp), "l"(gp) : "memory");
     }
 }
 

@@ -62,6 +62,7 @@ __device__ __forceinline__ void corner_offsets(const Corner<T>& c, int sh, int s
 // corners; corners outside the image are skipped (zeros padding).
 struct GridWarpScatterGeo {
     static constexpr int NT = 4;
+    static constexpr int RW = 31;
     View<const float> flow;
     int hi, wi;
     __device__ __forceinline__ void region_origin(int tx0, int ty0, int ml, int& rx0, int& ry0) const {

@@ -72,6 +72,7 @@ __device__ __forceinline__ T tap_weights(const T* dxs, const T* dys, T sigma, T*
 template <int HALF>
 struct Resample2dScatterGeo {
     static constexpr int NT = 4 * HALF * HALF;
+    static constexpr int RW = 31;
     View<const float> in2;
     int dil, ih, iw;
     __device__ __forceinline__ void region_origin(int tx0, int ty0, int ml, int& rx0, int& ry0) const {

@@ -46,10 +46,21 @@ def main():
         model = FlowNetModel(opt)
         model.reverse = False                      # train_flow.py sets it from --reverse
         MC.fill_state(model.flowNet, torch.float32)
+        class _Extract(torch.nn.Module):
+            def __init__(self, kz):
+                super().__init__()
+                self.kz = kz
+
+            def forward(self, s, f):
+                return train_cpu._BlockExtractorCPU.apply(s, f, self.kz)
+
+        class _Reshape(torch.nn.Module):
+            def forward(self, x, k):
+                return train_cpu._LocalAttnReshapeCPU.apply(x, k)
+
         for reg in model.Regularization.method_dic.values():
-            kz = reg.kz
-            reg.extractor = (lambda s, f, kz=kz: train_cpu._BlockExtractorCPU.apply(s, f, kz))
-            reg.reshape = (lambda x, k: train_cpu._LocalAttnReshapeCPU.apply(x, k))
+            reg.extractor = _Extract(reg.kz)
+            reg.reshape = _Reshape()
         inner = model.criterionLD.criterionLD
 
         def ld_forward(flows, lm_S, lm_F, gate, self=model.criterionLD):
