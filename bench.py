@@ -123,6 +123,15 @@ def warp_microbench(local_rank, pk, steps=10, warmup=3):
             "roofline": wl.roofline(pk), "kernels": wl.kernel_table(pk)}
 
 
+def note(msg):
+    """Phase marker on stderr (rank-tagged), so a stalled multi-GPU run shows where it stopped."""
+    sys.stderr.write("[bench r%s %6.1fs] %s\n" % (os.environ.get("RANK", "0"), time.time() - _T0, msg))
+    sys.stderr.flush()
+
+
+_T0 = time.time()
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -172,12 +181,15 @@ def main():
     import ffwm_b200
     from ffwm_b200 import _lib
     wl = wl_cls(device=torch.device("cuda", local_rank), rank=rank, world=world)
+    note("setup")
     wl.setup()
+    note("warm-up")
 
     # ---- device-resident leg: inputs already in HBM ------------------------------------
     for _ in range(warmup):
         wl.step(timed=False)
     barrier()
+    note("timed region")
     sampler = ClockSampler(local_rank)
     launches0 = _lib.kernel_launches() + wl.extra_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -203,6 +215,7 @@ def main():
     value = units / (ms_per_step * 1e-3)
 
     # ---- end-to-end leg: host buffers through the public API --------------------------
+    note("device leg done: %.2f ms/step" % ms_per_step)
     e2e = None
     if not args.no_e2e:
         for _ in range(3):
@@ -223,6 +236,7 @@ def main():
         e2e = {"value": eunits / (float(ems.item()) / e2e_steps * 1e-3), "unit": wl.UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps}
 
+    note("e2e leg done")
     if rank == 0:
         pk = peaks()
         line = {

@@ -17,8 +17,9 @@
 //             the reference's worst atomic hotspot — is reduced in registers,
 //             then across the CTA's channel slices through shared memory, and
 //             stored once: no atomics, deterministic.
+#include <stdlib.h>
+
 #include "common.cuh"
-#include "scatter_tiled.cuh"
 
 namespace ffwm {
 
@@ -187,29 +188,138 @@ block_extractor_fwd_tiled_kernel(View<const T> src, View<const T> flow, View<T> 
     }
 }
 
-// Tap list of one OUTPUT pixel (y,x) of the k*Hf x k*Wf map for the tiled scatter
-// (scatter_tiled.cuh): the four bilinear taps of block_tap, weights in K5's product order.
-// A 16x16 output tile covers ~(16/k)^2 flow pixels, so its taps land in a small neighbourhood of
-// (ty0/k, tx0/k) of the source plane.
-struct BlockExtractorScatterGeo {
-    static constexpr int NT = 4;
-    static constexpr int RW = 15;      // a 16x16 output tile covers ~6x6 flow pixels (k>=3)
-    View<const float> flow;
-    int k, hs, ws;
-    __device__ __forceinline__ void region_origin(int tx0, int ty0, int ml, int& rx0, int& ry0) const {
-        rx0 = tx0 / k - ml;
-        ry0 = ty0 / k - ml;
-    }
-    __device__ __forceinline__ void taps(int b, int y, int x, int* iy, int* ix, float* w) const {
-        const int yf = y / k, xf = x / k;
+// ---- backward, windowed: k is a template parameter -----------------------------------------
+// Same decomposition as the direct kernel below (CTA = 32 flow pixels x 8 channel slices, flow
+// gradient reduced in registers + shared memory, stored once), but per channel the k*k samples of a
+// flow pixel are folded into their shared (k+1)x(k+1) source window in registers first:
+//   * grad_source: (k+1)^2 REDs per (flow pixel, channel) instead of 4*k*k (16 vs 36 for k=3),
+//     and lanes are neighbouring flow pixels, so the REDs of a warp hit neighbouring addresses;
+//   * flow gradient: the source window is loaded once, (k+1)^2 gathers instead of 4*k*k.
+// Pixels whose clamped taps are not consecutive (float rounding at an integer boundary, rare)
+// take the per-tap path.
+template <int K, int SL>
+__global__ void __launch_bounds__(256, 2)
+block_extractor_bwd_window_kernel(View<const float> src, View<const float> flow, View<const float> gout,
+                                  View<float> gsrc, View<float> gflow) {
+    constexpr int PX = 256 / SL;
+    __shared__ float red[SL][2][PX];
+    const int lane_px = threadIdx.x, slice = threadIdx.y;
+    const int fpix = blockIdx.x * PX + lane_px;
+    const int b = blockIdx.z;
+    const bool live = fpix < flow.h * flow.w;
+    const bool want_src = gsrc.p != nullptr, want_flow = gflow.p != nullptr;
+
+    float gx = 0.f, gy = 0.f;
+    int yf = 0, xf = 0;
+    if (live) {
+        yf = fpix / flow.w;
+        xf = fpix - yf * flow.w;
         const float* f = flow.p + b * flow.sb + yf * flow.sh + xf * flow.sw;
-        const Bilin<float> t = block_tap<float>(__ldg(f), __ldg(f + flow.sc), xf, yf, x - xf * k - k / 2, y - yf * k - k / 2, hs, ws);
-        iy[0] = t.yT; ix[0] = t.xL; w[0] = t.xL_P * t.yT_P;
-        iy[1] = t.yT; ix[1] = t.xR; w[1] = t.xR_P * t.yT_P;
-        iy[2] = t.yB; ix[2] = t.xL; w[2] = t.xL_P * t.yB_P;
-        iy[3] = t.yB; ix[3] = t.xR; w[3] = t.xR_P * t.yB_P;
+        const float fx_raw = __ldg(f), fy_raw = __ldg(f + flow.sc);
+        int cx[K + 1], cy[K + 1];
+        float xLP[K], xRP[K], yTP[K], yBP[K];
+        bool shared_window = true;
+        {
+            int prev_xR = 0, prev_yB = 0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const Bilin<float> t = block_tap<float>(fx_raw, fy_raw, xf, yf, j - K / 2, j - K / 2, src.h, src.w);
+                xLP[j] = t.xL_P; xRP[j] = t.xR_P; yTP[j] = t.yT_P; yBP[j] = t.yB_P;
+                cx[j] = t.xL; cy[j] = t.yT;
+                if (j > 0) shared_window = shared_window && prev_xR == t.xL && prev_yB == t.yT;
+                prev_xR = t.xR; prev_yB = t.yB;
+            }
+            cx[K] = prev_xR;
+            cy[K] = prev_yB;
+        }
+        const int gbase = (yf * K) * gout.sh + (xf * K) * gout.sw;
+        if (shared_window) {
+            for (int c = slice; c < gout.c; c += SL) {
+                const float* gp = gout.plane(b, c) + gbase;
+                float g[K][K];
+#pragma unroll
+                for (int i = 0; i < K; ++i)
+#pragma unroll
+                    for (int j = 0; j < K; ++j) g[i][j] = ld_stream(gp + i * gout.sh + j * gout.sw);
+                if (want_flow) {
+                    const float* s = src.plane(b, c);
+                    float win[K + 1][K + 1];
+#pragma unroll
+                    for (int n = 0; n <= K; ++n)
+#pragma unroll
+                        for (int m = 0; m <= K; ++m) win[n][m] = __ldg(s + cy[n] * src.sh + cx[m] * src.sw);
+#pragma unroll
+                    for (int i = 0; i < K; ++i)
+#pragma unroll
+                        for (int j = 0; j < K; ++j) {
+                            const float xL_yT = win[i][j], xR_yT = win[i][j + 1], xL_yB = win[i + 1][j], xR_yB = win[i + 1][j + 1];
+                            gy += g[i][j] * (-xLP[j] * xL_yT - xRP[j] * xR_yT + xLP[j] * xL_yB + xRP[j] * xR_yB);
+                            gx += g[i][j] * (-yTP[i] * xL_yT - yBP[i] * xL_yB + yTP[i] * xR_yT + yBP[i] * xR_yB);
+                        }
+                }
+                if (want_src) {
+                    float acc[K + 1][K + 1];
+#pragma unroll
+                    for (int n = 0; n <= K; ++n)
+#pragma unroll
+                        for (int m = 0; m <= K; ++m) acc[n][m] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < K; ++i)
+#pragma unroll
+                        for (int j = 0; j < K; ++j) {
+                            acc[i][j] += g[i][j] * xLP[j] * yTP[i];
+                            acc[i][j + 1] += g[i][j] * xRP[j] * yTP[i];
+                            acc[i + 1][j] += g[i][j] * xLP[j] * yBP[i];
+                            acc[i + 1][j + 1] += g[i][j] * xRP[j] * yBP[i];
+                        }
+                    float* d = gsrc.plane(b, c);
+#pragma unroll
+                    for (int n = 0; n <= K; ++n)
+#pragma unroll
+                        for (int m = 0; m <= K; ++m) red_add(d + cy[n] * gsrc.sh + cx[m] * gsrc.sw, acc[n][m]);
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < K; ++i)
+#pragma unroll 1
+                for (int j = 0; j < K; ++j) {
+                    const Bilin<float> t = block_tap<float>(fx_raw, fy_raw, xf, yf, j - K / 2, i - K / 2, src.h, src.w);
+                    for (int c = slice; c < gout.c; c += SL) {
+                        const float grad = ld_stream(gout.plane(b, c) + gbase + i * gout.sh + j * gout.sw);
+                        if (want_src) {
+                            float* d = gsrc.plane(b, c);
+                            red_add(d + t.yT * gsrc.sh + t.xL * gsrc.sw, grad * t.xL_P * t.yT_P);
+                            red_add(d + t.yT * gsrc.sh + t.xR * gsrc.sw, grad * t.xR_P * t.yT_P);
+                            red_add(d + t.yB * gsrc.sh + t.xL * gsrc.sw, grad * t.xL_P * t.yB_P);
+                            red_add(d + t.yB * gsrc.sh + t.xR * gsrc.sw, grad * t.xR_P * t.yB_P);
+                        }
+                        if (want_flow) {
+                            const float* s = src.plane(b, c);
+                            const float xL_yT = __ldg(s + t.yT * src.sh + t.xL * src.sw), xR_yT = __ldg(s + t.yT * src.sh + t.xR * src.sw);
+                            const float xL_yB = __ldg(s + t.yB * src.sh + t.xL * src.sw), xR_yB = __ldg(s + t.yB * src.sh + t.xR * src.sw);
+                            gy += grad * (-t.xL_P * xL_yT - t.xR_P * xR_yT + t.xL_P * xL_yB + t.xR_P * xR_yB);
+                            gx += grad * (-t.yT_P * xL_yT - t.yB_P * xL_yB + t.yT_P * xR_yT + t.yB_P * xR_yB);
+                        }
+                    }
+                }
+        }
     }
-};
+    if (!want_flow) return;
+    red[slice][0][lane_px] = gx;
+    red[slice][1][lane_px] = gy;
+    __syncthreads();
+    if (slice != 0) return;
+#pragma unroll
+    for (int s = 1; s < SL; ++s) {
+        gx += red[s][0][lane_px];
+        gy += red[s][1][lane_px];
+    }
+    if (!live) return;
+    float* o = gflow.p + b * gflow.sb + yf * gflow.sh + xf * gflow.sw;
+    o[0] = gx;
+    o[gflow.sc] = gy;
+}
 
 template <typename T, int SL>
 __global__ void __launch_bounds__(256)
@@ -365,13 +475,12 @@ static int block_extractor_backward_t(const ffwm_tensor4* a, const ffwm_tensor4*
     if (gout.n > 65535) { set_error("block_extractor: batch %d > 65535", gout.n); return FFWM_ERR_TOO_LARGE; }
     if (src.h == 0 || src.w == 0) { set_error("block_extractor: empty source plane"); return FFWM_ERR_SHAPE; }
     if constexpr (sizeof(T) == 4) {
-        // grad_source through the tiled scatter; the fused kernel below then only reduces the flow gradient
-        if (gs.p && scatter_tiled_applicable(gout, gs)) {
-            int rc2 = launch_scatter_tiled(BlockExtractorScatterGeo{flow, k, src.h, src.w}, gout, gs, k >= 3 ? 4 : 2, st);
-            if (rc2) return rc2;
-            if ((rc2 = check_launch("block_extractor_backward(tiled scatter)"))) return rc2;
-            if (!gf.p) return FFWM_OK;
-            gs.p = nullptr;
+        if ((k == 2 || k == 3) && gout.c >= 8 && !getenv("FFWM_DISABLE_TILED")) {
+            constexpr int SL = 8, PX = 256 / SL;
+            dim3 grid(ceil_div(flow.h * flow.w, PX), 1, gout.n), block(PX, SL);
+            if (k == 2) block_extractor_bwd_window_kernel<2, SL><<<grid, block, 0, st>>>(src, flow, gout, gs, gf);
+            else block_extractor_bwd_window_kernel<3, SL><<<grid, block, 0, st>>>(src, flow, gout, gs, gf);
+            return check_launch("block_extractor_backward(window)");
         }
     }
     const int c = gout.c;

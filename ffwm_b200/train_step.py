@@ -156,14 +156,21 @@ class FFWMTrainer:
         self._step(self.optimizers_G)
 
     # ------------------------------------------------------------------ CUDA graph
-    def enable_cuda_graph(self, example_batch, warmup=3):
-        """Capture one whole `optimize_parameters()` — ~10^4 kernel launches — into a CUDA graph and
-        replay it from then on (`set_input` copies into the captured input buffers).  The step is
+    def enable_cuda_graph(self, example_batch, warmup=3, segmented=None):
+        """Capture `optimize_parameters()` — ~10^4 kernel launches — into CUDA graph(s) and replay
+        from then on (`step` copies the batch into the captured input buffers).  The step is
         launch-bound when issued from Python; replaying removes the CPU from the loop.  Requires the
-        optimisers to be built with `capturable=True` (constructor argument `graph=True`)."""
+        optimisers to be built with `capturable=True` (constructor argument `graph=True`).
+
+        Single process: one graph.  Data parallel: three graphs sharing one memory pool,
+            [forward, backward_D]  | all-reduce D grads |  [step D, backward_G]  | all-reduce G,F grads |  [step G,F]
+        with the NCCL all-reduces issued eagerly between the replays (collectives are kept out of
+        the captured region on purpose: nothing about the capture depends on the communicator)."""
         assert self.device.type == "cuda" and self._capturable, "construct the trainer with graph=True"
+        if segmented is None:
+            segmented = self.avg_D is not None
         self._static = {k: (v.to(self.device).clone() if torch.is_tensor(v) else v) for k, v in example_batch.items()}
-        self._graph = None
+        self._graphs = None
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -174,14 +181,31 @@ class FFWMTrainer:
         torch.cuda.synchronize(self.device)
         self._zero(self.optimizers)
         from . import _lib
-        graph = torch.cuda.CUDAGraph()
         self._bind(self._static)
         n0 = _lib.kernel_launches()
-        with torch.cuda.graph(graph):
-            self.optimize_parameters()
-        self.graph_kernel_nodes = _lib.kernel_launches() - n0     # ffwm_b200 kernels recorded in the graph
+        if not segmented:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.optimize_parameters()
+            self._graphs = [(g, None)]
+        else:
+            g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self.forward()
+                set_requires_grad(self.netD, True)
+                self._zero(self.optimizers_D)
+                self.backward_D()
+            pool = g1.pool()
+            with torch.cuda.graph(g2, pool=pool):
+                self._step(self.optimizers_D)
+                set_requires_grad(self.netD, False)
+                self._zero(self.optimizers_G)
+                self.backward_G()
+            with torch.cuda.graph(g3, pool=pool):
+                self._step(self.optimizers_G)
+            self._graphs = [(g1, self.avg_D), (g2, self.avg_G), (g3, None)]
+        self.graph_kernel_nodes = _lib.kernel_launches() - n0     # ffwm_b200 kernels recorded in the graph(s)
         self.graph_replays = 0
-        self._graph = graph
 
     def _bind(self, batch):
         self.img_S, self.img_F, self.lm_F = batch['img_S'], batch['img_F'], batch['lm_F']
@@ -191,7 +215,7 @@ class FFWMTrainer:
 
     def step(self, batch):
         """set_input + optimize_parameters; replays the captured graph when there is one."""
-        if getattr(self, "_graph", None) is None:
+        if getattr(self, "_graphs", None) is None:
             self.set_input(batch)
             self.optimize_parameters()
             return
@@ -200,7 +224,10 @@ class FFWMTrainer:
             for k, v in self._static.items():
                 if torch.is_tensor(v):
                     v.copy_(batch[k], non_blocking=True)
-        self._graph.replay()
+        for graph, averager in self._graphs:
+            graph.replay()
+            if averager is not None:
+                averager.average()
         self.graph_replays += 1
 
     @staticmethod

@@ -85,11 +85,11 @@ def test_cuda_graph_replay_matches_eager_launches():
     from oracle.train_cpu import synthetic_batch
     batches = [synthetic_batch(2, seed=900 + i) for i in range(3)]
 
-    def run(graph):
+    def run(graph, segmented=False):
         torch.manual_seed(3)
         tr = FFWMTrainer("cuda:0", graph=graph)
         if graph:
-            tr.enable_cuda_graph(batches[0], warmup=3)      # 3 real optimisation steps on batches[0]
+            tr.enable_cuda_graph(batches[0], warmup=3, segmented=segmented)   # 3 real steps on batches[0]
             assert tr.graph_kernel_nodes >= 16
         else:
             for _ in range(3):
@@ -100,8 +100,10 @@ def test_cuda_graph_replay_matches_eager_launches():
             out.append(tr.get_current_losses())
         return out
 
-    e1, e2, g = run(False), run(False), run(True)
-    for a, b, c in zip(e1, e2, g):
+    e1, e2, g, gs = run(False), run(False), run(True), run(True, segmented=True)   # gs: the data-parallel layout
+    for a, b, c, d in zip(e1, e2, g, gs):
         for k in a:
             spread = abs(a[k] - b[k])
-            assert abs(a[k] - c[k]) <= max(5 * spread, 2e-2 * max(abs(a[k]), 1e-3)), (k, a[k], b[k], c[k])
+            tol = max(5 * spread, 2e-2 * max(abs(a[k]), 1e-3))
+            assert abs(a[k] - c[k]) <= tol, ("one graph", k, a[k], b[k], c[k])
+            assert abs(a[k] - d[k]) <= tol, ("three graphs", k, a[k], b[k], d[k])
