@@ -90,7 +90,9 @@ class TrainStepWorkload:
                 "nets": "netG(FFWM sn) + flowNetF + flowNetB + netD(MSDiscriminator) + LightCNN-29 + VGG19",
                 "parallelism": "dp%d (NCCL grad all-reduce, per-rank BN)" % self.world,
                 "conv_math": "tf32" if self.tf32 else "fp32 (cudnn.allow_tf32=False)",
-                "launch": "whole step replayed as one CUDA graph" if getattr(self, "use_graph", True) else "eager launches",
+                "launch": ("eager launches" if not getattr(self, "use_graph", True) else
+                           "whole step replayed as one CUDA graph" if self.world == 1 else
+                           "step replayed as three CUDA graphs with the two NCCL all-reduces issued eagerly between them"),
                 "l2": "activations of one step (several GB) exceed L2; weights 488 MB", "weights": "random init"}
 
     def roofline(self, pk):

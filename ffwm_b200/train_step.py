@@ -39,12 +39,13 @@ class FFWMTrainer:
         self.device = torch.device(device)
         self._capturable = bool(graph)
         dev = self.device
-        self.flowNetF = base_networks.FlowNet(64).to(dev)
-        self.flowNetB = base_networks.FlowNet(64).to(dev)
-        self.warpNet = base_networks.WarpNet().to(dev).eval()
-        self.lightCNN = LightCNN_29Layers().to(dev).eval()
-        self.netG = base_networks.FFWM(sn=True).to(dev)
-        self.netD = base_networks.MSDiscriminator(128, sigmoid=False).to(dev)
+        with torch.device(dev):        # parameters are created and initialised on the device (122 M of them)
+            self.flowNetF = base_networks.FlowNet(64)
+            self.flowNetB = base_networks.FlowNet(64)
+            self.warpNet = base_networks.WarpNet().eval()
+            self.lightCNN = LightCNN_29Layers().eval()
+            self.netG = base_networks.FFWM(sn=True)
+            self.netD = base_networks.MSDiscriminator(128, sigmoid=False)
         for net, state in ((self.lightCNN, lightcnn_state), (self.flowNetF, flownetf_state), (self.flowNetB, flownetb_state)):
             if state is not None:
                 net.load_state_dict(state)
@@ -52,7 +53,8 @@ class FFWMTrainer:
 
         self.criterionL1 = torch.nn.L1Loss().to(dev)
         self.criterionIllu = losses.MSL1Loss(self.criterionL1).to(dev)
-        self.criterionPerceptual = losses.PerceptualLoss().to(dev)
+        with torch.device(dev):
+            self.criterionPerceptual = losses.PerceptualLoss()
         if vgg_weights is not None:
             self.criterionPerceptual.vgg.load_torchvision(vgg_weights)
         self.criterionIden = losses.IdentityLoss(self.lightCNN, crop=crop).to(dev)
