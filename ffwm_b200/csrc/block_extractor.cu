@@ -6,17 +6,17 @@
 // (xf + flow_x + j - k/2, yf + flow_y + i - k/2), tap indices clamped after
 // the weights are formed.
 //
-// Execution plan (not the reference's thread-per-element):
-//   forward   one thread per OUTPUT pixel walks a slice of channels: flow and
-//             the four weights/offsets are formed once, stores are coalesced
-//             and streamed, gathers hit L1/L2.
-//   backward  one thread per FLOW pixel x channel slice; loop (i,j) outside,
-//             channels inside, so geometry is formed k*k times per flow pixel
-//             instead of k*k*C times.  grad_source is a scatter (RED.ADD, as in
-//             the reference).  grad_flow — k*k*C contributions per address,
-//             the reference's worst atomic hotspot — is reduced in registers,
-//             then across the CTA's channel slices through shared memory, and
-//             stored once: no atomics, deterministic.
+// Execution plans (not the reference's thread-per-element):
+//   forward, k = 2,3 (fp32)  block_extractor_fwd_tiled_kernel: the k*k samples of a flow pixel share a
+//             (k+1)x(k+1) source window held in registers; output rows leave as full 128-byte
+//             stores through a per-warp shared-memory row; source rows are prefetched into L2/L1.
+//   backward, k = 2,3 (fp32) block_extractor_bwd_window_kernel: the same window folding for the
+//             scatter ((k+1)^2 REDs instead of 4*k*k per flow pixel and channel) and the gather.
+//   any other k / fp64       one thread per output pixel (forward) or per flow pixel x channel
+//             slice (backward); grad_source is a scatter (RED.ADD, as in the reference).
+//   grad_flow — k*k*C contributions per address, the reference's worst atomic hotspot — is always
+//   reduced in registers, then across the CTA's channel slices through shared memory, and stored
+//   once: no atomics, deterministic.
 #include <stdlib.h>
 
 #include "common.cuh"

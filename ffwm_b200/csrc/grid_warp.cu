@@ -10,12 +10,18 @@
 //   taps outside the image contribute nothing; d ix / d gx = W/2.
 //
 // Execution plan: the flow is read straight from the network's (B,2,H,W)
-// layout (no permuted copy); one thread owns one output pixel and walks a
-// slice of channels with the four weights/offsets/validity bits in registers.
-// Backward is one fused pass: grad_images is a scatter (RED.ADD), grad_flow
-// is reduced over channels in registers + across the CTA's channel slices in
-// shared memory and stored once (ATen does the same per-pixel reduction but
-// serially over all C in one thread).
+// layout (no permuted copy).
+//   Large fp32 maps of equal input/output size — TILED backward: grid_warp_tiled_kernel<1> (flow
+//   gradient) is a channel-lane gather (gather_tiled.cuh); grad_images is the destination-sorted
+//   scatter (scatter_tiled.cuh).  The tiled forward (<0>) exists but loses to the direct kernel
+//   for four taps and is opt-in (FFWM_GRID_WARP_TILED_FWD).  The model's own maps
+//   ((8,64,128,128), (8,64,64,64)) take this path, the 32x32 crops do not.
+//   Otherwise — DIRECT kernels: one thread owns one output pixel and walks a
+//   slice of channels with the four weights/offsets/validity bits in registers.
+//   Backward is one fused pass: grad_images is a scatter (RED.ADD), grad_flow
+//   is reduced over channels in registers + across the CTA's channel slices in
+//   shared memory and stored once (ATen does the same per-pixel reduction but
+//   serially over all C in one thread).
 #include "common.cuh"
 #include "gather_tiled.cuh"
 #include "scatter_tiled.cuh"
@@ -333,7 +339,10 @@ static int grid_warp_forward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, con
     if ((int64_t)out.n * out.c * out.h * out.w == 0) return FFWM_OK;
     if (out.n > 65535) { set_error("grid_warp: batch %d > 65535", out.n); return FFWM_ERR_TOO_LARGE; }
     if constexpr (sizeof(T) == 4) {
-        if (img.h == out.h && img.w == out.w && (int64_t)(img.h - 1) * img.sh + (int64_t)(img.w - 1) * img.sw < (1 << 30) &&
+        // measured at the cfg5 point: direct 0.38 ms (43 % of HBM) vs tiled 0.68 ms — with only four
+        // taps the slab fill costs more than the gather saves, so the tiled forward is opt-in
+        if (getenv("FFWM_GRID_WARP_TILED_FWD") && img.h == out.h && img.w == out.w &&
+            (int64_t)(img.h - 1) * img.sh + (int64_t)(img.w - 1) * img.sw < (1 << 30) &&
             gather_tiled_applicable(out.n, out.c, out.h, out.w, img)) {
             const int rc2 = launch_grid_warp_tiled<0>(img, flow, View<const float>{}, out, out.n, out.h, out.w, st);
             if (rc2) return rc2;

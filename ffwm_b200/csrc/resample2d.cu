@@ -1,20 +1,25 @@
-// resample2d: GFLA Gaussian-weighted flow resampling, forward + fused backward.
+// resample2d: GFLA Gaussian-weighted flow resampling, forward + backward.
 //
 // Semantics restate cuda/resample2d_package/resample2d_kernel.cu of the
 // reference (K1 :20-95, K2 :98-202, K3 :204-330) including its numerics
-// quirks.  The execution plan is different:
+// quirks.  The execution plans are different.
 //
+// Large fp32 maps (>= ~74 tiles of 16x16, >= 16 channels, kernel_size 2 or 4) — TILED kernels:
+//   forward        resample2d_fwd_tiled_kernel     channel-lane gather (gather_tiled.cuh); kernel_size 4
+//                  only — with 4 taps the direct kernel is faster (measured, profiles/README.md)
+//   grad_input1    scatter_tiled_kernel<Resample2dScatterGeo>  destination-sorted scatter, no
+//                  scattered REDs (scatter_tiled.cuh)
+//   grad_input2    resample2d_gflow_tiled_kernel   channel-lane gather of input1 + a packed warp
+//                  reduction over channels; deterministic, one store per pixel
+// Everything else (small maps, fp64, other kernel sizes, FFWM_DISABLE_TILED=1) — DIRECT kernels:
 //   * one thread owns one output PIXEL and walks a slice of the channels, so
 //     (dx,dy,sigma), the 4*(ks/2) double-precision exps, the tap offsets and
 //     the normaliser are computed once per pixel instead of once per element
 //     (the reference redoes them C times, and 3*C times in K3);
-//   * forward: HBM traffic is the algorithmic minimum (flow once, source
-//     through L1/L2 gathers, output streamed with coalesced stores);
 //   * backward: K2 and K3 are ONE pass over grad_output.  The scatter into
 //     grad_input1 uses RED.ADD (as the reference must); the flow gradient is
 //     reduced over channels in registers, across the channel slices of a CTA
-//     through shared memory, and stored once — no atomics, deterministic,
-//     and all three components (dx,dy,sigma) come out of the same pass.
+//     through shared memory, and stored once — no atomics, deterministic.
 #include "common.cuh"
 #include "gather_tiled.cuh"
 #include "scatter_tiled.cuh"
@@ -791,7 +796,9 @@ static int resample2d_forward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, co
     const int half = ks / 2;
     if constexpr (sizeof(T) == 4) {
         const int hmax = (15 - (2 * half - 1) * dil) / 2;
-        if ((half == 1 || half == 2) && dil >= 1 && hmax >= 2 && in1.n >= out.n &&
+        // 16-tap kernels only: with 4 taps the direct kernel (0.54 ms at the cfg5 point) beats the
+        // tiled one (0.78 ms), whose slab fill then outweighs the gather it saves
+        if (half == 2 && dil >= 1 && hmax >= 2 && in1.n >= out.n &&
             (int64_t)(in1.h - 1) * in1.sh + (int64_t)(in1.w - 1) * in1.sw < (1 << 30) &&
             gather_tiled_applicable(out.n, out.c, out.h, out.w, in1)) {
             const int ml = hmax + (half - 1) * dil;

@@ -430,12 +430,12 @@ def test_grid_warp_tiled_scatter_matches_direct_and_torch(ops, noise):
         del os.environ["FFWM_DISABLE_TILED"]
     assert rel_err(gi_t, gi_d) <= 2e-5 and rel_err(gf_t, gf_d) <= 5e-5
     out_t, out_d = torch.empty_like(d[0]), torch.empty_like(d[0])
-    ops.grid_warp_forward(d[0], d[1], out_t)
-    os.environ["FFWM_DISABLE_TILED"] = "1"
+    os.environ["FFWM_GRID_WARP_TILED_FWD"] = "1"          # the tiled forward is opt-in
     try:
-        ops.grid_warp_forward(d[0], d[1], out_d)
+        ops.grid_warp_forward(d[0], d[1], out_t)
     finally:
-        del os.environ["FFWM_DISABLE_TILED"]
+        del os.environ["FFWM_GRID_WARP_TILED_FWD"]
+    ops.grid_warp_forward(d[0], d[1], out_d)
     assert torch.equal(out_t, out_d)                      # same arithmetic, term by term
     x = img.double().requires_grad_(True)
     gr = grid.double().requires_grad_(True)
