@@ -39,6 +39,9 @@ SIGNATURES = {
     "ffwm_local_attn_reshape_backward": [_T4P, _T4P, _I, _I, _VP],
     "ffwm_grid_warp_forward": [_T4P, _T4P, _T4P, _I, _VP],
     "ffwm_grid_warp_backward": [_T4P, _T4P, _T4P, _T4P, _T4P, _I, _VP],
+    "ffwm_conv3x3_packed_floats": [_I, _I],
+    "ffwm_conv3x3_pack_weights": [_T4P, _I, _VP, ctypes.c_int64, _VP],
+    "ffwm_conv3x3_forward": [_T4P, _VP, _VP, _T4P, _VP],
 }
 
 _lib = None
@@ -62,7 +65,8 @@ def lib():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(l, name)          # AttributeError if the symbol is not exported
             fn.argtypes = argtypes
-            fn.restype = {"ffwm_last_error": ctypes.c_char_p, "ffwm_kernel_launches": ctypes.c_ulonglong}.get(name, ctypes.c_int)
+            fn.restype = {"ffwm_last_error": ctypes.c_char_p, "ffwm_kernel_launches": ctypes.c_ulonglong,
+                          "ffwm_conv3x3_packed_floats": ctypes.c_int64}.get(name, ctypes.c_int)
         if l.ffwm_abi_version() != ABI_VERSION:
             raise ImportError("ffwm_b200: ABI version mismatch (library %d, binding %d)"
                               % (l.ffwm_abi_version(), ABI_VERSION))

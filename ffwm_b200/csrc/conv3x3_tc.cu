@@ -1,0 +1,308 @@
+// conv3x3_tc: 3x3 / stride 1 / pad 1 convolution on the 5th-generation tensor cores (tcgen05),
+// fp32 in, fp32 out, fp32-level accuracy through a 3xTF32 operand split.
+//
+// Where it is used: the dense 3x3 convolutions at 128x128 that dominate the FFWM generator
+// (dres2: 195->195, att2: 128->128; SURVEY.md 8a a13 — 62 of netG's 105 GFLOP/image) and their
+// data gradients (same kernel, weights packed transposed + flipped).  The reference runs them on
+// cuDNN; under its fp32 parity target that means SIMT FFMA kernels (~35 TFLOP/s measured in the
+// train step).  Here they are implicit GEMMs on tcgen05:
+//
+//   D[pixel, co] += A[pixel, ci] * B[co, ci]      for each of the 9 taps, ci in blocks of 8
+//
+//   * M = 128 pixels = ONE image row (W must be 128), so TMEM lane = x and the epilogue's global
+//     stores are 128-byte coalesced rows of the NCHW output; N = 64 output channels; a CTA owns
+//     4 output rows x 64 channels = 4 accumulators = 256 TMEM columns.
+//   * A (activations) is staged K-major without swizzle as [k-chunk][slot][4 channels]: 16 bytes
+//     per pixel slot, slot = x + 1 with explicit zero halo slots, so the three horizontal taps
+//     are the SAME shared-memory row read through descriptors whose start address differs by
+//     16 bytes; the three vertical taps are neighbouring row buffers (6 input rows serve 4 output
+//     rows).  The NCHW -> K-major transposition happens in the staging threads (4 coalesced
+//     loads -> one 16-byte shared store).
+//   * B (weights) is pre-packed once per weight update into exactly the shared-memory image the
+//     MMA wants, hi and lo parts already split, and copied in with 16-byte loads/stores.
+//   * fp32 accuracy: every operand is split a = hi + lo with hi = a & 0xffffe000 (exactly
+//     representable in TF32) and lo = a - hi; three MMAs hi*hi + hi*lo + lo*hi accumulate in
+//     fp32 in TMEM (the dropped lo*lo term is < 2^-21 relative).
+//   * one thread issues the 108 MMAs of a K block (4 rows x 9 taps x 3 split terms) and commits
+//     them to an mbarrier; the other 255 threads meanwhile stage the next K block into the other
+//     buffer (2-stage pipeline).
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace ffwm {
+
+constexpr int CV_ROWS = 4;             // output rows per CTA
+constexpr int CV_W = 128;              // image width = MMA M
+constexpr int CV_NT = 64;              // output channels per CTA = MMA N
+constexpr int CV_KB = 8;               // input channels per K block = one tf32 MMA K
+constexpr int CV_SLOTS = 136;          // pixel slots per row buffer (130 used, 16-byte each per k-chunk)
+constexpr int CV_THREADS = 256;
+constexpr int CV_IN_ROWS = CV_ROWS + 2;
+
+// bytes
+constexpr int CV_A_CHUNK = CV_SLOTS * 16;                 // one k-chunk (4 channels) of one row
+constexpr int CV_A_ROW = 2 * CV_A_CHUNK;                  // both k-chunks
+constexpr int CV_A_PART = CV_IN_ROWS * CV_A_ROW;          // all rows, hi or lo
+constexpr int CV_A_STAGE = 2 * CV_A_PART;                 // hi + lo
+constexpr int CV_B_CHUNK = CV_NT * 16;                    // one k-chunk of one tap: 64 co x 4 ci
+constexpr int CV_B_TAP = 2 * CV_B_CHUNK;                  // both k-chunks
+constexpr int CV_B_PART = 9 * CV_B_TAP;                   // all taps, hi or lo... (layout: [tap][hl][kchunk])
+constexpr int CV_B_STAGE = 2 * CV_B_PART;
+constexpr int CV_STAGE = CV_A_STAGE + CV_B_STAGE;
+constexpr int CV_SMEM = 2 * CV_STAGE + 64;                // + barriers / tmem address
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address,
+// leading byte offset (between the two 16-byte k-chunks), stride byte offset (between 8-row
+// groups), all in 16-byte units; version 1 (Blackwell); layout type 0 (SWIZZLE_NONE).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46);
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+// Bounded wait: a protocol error traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spin > (1u << 26)) __trap();
+    }
+}
+
+// ---------------------------------------------------------------- weight packing
+// w (Cout, Cin, 3, 3) -> packed[cob][kb][tap][hl][kchunk][co_local 64][4 ci]  (hl: 0 = hi, 1 = lo)
+// dgrad = 1 packs the weights of the data-gradient convolution: roles of Cout/Cin swapped and the
+// taps flipped, so that conv3x3(grad_output, packed) = grad_input.
+__global__ void conv3x3_pack_kernel(const float* __restrict__ w, float* __restrict__ packed, int cout, int cin, int dgrad,
+                                    int64_t s_co, int64_t s_ci, int64_t s_ky, int64_t s_kx) {
+    const int n_out = dgrad ? cin : cout, n_in = dgrad ? cout : cin;     // of the convolution being packed
+    const int ncob = (n_out + CV_NT - 1) / CV_NT, nkb = (n_in + CV_KB - 1) / CV_KB;
+    const int64_t total = (int64_t)ncob * nkb * 9 * 2 * CV_NT * 4;       // (hi,lo) pairs are written together
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i;
+        const int j = r % 4; r /= 4;
+        const int col = r % CV_NT; r /= CV_NT;
+        const int kc = r % 2; r /= 2;
+        const int tap = r % 9; r /= 9;
+        const int kb = r % nkb; r /= nkb;
+        const int cob = (int)r;
+        const int o = cob * CV_NT + col, c = kb * CV_KB + kc * 4 + j;
+        float v = 0.f;
+        if (o < n_out && c < n_in) {
+            const int ky = tap / 3, kx = tap % 3;
+            v = dgrad ? w[c * s_co + o * s_ci + (2 - ky) * s_ky + (2 - kx) * s_kx]
+                      : w[o * s_co + c * s_ci + ky * s_ky + kx * s_kx];
+        }
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        const float lo = v - hi;
+        const int64_t base = ((((int64_t)cob * nkb + kb) * 9 + tap) * 2) * (2 * CV_NT * 4);
+        const int64_t within = ((int64_t)kc * CV_NT + col) * 4 + j;
+        packed[base + within] = hi;
+        packed[base + 2 * CV_NT * 4 + within] = lo;
+    }
+}
+
+// ---------------------------------------------------------------- the convolution
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const float* __restrict__ bias,
+                  View<float> out, int nkb) {
+    extern __shared__ __align__(128) unsigned char cv_smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cv_smem + 2 * CV_STAGE);    // [0],[1]: MMAs of buffer done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cv_smem + 2 * CV_STAGE + 32);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int y0 = blockIdx.x * CV_ROWS, cob = blockIdx.y, b = blockIdx.z;
+    const int ncob = gridDim.y;
+    (void)ncob;
+
+    // ---- one-time setup: zero both A stages (halo slots and out-of-image rows stay zero), barriers, TMEM
+    for (int i = tid; i < (2 * CV_STAGE) / 16; i += CV_THREADS) reinterpret_cast<float4*>(cv_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(CV_ROWS * CV_NT) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    // ---- staging of one K block into stage buffer `buf`
+    const float* pk_base = packed + ((int64_t)cob * nkb) * (CV_B_STAGE / 4);
+    auto stage = [&](int kb, int buf) {
+        unsigned char* sA = cv_smem + buf * CV_STAGE;
+        unsigned char* sB = sA + CV_A_STAGE;
+        // weights: straight 16-byte copy of the pre-packed image, re-ordered [tap][hl] -> [hl][tap]... kept as packed:
+        // packed layout per (cob,kb): [tap][hl][kchunk][co][4]  == CV_B_STAGE bytes
+        const float4* src = reinterpret_cast<const float4*>(pk_base + (int64_t)kb * (CV_B_STAGE / 4));
+        float4* dstB = reinterpret_cast<float4*>(sB);
+#pragma unroll
+        for (int i = 0; i < CV_B_STAGE / 16 / CV_THREADS; ++i) dstB[i * CV_THREADS + tid] = __ldg(src + i * CV_THREADS + tid);
+        // activations: task = (input row rr, k-chunk kc, pixel px); 4 channel loads -> hi/lo 16-byte stores
+        const int c_base = kb * CV_KB;
+        for (int t = tid; t < CV_IN_ROWS * 2 * CV_W; t += CV_THREADS) {
+            const int px = t & (CV_W - 1), kc = (t >> 7) & 1, rr = t >> 8;
+            const int yy = y0 - 1 + rr;
+            if ((unsigned)yy >= (unsigned)x.h) continue;                 // stays zero
+            const float* gp = x.p + b * x.sb + (int64_t)(c_base + kc * 4) * x.sc + yy * x.sh + px * x.sw;
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = (c_base + kc * 4 + j < x.c) ? __ldg(gp + (int64_t)j * x.sc) : 0.f;
+            float4 hi, lo;
+            hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u); lo.x = v[0] - hi.x;
+            hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u); lo.y = v[1] - hi.y;
+            hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u); lo.z = v[2] - hi.z;
+            hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u); lo.w = v[3] - hi.w;
+            unsigned char* d = sA + rr * CV_A_ROW + kc * CV_A_CHUNK + (px + 1) * 16;
+            *reinterpret_cast<float4*>(d) = hi;
+            *reinterpret_cast<float4*>(d + CV_A_PART) = lo;
+        }
+    };
+
+    constexpr uint32_t IDESC = umma_idesc_tf32(CV_W, CV_NT);
+    stage(0, 0);
+    for (int kb = 0; kb < nkb; ++kb) {
+        const int cur = kb & 1;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // staged data -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sA = smem_u32(cv_smem + cur * CV_STAGE), sB = sA + CV_A_STAGE;
+#pragma unroll 1
+            for (int r = 0; r < CV_ROWS; ++r) {
+#pragma unroll 1
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int ky = tap / 3, kx = tap - ky * 3;
+                    const uint32_t a_hi = sA + (r + ky) * CV_A_ROW + kx * 16, a_lo = a_hi + CV_A_PART;
+                    const uint32_t b_hi = sB + tap * (2 * CV_B_TAP), b_lo = b_hi + CV_B_TAP;
+                    const uint64_t dA_hi = umma_desc(a_hi, CV_A_CHUNK, 128), dA_lo = umma_desc(a_lo, CV_A_CHUNK, 128);
+                    const uint64_t dB_hi = umma_desc(b_hi, CV_B_CHUNK, 128), dB_lo = umma_desc(b_lo, CV_B_CHUNK, 128);
+                    const uint32_t d = tmem + r * CV_NT;
+                    umma_tf32(d, dA_hi, dB_hi, IDESC, kb > 0 || tap > 0);
+                    umma_tf32(d, dA_hi, dB_lo, IDESC, true);
+                    umma_tf32(d, dA_lo, dB_hi, IDESC, true);
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[cur])) : "memory");
+        }
+        if (kb + 1 < nkb) {
+            if (kb >= 1) mbar_wait(&bars[cur ^ 1], ((kb - 1) >> 1) & 1);   // MMAs that read the other buffer are done
+            stage(kb + 1, cur ^ 1);
+        }
+    }
+    mbar_wait(&bars[(nkb - 1) & 1], ((nkb - 1) >> 1) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue: TMEM -> registers -> NCHW global (lane = x, coalesced per channel)
+    {
+        const int q = warp & 3, half = warp >> 2;                      // TMEM lane quarter, column half
+        const int px = q * 32 + lane;
+#pragma unroll 1
+        for (int r = 0; r < CV_ROWS; ++r) {
+            const int y = y0 + r;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int col0 = half * 32 + cc * 16;
+                uint32_t v[16];
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * CV_NT + col0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (y < out.h && px < out.w) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int co = cob * CV_NT + col0 + j;
+                        if (co < out.c) {
+                            float o = __uint_as_float(v[j]);
+                            if (bias) o += __ldg(bias + co);
+                            st_stream(out.p + b * out.sb + (int64_t)co * out.sc + y * out.sh + px * out.sw, o);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(CV_ROWS * CV_NT) : "memory");
+}
+
+}  // namespace ffwm
+
+extern "C" int64_t ffwm_conv3x3_packed_floats(int cout, int cin) {
+    if (cout <= 0 || cin <= 0) return 0;
+    const int64_t ncob = (cout + ffwm::CV_NT - 1) / ffwm::CV_NT, nkb = (cin + ffwm::CV_KB - 1) / ffwm::CV_KB;
+    return ncob * nkb * (ffwm::CV_B_STAGE / 4);
+}
+
+extern "C" int ffwm_conv3x3_pack_weights(const ffwm_tensor4* weight, int dgrad, float* packed, int64_t packed_floats, void* stream) {
+    using namespace ffwm;
+    if (!weight || !weight->data || !packed) { set_error("conv3x3_pack_weights: null pointer"); return FFWM_ERR_NULL; }
+    if (weight->size[2] != 3 || weight->size[3] != 3) { set_error("conv3x3_pack_weights: kernel must be 3x3"); return FFWM_ERR_SHAPE; }
+    const int cout = (int)weight->size[0], cin = (int)weight->size[1];
+    const int64_t need = dgrad ? ffwm_conv3x3_packed_floats(cin, cout) : ffwm_conv3x3_packed_floats(cout, cin);
+    if (packed_floats < need) { set_error("conv3x3_pack_weights: packed buffer too small (%lld < %lld floats)", (long long)packed_floats, (long long)need); return FFWM_ERR_SHAPE; }
+    const int64_t pairs = need / 2;
+    const int blocks = (int)std::min<int64_t>((pairs + 255) / 256, 4096);
+    conv3x3_pack_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float*>(weight->data), packed, cout, cin, dgrad, weight->stride[0], weight->stride[1], weight->stride[2], weight->stride[3]);
+    return check_launch("conv3x3_pack_weights");
+}
+
+// conv2d(x, w, bias, stride 1, padding 1) for 3x3 kernels with `packed` = pack_weights(w): x (B,Cin,H,128) fp32,
+// out (B,Cout,H,128) fp32.  Replaces the cuDNN call behind nn.Conv2d(…, 3, 1, 1) for those shapes.
+extern "C" int ffwm_conv3x3_forward(const ffwm_tensor4* x, const float* packed, const float* bias, const ffwm_tensor4* out, void* stream) {
+    using namespace ffwm;
+    View<const float> xv;
+    View<float> ov;
+    int rc;
+    if ((rc = make_view<const float>(x, "x", &xv))) return rc;
+    if ((rc = make_view<float>(out, "out", &ov))) return rc;
+    if (!packed) { set_error("conv3x3_forward: null packed weights"); return FFWM_ERR_NULL; }
+    if (xv.w != CV_W || ov.w != CV_W || xv.h != ov.h || xv.n != ov.n) {
+        set_error("conv3x3_forward: needs W == %d and equal N,H (x %dx%dx%dx%d, out %dx%dx%dx%d)", CV_W, xv.n, xv.c, xv.h, xv.w, ov.n, ov.c, ov.h, ov.w);
+        return FFWM_ERR_SHAPE;
+    }
+    if ((int64_t)ov.n * ov.c * ov.h == 0) return FFWM_OK;
+    const int ncob = ceil_div(ov.c, CV_NT), nkb = ceil_div(xv.c, CV_KB);
+    if (ov.n > 65535 || ncob > 65535) { set_error("conv3x3_forward: grid too large"); return FFWM_ERR_TOO_LARGE; }
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM);
+    if (e != cudaSuccess) { set_error("conv3x3_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
+    dim3 grid(ceil_div(ov.h, CV_ROWS), ncob, ov.n);
+    conv3x3_tc_kernel<<<grid, CV_THREADS, CV_SMEM, static_cast<cudaStream_t>(stream)>>>(xv, packed, bias, ov, nkb);
+    return check_launch("conv3x3_forward");
+}

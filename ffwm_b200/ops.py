@@ -51,3 +51,22 @@ def grid_warp_backward(images, flow, grad_output, grad_images, grad_flow):
     dev = L.require_cuda(images, flow, grad_output, grad_images, grad_flow)
     L.call("ffwm_grid_warp_backward", dev, L.t4(images), L.t4(flow), L.t4(grad_output),
            L.t4(grad_images), L.t4(grad_flow), L.dtype_code(images))
+
+
+def conv3x3_pack_weights(weight, dgrad=False):
+    """(Cout,Cin,3,3) fp32 CUDA weight -> packed image for conv3x3_forward (dgrad: for the data gradient)."""
+    import ctypes
+    import torch
+    dev = L.require_cuda(weight)
+    cout, cin = weight.shape[:2]
+    n = L.lib().ffwm_conv3x3_packed_floats(int(cin if dgrad else cout), int(cout if dgrad else cin))
+    packed = torch.empty(n, dtype=torch.float32, device=weight.device)
+    L.call("ffwm_conv3x3_pack_weights", dev, L.t4(weight), int(bool(dgrad)), ctypes.c_void_p(packed.data_ptr()), ctypes.c_int64(n))
+    return packed
+
+
+def conv3x3_forward(x, packed, bias, out):
+    import ctypes
+    dev = L.require_cuda(x, packed, out)
+    L.call("ffwm_conv3x3_forward", dev, L.t4(x), ctypes.c_void_p(packed.data_ptr()),
+           ctypes.c_void_p(bias.data_ptr() if bias is not None else None), L.t4(out))

@@ -1,0 +1,57 @@
+"""tcgen05 3x3 convolution (ffwm_b200/csrc/conv3x3_tc.cu) against PyTorch float64 on the same inputs.
+Tolerance: 2e-5 relative to max|ref| (3xTF32 split: fp32-level accuracy), stated per SURVEY 7 "hard parts"."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from ffwm_b200 import ops as o
+    return o
+
+
+@pytest.mark.parametrize("b,cin,cout,h", [(1, 8, 64, 4), (2, 16, 64, 8), (1, 3, 64, 128), (2, 195, 195, 10),
+                                          (1, 128, 128, 128), (1, 64, 3, 7), (1, 20, 130, 5)])
+def test_conv3x3_forward_matches_fp64(ops, b, cin, cout, h):
+    g = torch.Generator().manual_seed(cin * 1000 + cout)
+    x = torch.randn(b, cin, h, 128, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    bias = torch.randn(cout, generator=g)
+    want = F.conv2d(x.double(), w.double(), bias.double(), padding=1)
+    xd, wd, bd = x.to(DEV), w.to(DEV), bias.to(DEV)
+    packed = ops.conv3x3_pack_weights(wd)
+    out = torch.full((b, cout, h, 128), float("nan"), device=DEV)
+    ops.conv3x3_forward(xd, packed, bd, out)
+    torch.cuda.synchronize()
+    assert rel(out.cpu(), want) <= 2e-5
+    out2 = torch.empty_like(out)
+    ops.conv3x3_forward(xd, packed, None, out2)
+    assert rel(out2.cpu(), want - bias.double().view(1, -1, 1, 1)) <= 2e-5
+
+
+def test_conv3x3_dgrad_packing(ops):
+    g = torch.Generator().manual_seed(5)
+    b, cin, cout, h = 2, 24, 70, 9
+    x = torch.randn(b, cin, h, 128, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(cout, cin, 3, 3, generator=g, dtype=torch.float64) / (cin * 9) ** 0.5
+    go = torch.randn(b, cout, h, 128, generator=g, dtype=torch.float64)
+    F.conv2d(x, w, None, padding=1).backward(go)
+    packed = ops.conv3x3_pack_weights(w.float().to(DEV), dgrad=True)
+    gx = torch.empty(b, cin, h, 128, device=DEV)
+    ops.conv3x3_forward(go.float().to(DEV), packed, None, gx)
+    assert rel(gx.cpu(), x.grad) <= 2e-5
+
+
+def test_conv3x3_rejects_other_widths(ops):
+    x = torch.zeros(1, 8, 4, 64, device=DEV)
+    packed = ops.conv3x3_pack_weights(torch.zeros(8, 8, 3, 3, device=DEV))
+    with pytest.raises(RuntimeError):
+        ops.conv3x3_forward(x, packed, None, torch.zeros(1, 8, 4, 64, device=DEV))
