@@ -1,0 +1,72 @@
+"""3x3 convolution microbench: the hand-written tcgen05 kernel (3xTF32, fp32-level accuracy) vs cuDNN
+in strict fp32 and in TF32, on the generator's dominant shapes, B = 8, 128x128.
+
+    python -m benchmarks.conv [--out gpurun_out/conv.json]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def timeit(fn, iters=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "conv.json"))
+    args = ap.parse_args()
+    from ffwm_b200 import ops
+    dev = torch.device("cuda", 0)
+    torch.backends.cudnn.benchmark = True
+    rows = []
+    for name, cin, cout in (("dres2 195->195", 195, 195), ("att2 128->128", 128, 128), ("e0 res 64->64", 64, 64),
+                            ("vgg relu1_2 64->64", 64, 64), ("256->256", 256, 256)):
+        x = torch.randn(8, cin, 128, 128, device=dev)
+        w = torch.randn(cout, cin, 3, 3, device=dev) / (cin * 9) ** 0.5
+        b = torch.randn(cout, device=dev)
+        out = torch.empty(8, cout, 128, 128, device=dev)
+        packed = ops.conv3x3_pack_weights(w)
+        flop = 2.0 * 8 * 128 * 128 * cin * cout * 9
+        t_mine = timeit(lambda: ops.conv3x3_forward(x, packed, b, out))
+        t_pack = timeit(lambda: ops.conv3x3_pack_weights(w))
+        torch.backends.cudnn.allow_tf32 = False
+        t_fp32 = timeit(lambda: F.conv2d(x, w, b, padding=1))
+        ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+        err_mine = float((out.double() - ref).abs().max() / ref.abs().max())
+        err_fp32 = float((F.conv2d(x, w, b, padding=1).double() - ref).abs().max() / ref.abs().max())
+        torch.backends.cudnn.allow_tf32 = True
+        t_tf32 = timeit(lambda: F.conv2d(x, w, b, padding=1))
+        err_tf32 = float((F.conv2d(x, w, b, padding=1).double() - ref).abs().max() / ref.abs().max())
+        rows.append(dict(shape=name, cin=cin, cout=cout, gflop=flop / 1e9, ms_tcgen05=t_mine, ms_pack=t_pack,
+                         ms_cudnn_fp32=t_fp32, ms_cudnn_tf32=t_tf32, tflops_tcgen05=flop / t_mine / 1e9,
+                         tflops_tensor_issued=3 * flop / t_mine / 1e9, err_tcgen05=err_mine, err_cudnn_fp32=err_fp32,
+                         err_cudnn_tf32=err_tf32))
+        del ref
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    json.dump(rows, open(args.out, "w"), indent=1)
+    print("%-20s %8s %8s %8s %8s %8s %9s %9s %9s" % ("shape", "tc ms", "pack ms", "fp32 ms", "tf32 ms", "TF/s", "err tc", "err fp32", "err tf32"))
+    for r in rows:
+        print("%-20s %8.3f %8.3f %8.3f %8.3f %8.1f %9.1e %9.1e %9.1e" % (
+            r["shape"], r["ms_tcgen05"], r["ms_pack"], r["ms_cudnn_fp32"], r["ms_cudnn_tf32"], r["tflops_tcgen05"],
+            r["err_tcgen05"], r["err_cudnn_fp32"], r["err_cudnn_tf32"]))
+
+
+if __name__ == "__main__":
+    main()

@@ -23,9 +23,10 @@
 //   * fp32 accuracy: every operand is split a = hi + lo with hi = a & 0xffffe000 (exactly
 //     representable in TF32) and lo = a - hi; three MMAs hi*hi + hi*lo + lo*hi accumulate in
 //     fp32 in TMEM (the dropped lo*lo term is < 2^-21 relative).
-//   * one thread issues the 108 MMAs of a K block (4 rows x 9 taps x 3 split terms) and commits
-//     them to an mbarrier; the other 255 threads meanwhile stage the next K block into the other
-//     buffer (2-stage pipeline).
+//   * warp-specialised 2-stage pipeline on mbarriers: 8 producer warps stage the activations of
+//     K block k+1 while one elected thread of a 9th warp has the 108 MMAs of block k in flight
+//     (4 rows x 9 taps x 3 split terms, committed to an mbarrier with tcgen05.commit) and pulls the
+//     next packed weight tile with one bulk async copy (cp.async.bulk + complete_tx).
 #include <stdint.h>
 
 #include <algorithm>
@@ -52,7 +53,7 @@ constexpr int CV_B_TAP = 2 * CV_B_CHUNK;                  // both k-chunks
 constexpr int CV_B_PART = 9 * CV_B_TAP;                   // all taps, hi or lo... (layout: [tap][hl][kchunk])
 constexpr int CV_B_STAGE = 2 * CV_B_PART;
 constexpr int CV_STAGE = CV_A_STAGE + CV_B_STAGE;
-constexpr int CV_SMEM = 2 * CV_STAGE + 64;                // + barriers / tmem address
+constexpr int CV_SMEM = 2 * CV_STAGE + 64;                // + 6 mbarriers + tmem address
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -130,102 +131,131 @@ __global__ void conv3x3_pack_kernel(const float* __restrict__ w, float* __restri
 }
 
 // ---------------------------------------------------------------- the convolution
-__global__ void __launch_bounds__(CV_THREADS, 1)
+// Warp roles (288 threads): warps 0-7 stage activations (producers) and run the epilogue; warp 8
+// lane 0 copies the packed weights with one bulk async copy per K block and issues the MMAs.
+// Pipeline state lives in mbarriers: fullA[2] (256 producer arrivals), fullB[2] (bulk-copy
+// transaction bytes), empty[2] (tcgen05.commit of the MMAs that read the buffer).
+constexpr int CV_PRODUCERS = 256;
+
+__device__ __forceinline__ void umma_tf32_acc(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(CV_PRODUCERS + 32, 1)
 conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const float* __restrict__ bias,
                   View<float> out, int nkb) {
     extern __shared__ __align__(128) unsigned char cv_smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(cv_smem + 2 * CV_STAGE);    // [0],[1]: MMAs of buffer done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cv_smem + 2 * CV_STAGE + 32);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cv_smem + 2 * CV_STAGE);    // fullA[0,1] fullB[2,3] empty[4,5]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cv_smem + 2 * CV_STAGE + 48);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int y0 = blockIdx.x * CV_ROWS, cob = blockIdx.y, b = blockIdx.z;
-    const int ncob = gridDim.y;
-    (void)ncob;
 
-    // ---- one-time setup: zero both A stages (halo slots and out-of-image rows stay zero), barriers, TMEM
-    for (int i = tid; i < (2 * CV_STAGE) / 16; i += CV_THREADS) reinterpret_cast<float4*>(cv_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // ---- one-time setup: zero both stages (halo slots and out-of-image rows stay zero), barriers, TMEM
+    for (int i = tid; i < (2 * CV_STAGE) / 16; i += CV_PRODUCERS + 32) reinterpret_cast<float4*>(cv_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        mbar_init(&bars[0], CV_PRODUCERS);
+        mbar_init(&bars[1], CV_PRODUCERS);
+        mbar_init(&bars[2], 1);
+        mbar_init(&bars[3], 1);
+        mbar_init(&bars[4], 1);
+        mbar_init(&bars[5], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(CV_ROWS * CV_NT) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // the zero fill, before any async-proxy access
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
-
-    // ---- staging of one K block into stage buffer `buf`
     const float* pk_base = packed + ((int64_t)cob * nkb) * (CV_B_STAGE / 4);
-    auto stage = [&](int kb, int buf) {
-        unsigned char* sA = cv_smem + buf * CV_STAGE;
-        unsigned char* sB = sA + CV_A_STAGE;
-        // weights: straight 16-byte copy of the pre-packed image, re-ordered [tap][hl] -> [hl][tap]... kept as packed:
-        // packed layout per (cob,kb): [tap][hl][kchunk][co][4]  == CV_B_STAGE bytes
-        const float4* src = reinterpret_cast<const float4*>(pk_base + (int64_t)kb * (CV_B_STAGE / 4));
-        float4* dstB = reinterpret_cast<float4*>(sB);
-#pragma unroll
-        for (int i = 0; i < CV_B_STAGE / 16 / CV_THREADS; ++i) dstB[i * CV_THREADS + tid] = __ldg(src + i * CV_THREADS + tid);
-        // activations: task = (input row rr, k-chunk kc, pixel px); 4 channel loads -> hi/lo 16-byte stores
-        const int c_base = kb * CV_KB;
-        for (int t = tid; t < CV_IN_ROWS * 2 * CV_W; t += CV_THREADS) {
-            const int px = t & (CV_W - 1), kc = (t >> 7) & 1, rr = t >> 8;
-            const int yy = y0 - 1 + rr;
-            if ((unsigned)yy >= (unsigned)x.h) continue;                 // stays zero
-            const float* gp = x.p + b * x.sb + (int64_t)(c_base + kc * 4) * x.sc + yy * x.sh + px * x.sw;
-            float v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = (c_base + kc * 4 + j < x.c) ? __ldg(gp + (int64_t)j * x.sc) : 0.f;
-            float4 hi, lo;
-            hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u); lo.x = v[0] - hi.x;
-            hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u); lo.y = v[1] - hi.y;
-            hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u); lo.z = v[2] - hi.z;
-            hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u); lo.w = v[3] - hi.w;
-            unsigned char* d = sA + rr * CV_A_ROW + kc * CV_A_CHUNK + (px + 1) * 16;
-            *reinterpret_cast<float4*>(d) = hi;
-            *reinterpret_cast<float4*>(d + CV_A_PART) = lo;
-        }
-    };
 
-    constexpr uint32_t IDESC = umma_idesc_tf32(CV_W, CV_NT);
-    stage(0, 0);
-    for (int kb = 0; kb < nkb; ++kb) {
-        const int cur = kb & 1;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // staged data -> visible to the tensor core
-        __syncthreads();
-        if (tid == 0) {
+    if (warp < CV_PRODUCERS / 32) {
+        // ================= producers: activations of K block kb -> stage buffer kb & 1 =================
+        // thread -> (pixel px, k-chunk kc); it loads 4 channels x 6 input rows (24 loads in flight),
+        // splits hi/lo and writes one 16-byte slot per row and part
+        const int px = tid & (CV_W - 1), kc = tid >> 7;
+        bool row_ok[CV_IN_ROWS];
+#pragma unroll
+        for (int rr = 0; rr < CV_IN_ROWS; ++rr) row_ok[rr] = (unsigned)(y0 - 1 + rr) < (unsigned)x.h;
+        const float* gp0 = x.p + b * x.sb + (int64_t)(y0 - 1) * x.sh + px * x.sw;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int buf = kb & 1;
+            if (kb >= 2) mbar_wait(&bars[4 + buf], ((kb >> 1) - 1) & 1);          // MMAs of K block kb-2 done
+            const int c0 = kb * CV_KB + kc * 4;
+            float v[CV_IN_ROWS][4];
+#pragma unroll
+            for (int rr = 0; rr < CV_IN_ROWS; ++rr)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    v[rr][j] = (row_ok[rr] && c0 + j < x.c) ? __ldg(gp0 + (int64_t)(c0 + j) * x.sc + rr * x.sh) : 0.f;
+            unsigned char* d = cv_smem + buf * CV_STAGE + kc * CV_A_CHUNK + (px + 1) * 16;
+#pragma unroll
+            for (int rr = 0; rr < CV_IN_ROWS; ++rr) {
+                if (!row_ok[rr]) continue;                                       // stays zero
+                float4 hi, lo;
+                hi.x = __uint_as_float(__float_as_uint(v[rr][0]) & 0xffffe000u); lo.x = v[rr][0] - hi.x;
+                hi.y = __uint_as_float(__float_as_uint(v[rr][1]) & 0xffffe000u); lo.y = v[rr][1] - hi.y;
+                hi.z = __uint_as_float(__float_as_uint(v[rr][2]) & 0xffffe000u); lo.z = v[rr][2] - hi.z;
+                hi.w = __uint_as_float(__float_as_uint(v[rr][3]) & 0xffffe000u); lo.w = v[rr][3] - hi.w;
+                *reinterpret_cast<float4*>(d + rr * CV_A_ROW) = hi;
+                *reinterpret_cast<float4*>(d + rr * CV_A_ROW + CV_A_PART) = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // my stores -> visible to the tensor core
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[buf])) : "memory");
+        }
+    } else if (lane == 0) {
+        // ================= issuer: weight copies + MMAs =================
+        constexpr uint32_t IDESC = umma_idesc_tf32(CV_W, CV_NT);
+        auto copy_b = [&](int kb) {
+            const int buf = kb & 1;
+            const uint32_t bar = smem_u32(&bars[2 + buf]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(CV_B_STAGE) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(cv_smem + buf * CV_STAGE + CV_A_STAGE)),
+                         "l"(pk_base + (int64_t)kb * (CV_B_STAGE / 4)), "r"(CV_B_STAGE), "r"(bar)
+                         : "memory");
+        };
+        copy_b(0);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int buf = kb & 1;
+            mbar_wait(&bars[buf], (kb >> 1) & 1);            // activations staged
+            mbar_wait(&bars[2 + buf], (kb >> 1) & 1);        // weights landed
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sA = smem_u32(cv_smem + cur * CV_STAGE), sB = sA + CV_A_STAGE;
-#pragma unroll 1
+            const uint32_t sA = smem_u32(cv_smem + buf * CV_STAGE), sB = sA + CV_A_STAGE;
+            const uint64_t dA0 = umma_desc(sA, CV_A_CHUNK, 128), dB0 = umma_desc(sB, CV_B_CHUNK, 128);
+#pragma unroll
             for (int r = 0; r < CV_ROWS; ++r) {
-#pragma unroll 1
+#pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
-                    const int ky = tap / 3, kx = tap - ky * 3;
-                    const uint32_t a_hi = sA + (r + ky) * CV_A_ROW + kx * 16, a_lo = a_hi + CV_A_PART;
-                    const uint32_t b_hi = sB + tap * (2 * CV_B_TAP), b_lo = b_hi + CV_B_TAP;
-                    const uint64_t dA_hi = umma_desc(a_hi, CV_A_CHUNK, 128), dA_lo = umma_desc(a_lo, CV_A_CHUNK, 128);
-                    const uint64_t dB_hi = umma_desc(b_hi, CV_B_CHUNK, 128), dB_lo = umma_desc(b_lo, CV_B_CHUNK, 128);
+                    const int ky = tap / 3, kx = tap % 3;
+                    const uint64_t dA_hi = dA0 + (uint64_t)(((r + ky) * CV_A_ROW + kx * 16) >> 4), dA_lo = dA_hi + (CV_A_PART >> 4);
+                    const uint64_t dB_hi = dB0 + (uint64_t)((tap * 2 * CV_B_TAP) >> 4), dB_lo = dB_hi + (CV_B_TAP >> 4);
                     const uint32_t d = tmem + r * CV_NT;
-                    umma_tf32(d, dA_hi, dB_hi, IDESC, kb > 0 || tap > 0);
-                    umma_tf32(d, dA_hi, dB_lo, IDESC, true);
-                    umma_tf32(d, dA_lo, dB_hi, IDESC, true);
+                    if (tap == 0) umma_tf32(d, dA_hi, dB_hi, IDESC, kb > 0);
+                    else umma_tf32_acc(d, dA_hi, dB_hi, IDESC);
+                    umma_tf32_acc(d, dA_hi, dB_lo, IDESC);
+                    umma_tf32_acc(d, dA_lo, dB_hi, IDESC);
                 }
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[cur])) : "memory");
-        }
-        if (kb + 1 < nkb) {
-            if (kb >= 1) mbar_wait(&bars[cur ^ 1], ((kb - 1) >> 1) & 1);   // MMAs that read the other buffer are done
-            stage(kb + 1, cur ^ 1);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[4 + buf])) : "memory");
+            if (kb + 1 < nkb) {
+                if (kb >= 1) mbar_wait(&bars[4 + (buf ^ 1)], (((kb + 1) >> 1) - 1) & 1);   // MMAs of K block kb-1 done
+                copy_b(kb + 1);
+            }
         }
     }
-    mbar_wait(&bars[(nkb - 1) & 1], ((nkb - 1) >> 1) & 1);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---- epilogue: TMEM -> registers -> NCHW global (lane = x, coalesced per channel)
-    {
+    // ---- epilogue (producer warps): TMEM -> registers -> NCHW global (lane = x, coalesced per channel)
+    if (warp < CV_PRODUCERS / 32) {
+        mbar_wait(&bars[4 + ((nkb - 1) & 1)], ((nkb - 1) >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3, half = warp >> 2;                      // TMEM lane quarter, column half
         const int px = q * 32 + lane;
 #pragma unroll 1
@@ -303,6 +333,6 @@ extern "C" int ffwm_conv3x3_forward(const ffwm_tensor4* x, const float* packed, 
     cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM);
     if (e != cudaSuccess) { set_error("conv3x3_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
     dim3 grid(ceil_div(ov.h, CV_ROWS), ncob, ov.n);
-    conv3x3_tc_kernel<<<grid, CV_THREADS, CV_SMEM, static_cast<cudaStream_t>(stream)>>>(xv, packed, bias, ov, nkb);
+    conv3x3_tc_kernel<<<grid, CV_PRODUCERS + 32, CV_SMEM, static_cast<cudaStream_t>(stream)>>>(xv, packed, bias, ov, nkb);
     return check_launch("conv3x3_forward");
 }
