@@ -9,8 +9,8 @@ from . import _lib
 _lib.lib()   # raises ImportError when the library is missing or stale
 
 from . import ops, external_function, dropin  # noqa: E402
-from . import base_networks, light_cnn, losses, parallel, train_step, compat  # noqa: E402
+from . import conv, base_networks, light_cnn, losses, parallel, train_step, compat  # noqa: E402
 from .dropin import install as install_dropin  # noqa: E402
 
 __all__ = ["ops", "external_function", "dropin", "install_dropin", "base_networks", "light_cnn", "losses",
-           "parallel", "train_step", "compat"]
+           "parallel", "train_step", "compat", "conv"]

@@ -26,6 +26,7 @@ import torch.nn.functional as F
 from torch.nn.utils import spectral_norm
 
 from . import external_function as EF
+from .conv import Conv2d
 
 LRELU_SLOPE = 0.2
 
@@ -47,7 +48,7 @@ def _unit(cin, cout, norm, k=3, stride=1, transposed=False, bias=True):
     if transposed:
         op = nn.ConvTranspose2d(cin, cout, kernel_size=4, stride=2, padding=1, bias=True)
     else:
-        op = nn.Conv2d(cin, cout, kernel_size=k, stride=stride, padding=(k - 1) // 2, bias=bias)
+        op = Conv2d(cin, cout, kernel_size=k, stride=stride, padding=(k - 1) // 2, bias=bias)
     return nn.Sequential(op, norm(cout), nn.LeakyReLU(LRELU_SLOPE, inplace=True))
 
 
@@ -65,7 +66,7 @@ def i_conv(in_planes, out_planes, norm_layer, kernel_size=3, stride=1, bias=True
 
 def predict_flow(in_planes):
     """3x3 conv to 2 channels + tanh: an ABSOLUTE sampling grid in [-1,1]."""
-    return nn.Sequential(nn.Conv2d(in_planes, 2, kernel_size=3, stride=1, padding=1, bias=True), nn.Tanh())
+    return nn.Sequential(Conv2d(in_planes, 2, kernel_size=3, stride=1, padding=1, bias=True), nn.Tanh())
 
 
 class FlowNet(nn.Module):
@@ -174,10 +175,10 @@ class ResidualBlock(nn.Module):
         outc = inc // stride if outc is None else outc
         pad = kernel // 2 if sn else kernel
         self.activ = get_activ(activ)
-        self.input = _maybe_sn(nn.Conv2d(inc, outc, 1, 1, padding=0), sn)
-        self.blocks = nn.Sequential(_maybe_sn(nn.Conv2d(inc, outc, kernel, 1, pad), sn), get_norm(norm, outc),
+        self.input = _maybe_sn(Conv2d(inc, outc, 1, 1, padding=0), sn)
+        self.blocks = nn.Sequential(_maybe_sn(Conv2d(inc, outc, kernel, 1, pad), sn), get_norm(norm, outc),
                                     nn.LeakyReLU(LRELU_SLOPE),
-                                    _maybe_sn(nn.Conv2d(outc, outc, kernel, 1, pad), sn), get_norm(norm, outc))
+                                    _maybe_sn(Conv2d(outc, outc, kernel, 1, pad), sn), get_norm(norm, outc))
 
     def forward(self, x):
         return self.activ(self.blocks(x) + self.input(x))
@@ -194,7 +195,7 @@ def _block(first, outc, activ, norm, res, resk, bn, sn):
 
 
 def ConvBlock(inc, outc, ks=3, s=1, p=0, activ='lrelu', norm='bn', res=0, resk=3, bn=True, sn=False):
-    return _block([_maybe_sn(nn.Conv2d(inc, outc, ks, s, p), sn)], outc, activ, norm, res, resk, bn, sn)
+    return _block([_maybe_sn(Conv2d(inc, outc, ks, s, p), sn)], outc, activ, norm, res, resk, bn, sn)
 
 
 def DeConvBlock(inc, outc, ks=3, s=1, p=0, op=0, activ='relu', norm='bn', res=0, resk=3, bn=True, sn=False):
@@ -203,7 +204,7 @@ def DeConvBlock(inc, outc, ks=3, s=1, p=0, op=0, activ='relu', norm='bn', res=0,
 
 def PixelSuffleBlock(inc, outc, ks=3, s=1, p=0, activ='lrelu', norm='bn', res=0, bn=True, sn=False):
     """3x3 conv to 4*outc channels + PixelShuffle(2); ks/s/p are accepted and ignored, as in the reference."""
-    return _block([_maybe_sn(nn.Conv2d(inc, outc * 4, 3, 1, 1), sn), nn.PixelShuffle(2)], outc, activ, norm, res, 3, bn, sn)
+    return _block([_maybe_sn(Conv2d(inc, outc * 4, 3, 1, 1), sn), nn.PixelShuffle(2)], outc, activ, norm, res, 3, bn, sn)
 
 
 class FFWM(nn.Module):
@@ -279,15 +280,15 @@ class MSDiscriminator(nn.Module):
         c = self.base_channels
         layers = []
         for cin, cout in ((self.inc, c), (c, 2 * c), (2 * c, 4 * c)):      # three stride-2 SN conv blocks
-            layers += [spectral_norm(nn.Conv2d(cin, cout, kernel_size=3, stride=2, padding=1)),
+            layers += [spectral_norm(Conv2d(cin, cout, kernel_size=3, stride=2, padding=1)),
                        nn.BatchNorm2d(cout), nn.LeakyReLU(LRELU_SLOPE, True)]
         for _ in range(self.extra_conv_layers):
-            layers += [spectral_norm(nn.Conv2d(2 * c, 2 * c, kernel_size=3, bias=True)),
+            layers += [spectral_norm(Conv2d(2 * c, 2 * c, kernel_size=3, bias=True)),
                        nn.BatchNorm2d(2 * c), nn.LeakyReLU(LRELU_SLOPE, True)]
         if self.sigmoid:
-            layers += [spectral_norm(nn.Conv2d(4 * c, 1, kernel_size=1)), nn.Sigmoid()]
+            layers += [spectral_norm(Conv2d(4 * c, 1, kernel_size=1)), nn.Sigmoid()]
         else:
-            layers += [nn.Conv2d(4 * c, 1, kernel_size=1)]
+            layers += [Conv2d(4 * c, 1, kernel_size=1)]
         return nn.Sequential(*layers)
 
     def forward(self, input_tensor):

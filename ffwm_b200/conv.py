@@ -1,0 +1,67 @@
+"""Convolution layer of the mirrored networks: `nn.Conv2d` whose eligible calls run on the
+hand-written tcgen05 kernel (ffwm_b200/csrc/conv3x3_tc.cu) instead of cuDNN.
+
+Eligible: CUDA fp32, 3x3, stride 1, padding 1, dilation 1, groups 1, zero padding, map width 128 —
+the generator's dres2 / att2 / rec2 / e0 residual convolutions, FlowNet's 128x128 layers and VGG19's
+first block on 128x128 inputs.  Everything else stays on cuDNN (library).
+
+    forward        conv3x3_tc (implicit GEMM, 3xTF32 split: fp32-level accuracy)
+    grad input     the same kernel with the weights packed transposed + flipped
+    grad weight    cuDNN (`aten.convolution_backward`, weight/bias outputs only) — not hand-written yet
+
+The module is a drop-in `nn.Conv2d`: same parameters, same state_dict keys, spectral norm hooks work
+unchanged (the weight is re-packed on every call: 0.02 ms).
+"""
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from . import ops
+
+ENABLED = True          # set False to force cuDNN everywhere (A/B measurements)
+
+
+def eligible(x, weight, stride, padding, dilation, groups, padding_mode="zeros"):
+    return (ENABLED and x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.dim() == 4
+            and x.size(3) == 128 and tuple(weight.shape[2:]) == (3, 3) and tuple(stride) == (1, 1)
+            and tuple(padding) == (1, 1) and tuple(dilation) == (1, 1) and groups == 1 and padding_mode == "zeros")
+
+
+class Conv3x3TCFunction(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = x.contiguous()
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        out = x.new_empty((x.size(0), weight.size(0), x.size(2), x.size(3)))
+        ops.conv3x3_forward(x, ops.conv3x3_pack_weights(weight), bias, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, weight = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            ops.conv3x3_forward(grad_out, ops.conv3x3_pack_weights(weight, dgrad=True), None, gx)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            _, gw, gb = torch.ops.aten.convolution_backward(
+                grad_out, x, weight, [weight.size(0)] if ctx.has_bias else None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
+                [False, bool(ctx.needs_input_grad[1]), bool(ctx.has_bias and ctx.needs_input_grad[2])])
+        return gx, gw, gb
+
+
+def conv2d(x, weight, bias, stride=(1, 1), padding=(0, 0), dilation=(1, 1), groups=1):
+    """F.conv2d with the tcgen05 path for eligible calls."""
+    if eligible(x, weight, stride, padding, dilation, groups):
+        return Conv3x3TCFunction.apply(x, weight, bias)
+    return torch.nn.functional.conv2d(x, weight, bias, stride, padding, dilation, groups)
+
+
+class Conv2d(nn.Conv2d):
+    def _conv_forward(self, input, weight, bias):
+        if isinstance(self.padding, tuple) and eligible(input, weight, self.stride, self.padding, self.dilation,
+                                                        self.groups, self.padding_mode):
+            return Conv3x3TCFunction.apply(input, weight, bias)
+        return super()._conv_forward(input, weight, bias)

@@ -12,13 +12,15 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .conv import Conv2d
+
 
 class mfm(nn.Module):
     def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, type=1):
         super().__init__()
         self.out_channels = out_channels
         if type == 1:
-            self.filter = nn.Conv2d(in_channels, 2 * out_channels, kernel_size=kernel_size, stride=stride, padding=padding)
+            self.filter = Conv2d(in_channels, 2 * out_channels, kernel_size=kernel_size, stride=stride, padding=padding)
         else:
             self.filter = nn.Linear(in_channels, 2 * out_channels)
 

@@ -25,6 +25,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import base_networks
+from .conv import Conv2d
 from .external_function import BlockExtractor, LocalAttnReshape, Resample2d, grid_warp
 
 
@@ -226,7 +227,7 @@ class VGG19(nn.Module):
             if v == 'M':
                 layers.append(nn.MaxPool2d(kernel_size=2, stride=2))
             else:
-                layers += [nn.Conv2d(cin, v, kernel_size=3, padding=1), nn.ReLU(inplace=True)]
+                layers += [Conv2d(cin, v, kernel_size=3, padding=1), nn.ReLU(inplace=True)]
                 cin = v
         self.stage_names = []
         block, conv_i, idx = 1, 0, 0

@@ -55,3 +55,27 @@ def test_conv3x3_rejects_other_widths(ops):
     packed = ops.conv3x3_pack_weights(torch.zeros(8, 8, 3, 3, device=DEV))
     with pytest.raises(RuntimeError):
         ops.conv3x3_forward(x, packed, None, torch.zeros(1, 8, 4, 64, device=DEV))
+
+
+def test_conv_module_autograd_matches_cudnn_fp64():
+    """ffwm_b200.conv.Conv2d: forward and grad_input on tcgen05, grad_weight/bias on cuDNN."""
+    from ffwm_b200 import _lib
+    from ffwm_b200.conv import Conv2d
+    torch.manual_seed(0)
+    m = Conv2d(20, 70, 3, 1, 1).to(DEV)
+    x = torch.randn(2, 20, 12, 128, device=DEV, requires_grad=True)
+    go = torch.randn(2, 70, 12, 128, device=DEV)
+    n0 = _lib.kernel_launches()
+    out = m(x)
+    out.backward(go)
+    assert _lib.kernel_launches() - n0 == 4                  # pack + conv, forward and data gradient
+    xr = x.detach().double().requires_grad_(True)
+    wr = m.weight.detach().double().requires_grad_(True)
+    br = m.bias.detach().double().requires_grad_(True)
+    F.conv2d(xr, wr, br, padding=1).backward(go.double())
+    assert rel(out, F.conv2d(xr, wr, br, padding=1)) <= 2e-5
+    assert rel(x.grad, xr.grad) <= 2e-5
+    assert rel(m.weight.grad, wr.grad) <= 1e-4 and rel(m.bias.grad, br.grad) <= 1e-4
+    # not eligible (width 64): falls back to the library convolution, same module
+    y = m(torch.randn(1, 20, 8, 64, device=DEV))
+    assert y.shape == (1, 70, 8, 64)
