@@ -36,14 +36,16 @@ def main():
     dev = torch.device("cuda", 0)
     torch.backends.cudnn.benchmark = True
     rows = []
-    for name, cin, cout in (("dres2 195->195", 195, 195), ("att2 128->128", 128, 128), ("e0 res 64->64", 64, 64),
-                            ("vgg relu1_2 64->64", 64, 64), ("256->256", 256, 256)):
-        x = torch.randn(8, cin, 128, 128, device=dev)
+    for name, cin, cout, r in (("dres2 195->195 @128", 195, 195, 128), ("att2 128->128 @128", 128, 128, 128),
+                               ("e0 res 64->64 @128", 64, 64, 128), ("dres1 195->195 @64", 195, 195, 64),
+                               ("d2 195->256 @64", 195, 256, 64), ("vgg 128->128 @64", 128, 128, 64),
+                               ("dres0 384->384 @32", 384, 384, 32), ("vgg 256->256 @32", 256, 256, 32)):
+        x = torch.randn(8, cin, r, r, device=dev)
         w = torch.randn(cout, cin, 3, 3, device=dev) / (cin * 9) ** 0.5
         b = torch.randn(cout, device=dev)
-        out = torch.empty(8, cout, 128, 128, device=dev)
+        out = torch.empty(8, cout, r, r, device=dev)
         packed = ops.conv3x3_pack_weights(w)
-        flop = 2.0 * 8 * 128 * 128 * cin * cout * 9
+        flop = 2.0 * 8 * r * r * cin * cout * 9
         t_mine = timeit(lambda: ops.conv3x3_forward(x, packed, b, out))
         t_pack = timeit(lambda: ops.conv3x3_pack_weights(w))
         torch.backends.cudnn.allow_tf32 = False
@@ -61,9 +63,9 @@ def main():
         del ref
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(rows, open(args.out, "w"), indent=1)
-    print("%-20s %8s %8s %8s %8s %8s %9s %9s %9s" % ("shape", "tc ms", "pack ms", "fp32 ms", "tf32 ms", "TF/s", "err tc", "err fp32", "err tf32"))
+    print("%-22s %8s %8s %8s %8s %8s %9s %9s %9s" % ("shape", "tc ms", "pack ms", "fp32 ms", "tf32 ms", "TF/s", "err tc", "err fp32", "err tf32"))
     for r in rows:
-        print("%-20s %8.3f %8.3f %8.3f %8.3f %8.1f %9.1e %9.1e %9.1e" % (
+        print("%-22s %8.3f %8.3f %8.3f %8.3f %8.1f %9.1e %9.1e %9.1e" % (
             r["shape"], r["ms_tcgen05"], r["ms_pack"], r["ms_cudnn_fp32"], r["ms_cudnn_tf32"], r["tflops_tcgen05"],
             r["err_tcgen05"], r["err_cudnn_fp32"], r["err_cudnn_tf32"]))
 

@@ -9,15 +9,17 @@
 //
 //   D[pixel, co] += A[pixel, ci] * B[co, ci]      for each of the 9 taps, ci in blocks of 8
 //
-//   * M = 128 pixels = ONE image row (W must be 128), so TMEM lane = x and the epilogue's global
-//     stores are 128-byte coalesced rows of the NCHW output; N = 64 output channels; a CTA owns
-//     4 output rows x 64 channels = 4 accumulators = 256 TMEM columns.
+//   * M = 128 pixels = one image row (W = 128), two (W = 64) or four (W = 32), so TMEM lanes are
+//     consecutive x and the epilogue's global stores are coalesced rows of the NCHW output;
+//     N = 64 output channels; a CTA owns 2-4 M tiles x 64 channels (128-256 TMEM columns).
 //   * A (activations) is staged K-major without swizzle as [k-chunk][slot][4 channels]: 16 bytes
 //     per pixel slot, slot = x + 1 with explicit zero halo slots, so the three horizontal taps
 //     are the SAME shared-memory row read through descriptors whose start address differs by
 //     16 bytes; the three vertical taps are neighbouring row buffers (6 input rows serve 4 output
-//     rows).  The NCHW -> K-major transposition happens in the staging threads (4 coalesced
-//     loads -> one 16-byte shared store).
+//     rows).  For W < 128 an M tile spans several image rows, so three horizontally shifted
+//     copies are staged instead and the vertical taps become start-address offsets (CvGeo).
+//     The NCHW -> K-major transposition happens in the staging threads (4 coalesced loads ->
+//     one 16-byte shared store per copy).
 //   * B (weights) is pre-packed once per weight update into exactly the shared-memory image the
 //     MMA wants, hi and lo parts already split, and copied in with 16-byte loads/stores.
 //   * fp32 accuracy: every operand is split a = hi + lo with hi = a & 0xffffe000 (exactly
@@ -35,25 +37,36 @@
 
 namespace ffwm {
 
-constexpr int CV_ROWS = 4;             // output rows per CTA
-constexpr int CV_W = 128;              // image width = MMA M
 constexpr int CV_NT = 64;              // output channels per CTA = MMA N
 constexpr int CV_KB = 8;               // input channels per K block = one tf32 MMA K
-constexpr int CV_SLOTS = 136;          // pixel slots per row buffer (130 used, 16-byte each per k-chunk)
-constexpr int CV_THREADS = 256;
-constexpr int CV_IN_ROWS = CV_ROWS + 2;
+constexpr int CV_PRODUCERS = 256;
 
-// bytes
-constexpr int CV_A_CHUNK = CV_SLOTS * 16;                 // one k-chunk (4 channels) of one row
-constexpr int CV_A_ROW = 2 * CV_A_CHUNK;                  // both k-chunks
-constexpr int CV_A_PART = CV_IN_ROWS * CV_A_ROW;          // all rows, hi or lo
-constexpr int CV_A_STAGE = 2 * CV_A_PART;                 // hi + lo
+// Geometry per image width WI (= 128, 64 or 32).  The MMA M dimension is always 128 pixels:
+//   WI = 128: an M tile is one image row; one copy of each input row with explicit zero halo
+//             slots (slot = x + 1), horizontal taps = descriptor start + kx * 16 bytes.
+//   WI < 128: an M tile is 128/WI consecutive image rows, stored back to back (slot = row*WI + x),
+//             so a horizontal shift cannot be expressed by the start address across the row
+//             seam; three copies are staged instead, copy kx holding in[.., x + kx - 1] with zeros
+//             at the border; vertical taps = descriptor start + ky * WI * 16 bytes.
+template <int WI>
+struct CvGeo {
+    static constexpr int RPT = 128 / WI;                       // image rows per M tile
+    static constexpr int MT = WI == 128 ? 4 : 2;               // M tiles (accumulators) per CTA
+    static constexpr int ROWS = MT * RPT;                      // output rows per CTA
+    static constexpr int IN_ROWS = ROWS + 2;
+    static constexpr int NCOPY = WI == 128 ? 1 : 3;
+    static constexpr int ROW_SLOTS = WI == 128 ? 136 : WI;     // 16-byte slots per input row and k-chunk
+    static constexpr int A_CHUNK = IN_ROWS * ROW_SLOTS * 16;   // one k-chunk (4 channels), all rows, one copy
+    static constexpr int A_COPY = 2 * A_CHUNK;                 // both k-chunks
+    static constexpr int A_PART = NCOPY * A_COPY;              // hi or lo
+    static constexpr int A_STAGE = 2 * A_PART;
+    static constexpr int STAGE = A_STAGE + 2 * 9 * 2 * CV_NT * 16;
+    static constexpr int SMEM = 2 * STAGE + 64;                // + 6 mbarriers + tmem address
+    static constexpr int TMEM_COLS = 256;
+};
 constexpr int CV_B_CHUNK = CV_NT * 16;                    // one k-chunk of one tap: 64 co x 4 ci
 constexpr int CV_B_TAP = 2 * CV_B_CHUNK;                  // both k-chunks
-constexpr int CV_B_PART = 9 * CV_B_TAP;                   // all taps, hi or lo... (layout: [tap][hl][kchunk])
-constexpr int CV_B_STAGE = 2 * CV_B_PART;
-constexpr int CV_STAGE = CV_A_STAGE + CV_B_STAGE;
-constexpr int CV_SMEM = 2 * CV_STAGE + 64;                // + 6 mbarriers + tmem address
+constexpr int CV_B_STAGE = 2 * 9 * CV_B_TAP;              // layout: [tap][hl][kchunk][co][4]
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -135,8 +148,6 @@ __global__ void conv3x3_pack_kernel(const float* __restrict__ w, float* __restri
 // lane 0 copies the packed weights with one bulk async copy per K block and issues the MMAs.
 // Pipeline state lives in mbarriers: fullA[2] (256 producer arrivals), fullB[2] (bulk-copy
 // transaction bytes), empty[2] (tcgen05.commit of the MMAs that read the buffer).
-constexpr int CV_PRODUCERS = 256;
-
 __device__ __forceinline__ void umma_tf32_acc(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
@@ -144,18 +155,30 @@ __device__ __forceinline__ void umma_tf32_acc(uint32_t d_tmem, uint64_t a_desc, 
         : "memory");
 }
 
+__device__ __forceinline__ void split_store(unsigned char* d, int part_bytes, const float* v) {
+    float4 hi, lo;
+    hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u); lo.x = v[0] - hi.x;
+    hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u); lo.y = v[1] - hi.y;
+    hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u); lo.z = v[2] - hi.z;
+    hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u); lo.w = v[3] - hi.w;
+    *reinterpret_cast<float4*>(d) = hi;
+    *reinterpret_cast<float4*>(d + part_bytes) = lo;
+}
+
+template <int WI>
 __global__ void __launch_bounds__(CV_PRODUCERS + 32, 1)
 conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const float* __restrict__ bias,
                   View<float> out, int nkb) {
+    using G = CvGeo<WI>;
     extern __shared__ __align__(128) unsigned char cv_smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(cv_smem + 2 * CV_STAGE);    // fullA[0,1] fullB[2,3] empty[4,5]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cv_smem + 2 * CV_STAGE + 48);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cv_smem + 2 * G::STAGE);    // fullA[0,1] fullB[2,3] empty[4,5]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cv_smem + 2 * G::STAGE + 48);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int y0 = blockIdx.x * CV_ROWS, cob = blockIdx.y, b = blockIdx.z;
+    const int y0 = blockIdx.x * G::ROWS, cob = blockIdx.y, b = blockIdx.z;
 
-    // ---- one-time setup: zero both stages (halo slots and out-of-image rows stay zero), barriers, TMEM
-    for (int i = tid; i < (2 * CV_STAGE) / 16; i += CV_PRODUCERS + 32) reinterpret_cast<float4*>(cv_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // ---- one-time setup: zero both stages (halo / border slots and out-of-image rows stay zero), barriers, TMEM
+    for (int i = tid; i < (2 * G::STAGE) / 16; i += CV_PRODUCERS + 32) reinterpret_cast<float4*>(cv_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {
         mbar_init(&bars[0], CV_PRODUCERS);
         mbar_init(&bars[1], CV_PRODUCERS);
@@ -166,7 +189,7 @@ conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const f
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(CV_ROWS * CV_NT) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(G::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // the zero fill, before any async-proxy access
@@ -178,47 +201,52 @@ conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const f
 
     if (warp < CV_PRODUCERS / 32) {
         // ================= producers: activations of K block kb -> stage buffer kb & 1 =================
-        // thread -> (pixel px, k-chunk kc); it loads 4 channels x 6 input rows (24 loads in flight),
-        // splits hi/lo and writes one 16-byte slot per row and part
-        const int px = tid & (CV_W - 1), kc = tid >> 7;
-        bool row_ok[CV_IN_ROWS];
-#pragma unroll
-        for (int rr = 0; rr < CV_IN_ROWS; ++rr) row_ok[rr] = (unsigned)(y0 - 1 + rr) < (unsigned)x.h;
+        // thread -> (pixel px, k-chunk kc, row phase ph); it loads 4 channels of every PH-th input row
+        // (all loads in flight), splits hi/lo and writes 16-byte slots
+        constexpr int PH = CV_PRODUCERS / (2 * WI);                // 1, 2 or 4 row phases
+        constexpr int NR = (G::IN_ROWS + PH - 1) / PH;             // rows per thread
+        const int px = tid % WI, kc = (tid / WI) & 1, ph = tid / (2 * WI);
         const float* gp0 = x.p + b * x.sb + (int64_t)(y0 - 1) * x.sh + px * x.sw;
         for (int kb = 0; kb < nkb; ++kb) {
             const int buf = kb & 1;
             if (kb >= 2) mbar_wait(&bars[4 + buf], ((kb >> 1) - 1) & 1);          // MMAs of K block kb-2 done
             const int c0 = kb * CV_KB + kc * 4;
-            float v[CV_IN_ROWS][4];
+            float v[NR][4];
 #pragma unroll
-            for (int rr = 0; rr < CV_IN_ROWS; ++rr)
+            for (int i = 0; i < NR; ++i) {
+                const int rr = ph + i * PH;
+                const bool ok = rr < G::IN_ROWS && (unsigned)(y0 - 1 + rr) < (unsigned)x.h;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    v[rr][j] = (row_ok[rr] && c0 + j < x.c) ? __ldg(gp0 + (int64_t)(c0 + j) * x.sc + rr * x.sh) : 0.f;
-            unsigned char* d = cv_smem + buf * CV_STAGE + kc * CV_A_CHUNK + (px + 1) * 16;
+                    v[i][j] = (ok && c0 + j < x.c) ? __ldg(gp0 + (int64_t)(c0 + j) * x.sc + rr * x.sh) : 0.f;
+            }
+            unsigned char* sA = cv_smem + buf * G::STAGE + kc * G::A_CHUNK;
 #pragma unroll
-            for (int rr = 0; rr < CV_IN_ROWS; ++rr) {
-                if (!row_ok[rr]) continue;                                       // stays zero
-                float4 hi, lo;
-                hi.x = __uint_as_float(__float_as_uint(v[rr][0]) & 0xffffe000u); lo.x = v[rr][0] - hi.x;
-                hi.y = __uint_as_float(__float_as_uint(v[rr][1]) & 0xffffe000u); lo.y = v[rr][1] - hi.y;
-                hi.z = __uint_as_float(__float_as_uint(v[rr][2]) & 0xffffe000u); lo.z = v[rr][2] - hi.z;
-                hi.w = __uint_as_float(__float_as_uint(v[rr][3]) & 0xffffe000u); lo.w = v[rr][3] - hi.w;
-                *reinterpret_cast<float4*>(d + rr * CV_A_ROW) = hi;
-                *reinterpret_cast<float4*>(d + rr * CV_A_ROW + CV_A_PART) = lo;
+            for (int i = 0; i < NR; ++i) {
+                const int rr = ph + i * PH;
+                if (rr >= G::IN_ROWS || (unsigned)(y0 - 1 + rr) >= (unsigned)x.h) continue;   // stays zero
+                if (WI == 128) {
+                    split_store(sA + (rr * G::ROW_SLOTS + px + 1) * 16, G::A_PART, v[i]);
+                } else {
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int xd = px - kx + 1;                              // copy kx holds in[x + kx - 1] at slot x
+                        if ((unsigned)xd < (unsigned)WI) split_store(sA + kx * G::A_COPY + (rr * WI + xd) * 16, G::A_PART, v[i]);
+                    }
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // my stores -> visible to the tensor core
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[buf])) : "memory");
         }
     } else if (lane == 0) {
         // ================= issuer: weight copies + MMAs =================
-        constexpr uint32_t IDESC = umma_idesc_tf32(CV_W, CV_NT);
+        constexpr uint32_t IDESC = umma_idesc_tf32(128, CV_NT);
         auto copy_b = [&](int kb) {
             const int buf = kb & 1;
             const uint32_t bar = smem_u32(&bars[2 + buf]);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(CV_B_STAGE) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             smem_u32(cv_smem + buf * CV_STAGE + CV_A_STAGE)),
+                             smem_u32(cv_smem + buf * G::STAGE + G::A_STAGE)),
                          "l"(pk_base + (int64_t)kb * (CV_B_STAGE / 4)), "r"(CV_B_STAGE), "r"(bar)
                          : "memory");
         };
@@ -228,16 +256,18 @@ conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const f
             mbar_wait(&bars[buf], (kb >> 1) & 1);            // activations staged
             mbar_wait(&bars[2 + buf], (kb >> 1) & 1);        // weights landed
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sA = smem_u32(cv_smem + buf * CV_STAGE), sB = sA + CV_A_STAGE;
-            const uint64_t dA0 = umma_desc(sA, CV_A_CHUNK, 128), dB0 = umma_desc(sB, CV_B_CHUNK, 128);
+            const uint32_t sA = smem_u32(cv_smem + buf * G::STAGE), sB = sA + G::A_STAGE;
+            const uint64_t dA0 = umma_desc(sA, G::A_CHUNK, 128), dB0 = umma_desc(sB, CV_B_CHUNK, 128);
 #pragma unroll
-            for (int r = 0; r < CV_ROWS; ++r) {
+            for (int t = 0; t < G::MT; ++t) {
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                     const int ky = tap / 3, kx = tap % 3;
-                    const uint64_t dA_hi = dA0 + (uint64_t)(((r + ky) * CV_A_ROW + kx * 16) >> 4), dA_lo = dA_hi + (CV_A_PART >> 4);
+                    const int a_off = WI == 128 ? ((t + ky) * G::ROW_SLOTS + kx) * 16
+                                                : kx * G::A_COPY + (t * G::RPT + ky) * WI * 16;
+                    const uint64_t dA_hi = dA0 + (uint64_t)(a_off >> 4), dA_lo = dA_hi + (G::A_PART >> 4);
                     const uint64_t dB_hi = dB0 + (uint64_t)((tap * 2 * CV_B_TAP) >> 4), dB_lo = dB_hi + (CV_B_TAP >> 4);
-                    const uint32_t d = tmem + r * CV_NT;
+                    const uint32_t d = tmem + t * CV_NT;
                     if (tap == 0) umma_tf32(d, dA_hi, dB_hi, IDESC, kb > 0);
                     else umma_tf32_acc(d, dA_hi, dB_hi, IDESC);
                     umma_tf32_acc(d, dA_hi, dB_lo, IDESC);
@@ -252,34 +282,35 @@ conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const f
         }
     }
 
-    // ---- epilogue (producer warps): TMEM -> registers -> NCHW global (lane = x, coalesced per channel)
+    // ---- epilogue (producer warps): TMEM -> registers -> NCHW global (lanes = consecutive x, coalesced per channel)
     if (warp < CV_PRODUCERS / 32) {
         mbar_wait(&bars[4 + ((nkb - 1) & 1)], ((nkb - 1) >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3, half = warp >> 2;                      // TMEM lane quarter, column half
-        const int px = q * 32 + lane;
+        const int m = q * 32 + lane;                                   // row of the M tile
+        const int xo = m % WI, yo = m / WI;
 #pragma unroll 1
-        for (int r = 0; r < CV_ROWS; ++r) {
-            const int y = y0 + r;
+        for (int t = 0; t < G::MT; ++t) {
+            const int y = y0 + t * G::RPT + yo;
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
                 const int col0 = half * 32 + cc * 16;
                 uint32_t v[16];
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * CV_NT + col0);
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * CV_NT + col0);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (y < out.h && px < out.w) {
+                if (y < out.h) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int co = cob * CV_NT + col0 + j;
                         if (co < out.c) {
                             float o = __uint_as_float(v[j]);
                             if (bias) o += __ldg(bias + co);
-                            st_stream(out.p + b * out.sb + (int64_t)co * out.sc + y * out.sh + px * out.sw, o);
+                            st_stream(out.p + b * out.sb + (int64_t)co * out.sc + y * out.sh + xo * out.sw, o);
                         }
                     }
                 }
@@ -288,7 +319,18 @@ conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const f
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(CV_ROWS * CV_NT) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(G::TMEM_COLS) : "memory");
+}
+
+template <int WI>
+static int launch_conv3x3(const View<const float>& xv, const float* packed, const float* bias, const View<float>& ov, cudaStream_t st) {
+    using G = CvGeo<WI>;
+    const int ncob = ceil_div(ov.c, CV_NT), nkb = ceil_div(xv.c, CV_KB);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<WI>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+    if (e != cudaSuccess) { set_error("conv3x3_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
+    dim3 grid(ceil_div(ov.h, G::ROWS), ncob, ov.n);
+    conv3x3_tc_kernel<WI><<<grid, CV_PRODUCERS + 32, G::SMEM, st>>>(xv, packed, bias, ov, nkb);
+    return FFWM_OK;
 }
 
 }  // namespace ffwm
@@ -313,8 +355,8 @@ extern "C" int ffwm_conv3x3_pack_weights(const ffwm_tensor4* weight, int dgrad, 
     return check_launch("conv3x3_pack_weights");
 }
 
-// conv2d(x, w, bias, stride 1, padding 1) for 3x3 kernels with `packed` = pack_weights(w): x (B,Cin,H,128) fp32,
-// out (B,Cout,H,128) fp32.  Replaces the cuDNN call behind nn.Conv2d(…, 3, 1, 1) for those shapes.
+// conv2d(x, w, bias, stride 1, padding 1) for 3x3 kernels with `packed` = pack_weights(w): x (B,Cin,H,W) fp32,
+// out (B,Cout,H,W) fp32, W in {128, 64, 32}.  Replaces the cuDNN call behind nn.Conv2d(…, 3, 1, 1) for those shapes.
 extern "C" int ffwm_conv3x3_forward(const ffwm_tensor4* x, const float* packed, const float* bias, const ffwm_tensor4* out, void* stream) {
     using namespace ffwm;
     View<const float> xv;
@@ -323,16 +365,15 @@ extern "C" int ffwm_conv3x3_forward(const ffwm_tensor4* x, const float* packed, 
     if ((rc = make_view<const float>(x, "x", &xv))) return rc;
     if ((rc = make_view<float>(out, "out", &ov))) return rc;
     if (!packed) { set_error("conv3x3_forward: null packed weights"); return FFWM_ERR_NULL; }
-    if (xv.w != CV_W || ov.w != CV_W || xv.h != ov.h || xv.n != ov.n) {
-        set_error("conv3x3_forward: needs W == %d and equal N,H (x %dx%dx%dx%d, out %dx%dx%dx%d)", CV_W, xv.n, xv.c, xv.h, xv.w, ov.n, ov.c, ov.h, ov.w);
+    if ((xv.w != 128 && xv.w != 64 && xv.w != 32) || ov.w != xv.w || xv.h != ov.h || xv.n != ov.n) {
+        set_error("conv3x3_forward: needs W in {128,64,32} and equal N,H,W (x %dx%dx%dx%d, out %dx%dx%dx%d)", xv.n, xv.c, xv.h, xv.w, ov.n, ov.c, ov.h, ov.w);
         return FFWM_ERR_SHAPE;
     }
     if ((int64_t)ov.n * ov.c * ov.h == 0) return FFWM_OK;
-    const int ncob = ceil_div(ov.c, CV_NT), nkb = ceil_div(xv.c, CV_KB);
-    if (ov.n > 65535 || ncob > 65535) { set_error("conv3x3_forward: grid too large"); return FFWM_ERR_TOO_LARGE; }
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM);
-    if (e != cudaSuccess) { set_error("conv3x3_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
-    dim3 grid(ceil_div(ov.h, CV_ROWS), ncob, ov.n);
-    conv3x3_tc_kernel<<<grid, CV_PRODUCERS + 32, CV_SMEM, static_cast<cudaStream_t>(stream)>>>(xv, packed, bias, ov, nkb);
+    if (ov.n > 65535 || ceil_div(ov.c, CV_NT) > 65535) { set_error("conv3x3_forward: grid too large"); return FFWM_ERR_TOO_LARGE; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = xv.w == 128 ? launch_conv3x3<128>(xv, packed, bias, ov, st) : xv.w == 64 ? launch_conv3x3<64>(xv, packed, bias, ov, st)
+                                                                                : launch_conv3x3<32>(xv, packed, bias, ov, st);
+    if (rc) return rc;
     return check_launch("conv3x3_forward");
 }

@@ -18,17 +18,19 @@ def ops():
     return o
 
 
-@pytest.mark.parametrize("b,cin,cout,h", [(1, 8, 64, 4), (2, 16, 64, 8), (1, 3, 64, 128), (2, 195, 195, 10),
-                                          (1, 128, 128, 128), (1, 64, 3, 7), (1, 20, 130, 5)])
-def test_conv3x3_forward_matches_fp64(ops, b, cin, cout, h):
-    g = torch.Generator().manual_seed(cin * 1000 + cout)
-    x = torch.randn(b, cin, h, 128, generator=g)
+@pytest.mark.parametrize("b,cin,cout,h,wd", [(1, 8, 64, 4, 128), (2, 16, 64, 8, 128), (1, 3, 64, 128, 128), (2, 195, 195, 10, 128),
+                                             (1, 128, 128, 128, 128), (1, 64, 3, 7, 128), (1, 20, 130, 5, 128),
+                                             (2, 195, 256, 64, 64), (1, 24, 70, 7, 64), (1, 8, 64, 4, 64), (1, 3, 64, 2, 64),
+                                             (2, 384, 384, 32, 32), (1, 20, 66, 11, 32), (3, 8, 8, 8, 32), (1, 5, 3, 1, 32)])
+def test_conv3x3_forward_matches_fp64(ops, b, cin, cout, h, wd):
+    g = torch.Generator().manual_seed(cin * 1000 + cout + wd)
+    x = torch.randn(b, cin, h, wd, generator=g)
     w = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
     bias = torch.randn(cout, generator=g)
     want = F.conv2d(x.double(), w.double(), bias.double(), padding=1)
     xd, wd, bd = x.to(DEV), w.to(DEV), bias.to(DEV)
     packed = ops.conv3x3_pack_weights(wd)
-    out = torch.full((b, cout, h, 128), float("nan"), device=DEV)
+    out = torch.full((b, cout, h, wd), float("nan"), device=DEV)
     ops.conv3x3_forward(xd, packed, bd, out)
     torch.cuda.synchronize()
     assert rel(out.cpu(), want) <= 2e-5
@@ -37,24 +39,25 @@ def test_conv3x3_forward_matches_fp64(ops, b, cin, cout, h):
     assert rel(out2.cpu(), want - bias.double().view(1, -1, 1, 1)) <= 2e-5
 
 
-def test_conv3x3_dgrad_packing(ops):
+@pytest.mark.parametrize("wd", [128, 64, 32])
+def test_conv3x3_dgrad_packing(ops, wd):
     g = torch.Generator().manual_seed(5)
     b, cin, cout, h = 2, 24, 70, 9
-    x = torch.randn(b, cin, h, 128, generator=g, dtype=torch.float64, requires_grad=True)
+    x = torch.randn(b, cin, h, wd, generator=g, dtype=torch.float64, requires_grad=True)
     w = torch.randn(cout, cin, 3, 3, generator=g, dtype=torch.float64) / (cin * 9) ** 0.5
-    go = torch.randn(b, cout, h, 128, generator=g, dtype=torch.float64)
+    go = torch.randn(b, cout, h, wd, generator=g, dtype=torch.float64)
     F.conv2d(x, w, None, padding=1).backward(go)
     packed = ops.conv3x3_pack_weights(w.float().to(DEV), dgrad=True)
-    gx = torch.empty(b, cin, h, 128, device=DEV)
+    gx = torch.empty(b, cin, h, wd, device=DEV)
     ops.conv3x3_forward(go.float().to(DEV), packed, None, gx)
     assert rel(gx.cpu(), x.grad) <= 2e-5
 
 
 def test_conv3x3_rejects_other_widths(ops):
-    x = torch.zeros(1, 8, 4, 64, device=DEV)
+    x = torch.zeros(1, 8, 4, 48, device=DEV)
     packed = ops.conv3x3_pack_weights(torch.zeros(8, 8, 3, 3, device=DEV))
     with pytest.raises(RuntimeError):
-        ops.conv3x3_forward(x, packed, None, torch.zeros(1, 8, 4, 64, device=DEV))
+        ops.conv3x3_forward(x, packed, None, torch.zeros(1, 8, 4, 48, device=DEV))
 
 
 def test_conv_module_autograd_matches_cudnn_fp64():
@@ -76,6 +79,6 @@ def test_conv_module_autograd_matches_cudnn_fp64():
     assert rel(out, F.conv2d(xr, wr, br, padding=1)) <= 2e-5
     assert rel(x.grad, xr.grad) <= 2e-5
     assert rel(m.weight.grad, wr.grad) <= 1e-4 and rel(m.bias.grad, br.grad) <= 1e-4
-    # not eligible (width 64): falls back to the library convolution, same module
-    y = m(torch.randn(1, 20, 8, 64, device=DEV))
-    assert y.shape == (1, 70, 8, 64)
+    # not eligible (width 48): falls back to the library convolution, same module
+    y = m(torch.randn(1, 20, 8, 48, device=DEV))
+    assert y.shape == (1, 70, 8, 48)
