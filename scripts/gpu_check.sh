@@ -18,7 +18,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --c
     python bench.py --workload warp --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launches_$TAG.log 2>&1; echo "ncu launches rc=$?"
 timeout 1500 ncu --set full --clock-control none --import-source on -k "$KR" -s 11 -c 11 -f -o gpurun_out/prof_$TAG \
     python bench.py --workload warp --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
-FFWM_BENCH_NCU_RANGE=1 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 40000 --csv --log-file gpurun_out/launches_train_$TAG.csv \
+FFWM_BENCH_GRAPH=0 FFWM_BENCH_NCU_RANGE=1 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 40000 --csv --log-file gpurun_out/launches_train_$TAG.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-warp > gpurun_out/ncu_launches_train_$TAG.log 2>&1; echo "ncu train launches rc=$?"
 }
+[[ $SKIP == *conv* ]] || { timeout 300 python -m benchmarks.conv --out gpurun_out/conv_$TAG.json > gpurun_out/conv_$TAG.txt 2>&1; echo "conv bench rc=$?"; cat gpurun_out/conv_$TAG.txt;
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc -s 6 -c 6 -f -o gpurun_out/prof_conv_$TAG python -m benchmarks.conv --out gpurun_out/conv_ncu_tmp.json > gpurun_out/ncu_conv_$TAG.log 2>&1; echo "ncu conv rc=$?"; }
 ls -la gpurun_out | tail -30
