@@ -96,7 +96,7 @@ constexpr int BE_WARPS = 8;
 template <typename T, int K>
 __global__ void __launch_bounds__(32 * BE_WARPS, 2)
 block_extractor_fwd_tiled_kernel(View<const T> src, View<const T> flow, View<T> out, int chunks, int c_per_block) {
-    __shared__ T stage[BE_WARPS][K * 32];
+    __shared__ __align__(16) T stage[BE_WARPS][K * 32];
     const int lane = threadIdx.x, warp = threadIdx.y;
     const int xf0 = blockIdx.x * 32, xf = xf0 + lane;
     const int yf = blockIdx.y * BE_WARPS + warp;
@@ -133,45 +133,52 @@ block_extractor_fwd_tiled_kernel(View<const T> src, View<const T> flow, View<T> 
     const T* s = src.plane(b, c0);
     T* obase = out.plane(b, c0) + (yf * K) * out.sh + (xf0 * K) * out.sw;
     // The first touch of a source row is a DRAM round trip (~1500 cycles under load) and every
-    // channel touches new rows, so rows are requested far ahead into L2 and a few channels ahead
-    // into L1; the demand loads below then hit L1.
-    constexpr int PF_L1 = 3, PF_L2 = 20;
+    // channel touches new rows: rows are requested far ahead into L2, and the window of channel
+    // c+1 is loaded into registers before channel c is computed and stored (software pipeline).
+    constexpr int PF_L2 = 16;
+    // full rows of 32 flow pixels leave as 128-bit stores when the layout allows it
+    const bool vec = nx == 32 && out.sw == 1 && (out.sh & 3) == 0 && (out.sc & 3) == 0 && (K * 32) % 4 == 0 &&
+                     (reinterpret_cast<uintptr_t>(out.plane(b, 0) + (yf * K) * out.sh + (xf0 * K)) & 15) == 0;
+    T nxt[K + 1][K + 1];
+    if (live && shared_window) {
+#pragma unroll
+        for (int n = 0; n <= K; ++n)
+#pragma unroll
+            for (int m = 0; m <= K; ++m) nxt[n][m] = __ldg(s + cy[n] + cx[m]);
+    }
     for (int c = c0; c < c1; ++c, s += src.sc, obase += out.sc) {
-        if (live) {
+        T win[K + 1][K + 1];
+        if (live && shared_window) {
+#pragma unroll
+            for (int n = 0; n <= K; ++n)
+#pragma unroll
+                for (int m = 0; m <= K; ++m) win[n][m] = nxt[n][m];
+            if (c + 1 < c1) {
+                const T* s1 = s + src.sc;
+#pragma unroll
+                for (int n = 0; n <= K; ++n)
+#pragma unroll
+                    for (int m = 0; m <= K; ++m) nxt[n][m] = __ldg(s1 + cy[n] + cx[m]);
+            }
             if (c + PF_L2 < c1) {
                 const T* ps = s + (int64_t)PF_L2 * src.sc + cx[0];
 #pragma unroll
                 for (int n = 0; n <= K; ++n) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + cy[n]));
             }
-            if (c + PF_L1 < c1) {
-                const T* ps = s + (int64_t)PF_L1 * src.sc + cx[0];
-#pragma unroll
-                for (int n = 0; n <= K; ++n) asm volatile("prefetch.global.L1 [%0];" ::"l"(ps + cy[n]));
-            }
-        }
-        T top[K + 1];
-        if (live && shared_window) {
-#pragma unroll
-            for (int m = 0; m <= K; ++m) top[m] = __ldg(s + cy[0] + cx[m]);
         }
 #pragma unroll
         for (int i = 0; i < K; ++i) {
             if (live) {
                 if (shared_window) {
-                    T bot[K + 1];
-#pragma unroll
-                    for (int m = 0; m <= K; ++m) bot[m] = __ldg(s + cy[i + 1] + cx[m]);
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
                         T sample = T(0);
-                        sample += xLP[j] * yTP[i] * top[j];
-                        sample += xRP[j] * yTP[i] * top[j + 1];
-                        sample += xLP[j] * yBP[i] * bot[j];
-                        sample += xRP[j] * yBP[i] * bot[j + 1];
+                        sample += xLP[j] * yTP[i] * win[i][j];
+                        sample += xRP[j] * yTP[i] * win[i][j + 1];
+                        sample += xLP[j] * yBP[i] * win[i + 1][j];
+                        sample += xRP[j] * yBP[i] * win[i + 1][j + 1];
                         row[lane * K + j] = sample;
                     }
-#pragma unroll
-                    for (int m = 0; m <= K; ++m) top[m] = bot[m];
                 } else {
                     // rare: the clamped taps of this pixel are not consecutive (float rounding at an
                     // integer boundary); gather the four taps of every sample directly
@@ -188,10 +195,15 @@ block_extractor_fwd_tiled_kernel(View<const T> src, View<const T> flow, View<T> 
                 }
             }
             __syncwarp();
+            if (vec) {
+                if (lane < (K * 32) / 4)
+                    __stcs(reinterpret_cast<float4*>(obase + i * out.sh) + lane, reinterpret_cast<const float4*>(row)[lane]);
+            } else {
 #pragma unroll
-            for (int m = 0; m < K; ++m) {
-                const int idx = m * 32 + lane;
-                if (idx < nx * K) st_stream(obase + i * out.sh + idx * out.sw, row[idx]);
+                for (int m = 0; m < K; ++m) {
+                    const int idx = m * 32 + lane;
+                    if (idx < nx * K) st_stream(obase + i * out.sh + idx * out.sw, row[idx]);
+                }
             }
             __syncwarp();
         }

@@ -9,7 +9,7 @@
 //
 //   D[pixel, co] += A[pixel, ci] * B[co, ci]      for each of the 9 taps, ci in blocks of 8
 //
-//   * M = 128 pixels = one image row (W = 128), two (W = 64) or four (W = 32), so TMEM lanes are
+//   * M = 128 pixels = one image row (W = 128), two (W = 64), four (W = 32) or eight (W = 16), so TMEM lanes are
 //     consecutive x and the epilogue's global stores are coalesced rows of the NCHW output;
 //     N = 64 output channels; a CTA owns 2-4 M tiles x 64 channels (128-256 TMEM columns).
 //   * A (activations) is staged K-major without swizzle as [k-chunk][slot][4 channels]: 16 bytes
@@ -41,7 +41,7 @@ constexpr int CV_NT = 64;              // output channels per CTA = MMA N
 constexpr int CV_KB = 8;               // input channels per K block = one tf32 MMA K
 constexpr int CV_PRODUCERS = 256;
 
-// Geometry per image width WI (= 128, 64 or 32).  The MMA M dimension is always 128 pixels:
+// Geometry per image width WI (= 128, 64, 32 or 16).  The MMA M dimension is always 128 pixels:
 //   WI = 128: an M tile is one image row; one copy of each input row with explicit zero halo
 //             slots (slot = x + 1), horizontal taps = descriptor start + kx * 16 bytes.
 //   WI < 128: an M tile is 128/WI consecutive image rows, stored back to back (slot = row*WI + x),
@@ -356,7 +356,7 @@ extern "C" int ffwm_conv3x3_pack_weights(const ffwm_tensor4* weight, int dgrad, 
 }
 
 // conv2d(x, w, bias, stride 1, padding 1) for 3x3 kernels with `packed` = pack_weights(w): x (B,Cin,H,W) fp32,
-// out (B,Cout,H,W) fp32, W in {128, 64, 32}.  Replaces the cuDNN call behind nn.Conv2d(…, 3, 1, 1) for those shapes.
+// out (B,Cout,H,W) fp32, W in {128, 64, 32, 16}.  Replaces the cuDNN call behind nn.Conv2d(…, 3, 1, 1) for those shapes.
 extern "C" int ffwm_conv3x3_forward(const ffwm_tensor4* x, const float* packed, const float* bias, const ffwm_tensor4* out, void* stream) {
     using namespace ffwm;
     View<const float> xv;
@@ -365,15 +365,17 @@ extern "C" int ffwm_conv3x3_forward(const ffwm_tensor4* x, const float* packed, 
     if ((rc = make_view<const float>(x, "x", &xv))) return rc;
     if ((rc = make_view<float>(out, "out", &ov))) return rc;
     if (!packed) { set_error("conv3x3_forward: null packed weights"); return FFWM_ERR_NULL; }
-    if ((xv.w != 128 && xv.w != 64 && xv.w != 32) || ov.w != xv.w || xv.h != ov.h || xv.n != ov.n) {
-        set_error("conv3x3_forward: needs W in {128,64,32} and equal N,H,W (x %dx%dx%dx%d, out %dx%dx%dx%d)", xv.n, xv.c, xv.h, xv.w, ov.n, ov.c, ov.h, ov.w);
+    if ((xv.w != 128 && xv.w != 64 && xv.w != 32 && xv.w != 16) || ov.w != xv.w || xv.h != ov.h || xv.n != ov.n) {
+        set_error("conv3x3_forward: needs W in {128,64,32,16} and equal N,H,W (x %dx%dx%dx%d, out %dx%dx%dx%d)", xv.n, xv.c, xv.h, xv.w, ov.n, ov.c, ov.h, ov.w);
         return FFWM_ERR_SHAPE;
     }
     if ((int64_t)ov.n * ov.c * ov.h == 0) return FFWM_OK;
     if (ov.n > 65535 || ceil_div(ov.c, CV_NT) > 65535) { set_error("conv3x3_forward: grid too large"); return FFWM_ERR_TOO_LARGE; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    rc = xv.w == 128 ? launch_conv3x3<128>(xv, packed, bias, ov, st) : xv.w == 64 ? launch_conv3x3<64>(xv, packed, bias, ov, st)
-                                                                                : launch_conv3x3<32>(xv, packed, bias, ov, st);
+    rc = xv.w == 128  ? launch_conv3x3<128>(xv, packed, bias, ov, st)
+         : xv.w == 64 ? launch_conv3x3<64>(xv, packed, bias, ov, st)
+         : xv.w == 32 ? launch_conv3x3<32>(xv, packed, bias, ov, st)
+                      : launch_conv3x3<16>(xv, packed, bias, ov, st);
     if (rc) return rc;
     return check_launch("conv3x3_forward");
 }

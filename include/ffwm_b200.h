@@ -123,7 +123,7 @@ int ffwm_grid_warp_backward(const ffwm_tensor4* images, const ffwm_tensor4* flow
 
 /* ---- 3x3 / stride 1 / pad 1 convolution on the tcgen05 tensor cores (fp32 in/out, 3xTF32) --------
  * Replaces the cuDNN call behind nn.Conv2d(Cin, Cout, 3, 1, 1).forward (models/base_networks.py:218-222,
- * 235-246: the generator's ResidualBlock / ConvBlock convolutions) for maps of width 128, 64 or 32, and — with
+ * 235-246: the generator's ResidualBlock / ConvBlock convolutions) for maps of width 128, 64, 32 or 16, and — with
  * weights packed with dgrad=1 — its data gradient.  Weights are packed once per weight update. */
 
 /* number of floats of the packed image of a (cout, cin, 3, 3) weight */
@@ -133,7 +133,7 @@ int64_t ffwm_conv3x3_packed_floats(int cout, int cin);
  * convolution (channels swapped, taps flipped; needs ffwm_conv3x3_packed_floats(cin, cout) floats). */
 int ffwm_conv3x3_pack_weights(const ffwm_tensor4* weight, int dgrad, float* packed, int64_t packed_floats, void* stream);
 
-/* out (B,Cout,H,W) = conv2d(x (B,Cin,H,W), weight, bias, stride 1, padding 1), W in {128,64,32}; bias may be NULL. */
+/* out (B,Cout,H,W) = conv2d(x (B,Cin,H,W), weight, bias, stride 1, padding 1), W in {128,64,32,16}; bias may be NULL. */
 int ffwm_conv3x3_forward(const ffwm_tensor4* x, const float* packed, const float* bias, const ffwm_tensor4* out, void* stream);
 
 #ifdef __cplusplus

@@ -2,7 +2,7 @@
 """Summarise an .ncu-rep (captured with `ncu --set full`) into profiles/<tag>_ncu_summary.txt and
 update profiles/traffic.json (DRAM bytes per launch of each op, read by bench.py's roofline).
 
-    python scripts/ncu_summary.py gpurun_out/prof_r01a.ncu-rep r01a
+    python scripts/ncu_summary.py gpurun_out/prof_r01a.ncu-rep r01a [outdir]
 """
 import csv
 import io
@@ -28,6 +28,8 @@ METRICS = [
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_conflicts"),
     ("smsp__inst_executed_op_shared_ld.sum", "lds"),
     ("smsp__inst_executed_op_global_red.sum", "red_inst"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor_pipe%"),
+    ("sm__inst_executed_pipe_tensor.sum", "tensor_inst"),
 ]
 OPS = {"resample2d_fwd": "resample2d_fwd", "resample2d_bwd": "resample2d_bwd", "block_extractor_fwd": "block_extractor_fwd",
        "block_extractor_bwd": "block_extractor_bwd", "local_attn_reshape_fwd": "local_attn_reshape_fwd",
@@ -41,13 +43,14 @@ def to_bytes(v, unit):
 
 def main():
     rep, tag = sys.argv[1], sys.argv[2]
+    outdir = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "profiles")
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, body = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
     out = ["# ncu --set full --clock-control none summary of %s (per launch; cold cache, serialised)" % os.path.basename(rep),
            "# columns: " + " ".join(n for _, n in METRICS)]
-    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+    traffic_path = os.path.join(outdir, "traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
     for r in body:
         name = r[col["Kernel Name"]]
@@ -63,7 +66,7 @@ def main():
                 wr = to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
                 traffic[key] = rd + wr
     traffic["_source"] = "profiles/%s_ncu_summary.txt" % tag
-    open(os.path.join(ROOT, "profiles", "%s_ncu_summary.txt" % tag), "w").write("\n".join(out) + "\n")
+    open(os.path.join(outdir, "%s_ncu_summary.txt" % tag), "w").write("\n".join(out) + "\n")
     json.dump(traffic, open(traffic_path, "w"), indent=1)
     print("\n".join(out))
 

@@ -22,7 +22,8 @@ def ops():
 @pytest.mark.parametrize("b,cin,cout,h,width", [(1, 8, 64, 4, 128), (2, 16, 64, 8, 128), (1, 3, 64, 128, 128), (2, 195, 195, 10, 128),
                                              (1, 128, 128, 128, 128), (1, 64, 3, 7, 128), (1, 20, 130, 5, 128),
                                              (2, 195, 256, 64, 64), (1, 24, 70, 7, 64), (1, 8, 64, 4, 64), (1, 3, 64, 2, 64),
-                                             (2, 384, 384, 32, 32), (1, 20, 66, 11, 32), (3, 8, 8, 8, 32), (1, 5, 3, 1, 32)])
+                                             (2, 384, 384, 32, 32), (1, 20, 66, 11, 32), (3, 8, 8, 8, 32), (1, 5, 3, 1, 32),
+                                             (2, 256, 512, 16, 16), (1, 12, 70, 5, 16), (1, 8, 8, 19, 16)])
 def test_conv3x3_forward_matches_fp64(ops, b, cin, cout, h, width):
     g = torch.Generator().manual_seed(cin * 1000 + cout + width)
     x = torch.randn(b, cin, h, width, generator=g)
@@ -41,7 +42,7 @@ def test_conv3x3_forward_matches_fp64(ops, b, cin, cout, h, width):
     assert rel(out2.cpu(), want - bias.double().view(1, -1, 1, 1)) <= tol
 
 
-@pytest.mark.parametrize("wd", [128, 64, 32])
+@pytest.mark.parametrize("wd", [128, 64, 32, 16])
 def test_conv3x3_dgrad_packing(ops, wd):
     g = torch.Generator().manual_seed(5)
     b, cin, cout, h = 2, 24, 70, 9
