@@ -1,11 +1,11 @@
 """Convolution layer of the mirrored networks: `nn.Conv2d` whose eligible calls run on the
 hand-written tcgen05 kernel (ffwm_b200/csrc/conv3x3_tc.cu) instead of cuDNN.
 
-Eligible: CUDA fp32, 3x3, stride 1, padding 1, dilation 1, groups 1, zero padding, map width 128, 64,
-32 or 16 — the generator's residual / attention / reconstruction / pixel-shuffle convolutions at all
-three decoder scales, FlowNet's 3x3 layers down to 32x32, VGG19's blocks 1-4 and LightCNN's 3x3
-layers down to 16.  Everything else (strided 4x4 / 7x7 / 5x5 / 1x1 layers,
-maps of 8x8 and below) stays on cuDNN (library).
+Eligible: CUDA fp32, 3x3, stride 1, padding 1, dilation 1, groups 1, zero padding, map width 128, 64
+or 32 — the generator's residual / attention / reconstruction / pixel-shuffle convolutions at all
+three decoder scales, FlowNet's 3x3 layers down to 32x32, VGG19's blocks 1-3 and LightCNN's 3x3
+layers at 64 and 32.  Everything else (strided 4x4 / 7x7 / 5x5 / 1x1 layers,
+maps of 16x16 and below) stays on cuDNN (library).
 
     forward        conv3x3_tc (implicit GEMM, 3xTF32 split: fp32-level accuracy)
     grad input     the same kernel with the weights packed transposed + flipped
@@ -21,11 +21,14 @@ from torch.autograd import Function
 from . import ops
 
 ENABLED = True          # set False to force cuDNN everywhere (A/B measurements)
+# The kernel also handles width 16, but there a map is one or two CTAs per (image, channel tile) with a
+# long serial K loop: measured slower than cuDNN inside the train step (98.4 -> 101.8 ms), so it is off.
+WIDTHS = (128, 64, 32)
 
 
 def eligible(x, weight, stride, padding, dilation, groups, padding_mode="zeros"):
     return (ENABLED and x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.dim() == 4
-            and x.size(3) in (128, 64, 32, 16) and tuple(weight.shape[2:]) == (3, 3) and tuple(stride) == (1, 1)
+            and x.size(3) in WIDTHS and tuple(weight.shape[2:]) == (3, 3) and tuple(stride) == (1, 1)
             and tuple(padding) == (1, 1) and tuple(dilation) == (1, 1) and groups == 1 and padding_mode == "zeros")
 
 

@@ -50,6 +50,12 @@ class FFWMTrainer:
             if state is not None:
                 net.load_state_dict(state)
         self.model_names = ['netG', 'netD', 'flowNetF', 'flowNetB']
+        # LightCNN is a frozen feature extractor: the reference leaves requires_grad=True on its
+        # weights and so computes 14.5 GFLOP/image of weight gradients that no optimiser ever reads
+        # (SURVEY 8a a15).  They are not computed here; every loss and every applied gradient is
+        # unchanged (the gradient w.r.t. the generated image still flows through the network).
+        for p in self.lightCNN.parameters():
+            p.requires_grad_(False)
 
         self.criterionL1 = torch.nn.L1Loss().to(dev)
         self.criterionIllu = losses.MSL1Loss(self.criterionL1).to(dev)

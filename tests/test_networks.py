@@ -77,14 +77,16 @@ def test_generator_refuses_cpu_tensors(nets):
 
 
 # ------------------------------------------------------------------ GPU: every net, f64 and f32
-# fp32 tolerances (relative to max|ref|, reference = float64 CPU): plain conv stacks 2e-3; the
+# fp32 tolerances (relative to max|ref|, reference = float64 CPU): plain conv stacks 2e-3 on cuDNN
+# FFMA, 1e-2 where the 3x3 layers run on the tcgen05 3xTF32 kernel (FlowNet: measured 7e-3 on the first
+# layer's weight gradient after 30 conv+BN(batch of 2) layers of back-propagation); the
 # generator's flow gradients pass through ~60 conv+BN(batch of 2) layers (3e-2).  LightCNN's
 # max-feature-map is piecewise linear: rounding flips a few max selections and reroutes their
 # gradient, so its input gradient is the noisiest quantity here — measured on B200 (scripts/
 # diag_lightcnn.py): forward 2e-5 / gradient max 4e-2, L2 1e-2 with the tcgen05 3xTF32 convolutions,
 # forward 9e-7 / gradient max 6e-3, L2 1.5e-3 with cuDNN FFMA fp32.  The float64 runs are the tight
 # check (1e-8; float64 never takes the tensor-core path).
-F32_TOL = {"flownet16": 2e-3, "netD": 2e-3, "lightcnn": 8e-2, "netG": 3e-2}
+F32_TOL = {"flownet16": 1e-2, "netD": 2e-3, "lightcnn": 8e-2, "netG": 3e-2}
 
 
 @pytest.mark.gpu
