@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "gather_tiled.cuh"
 #include "scatter_tiled.cuh"
+#include "scatter_rows.cuh"
 
 namespace ffwm {
 
@@ -64,13 +65,36 @@ __device__ __forceinline__ void corner_offsets(const Corner<T>& c, int sh, int s
     o[3] = c.v[3] ? y1 * sh + x1 * sw : 0;
 }
 
+}  // namespace ffwm
+#include "grid_warp_roll.cuh"
+namespace ffwm {
+
 // Tap list of one output pixel for the tiled scatter (scatter_tiled.cuh): the four bilinear
 // corners; corners outside the image are skipped (zeros padding).
 struct GridWarpScatterGeo {
     static constexpr int NT = 4;
     static constexpr int RW = 31;
+    static constexpr int NW = 2;                 // scatter_rows.cuh: 2 x 2 window
+    static constexpr bool CLAMP = false;         // zeros padding: taps outside the image are dropped
     View<const float> flow;
     int hi, wi;
+    // scatter_rows.cuh: the 2x2 window in region coordinates; column weights (wx1, wx0), row weights (wy1, wy0)
+    __device__ __forceinline__ bool window(int b, int y, int x, int rx0, int ry0, int& cb, int& rb, float* wx, float* wy) const {
+        const float* f = flow.p + b * flow.sb + y * flow.sh + x * flow.sw;
+        const float gx = __ldg(f), gy = __ldg(f + flow.sc);
+        const float ix = ((gx + 1) * wi - 1) / 2;
+        const float iy = ((gy + 1) * hi - 1) / 2;
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        const bool near = fx0 >= float(rx0) && fx0 + 1.f <= float(rx0 + RW - 1) &&
+                          fy0 >= float(ry0) && fy0 + 1.f <= float(ry0 + RW - 1);
+        if (!near) return false;
+        const int x0 = int(fx0), y0 = int(fy0);
+        wx[0] = float(x0 + 1) - ix; wx[1] = ix - float(x0);
+        wy[0] = float(y0 + 1) - iy; wy[1] = iy - float(y0);
+        cb = x0 - rx0;
+        rb = y0 - ry0;
+        return true;
+    }
     __device__ __forceinline__ void region_origin(int tx0, int ty0, int ml, int& rx0, int& ry0) const {
         rx0 = tx0 - ml;
         ry0 = ty0 - ml;
@@ -339,6 +363,15 @@ static int grid_warp_forward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, con
     if ((int64_t)out.n * out.c * out.h * out.w == 0) return FFWM_OK;
     if (out.n > 65535) { set_error("grid_warp: batch %d > 65535", out.n); return FFWM_ERR_TOO_LARGE; }
     if constexpr (sizeof(T) == 4) {
+        // rolling-strip gather (roll_gather.cuh) for maps of equal size sampled near the identity
+        // (measured at the cfg5 point: 0.59 ms against 0.37 ms for the direct kernel — with four taps the ring fill
+        // costs more than the gather saves — so it is opt-in: FFWM_FORCE_ROLL)
+        if (img.h == out.h && img.w == out.w && getenv("FFWM_FORCE_ROLL") &&
+            roll_applicable(out.n, out.c, out.h, out.w, img, ceil_div(out.c, 32))) {
+            const int rc2 = launch_grid_warp_roll<0>(img, flow, View<const float>{}, out, out.n, out.c, out.h, out.w, st);
+            if (rc2) return rc2;
+            return check_launch("grid_warp_forward(roll)");
+        }
         // measured at the cfg5 point: direct 0.38 ms (43 % of HBM) vs tiled 0.68 ms — with only four
         // taps the slab fill costs more than the gather saves, so the tiled forward is opt-in
         if (getenv("FFWM_GRID_WARP_TILED_FWD") && img.h == out.h && img.w == out.w &&
@@ -388,11 +421,19 @@ static int grid_warp_backward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, co
         // grad_images through the tiled scatter when the maps are large and of equal size (a flow
         // that is a perturbed identity then lands inside the tile's halo)
         if (gi.p && img.h == gout.h && img.w == gout.w && scatter_tiled_applicable(gout, gi)) {
-            int rc2 = launch_scatter_tiled(GridWarpScatterGeo{flow, img.h, img.w}, gout, gi, 7, st);
+            int rc2 = getenv("FFWM_SCATTER_TILED") ? launch_scatter_tiled(GridWarpScatterGeo{flow, img.h, img.w}, gout, gi, 7, st)
+                                                   : launch_scatter_rows(GridWarpScatterGeo{flow, img.h, img.w}, gout, gi, 7, st);
             if (rc2) return rc2;
             if ((rc2 = check_launch("grid_warp_backward(tiled scatter)"))) return rc2;
             if (!gf.p) return FFWM_OK;
             gi.p = nullptr;
+        }
+        if (!gi.p && gf.p && img.h == gout.h && img.w == gout.w && !getenv("FFWM_DISABLE_TILED_GFLOW") &&
+            (getenv("FFWM_FORCE_ROLL") || getenv("FFWM_ROLL_GFLOW")) &&     // 0.95 ms against 0.90 ms tiled: opt-in
+            roll_applicable(gout.n, gout.c, gout.h, gout.w, img, ceil_div(gout.h, roll_segment_rows(gout.n, gout.h, gout.w)))) {
+            const int rc2 = launch_grid_warp_roll<1>(img, flow, gout, gf, gout.n, gout.c, gout.h, gout.w, st);
+            if (rc2) return rc2;
+            return check_launch("grid_warp_backward(roll flow gradient)");
         }
         if (!gi.p && gf.p && img.h == gout.h && img.w == gout.w && !getenv("FFWM_DISABLE_TILED_GFLOW") &&
             (int64_t)(img.h - 1) * img.sh + (int64_t)(img.w - 1) * img.sw < (1 << 30) &&

@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "gather_tiled.cuh"
 #include "scatter_tiled.cuh"
+#include "scatter_rows.cuh"
 
 namespace ffwm {
 
@@ -78,8 +79,42 @@ template <int HALF>
 struct Resample2dScatterGeo {
     static constexpr int NT = 4 * HALF * HALF;
     static constexpr int RW = 31;
+    static constexpr int NW = 2 * HALF;          // scatter_rows.cuh: window width (dilation 1 only)
+    static constexpr bool CLAMP = true;          // taps outside the image fold onto the border (N5)
     View<const float> in2;
     int dil, ih, iw;
+    // window position (left/top to right/bottom) of the reference's tap index: 2f -> floor - f, 2f+1 -> floor + f + 1
+    static __device__ __forceinline__ constexpr int win_pos(int k) { return (k & 1) ? HALF + (k >> 1) : HALF - 1 - (k >> 1); }
+    // scatter_rows.cuh: the NW x NW window of a pixel in region coordinates and its separable K2 weights
+    // (column weight, row weight / normaliser; truncation quirk of SURVEY N2 as in taps()).  dilation 1.
+    __device__ __forceinline__ bool window(int b, int y, int x, int rx0, int ry0, int& cb, int& rb, float* wx, float* wy) const {
+        constexpr int N2 = 2 * HALF;
+        const float* f = in2.p + b * in2.sb + y * in2.sh + x * in2.sw;
+        const float dx = f[0], dy = f[in2.sc], sigma = f[2 * in2.sc];
+        const float xf = float(x) + dx, yf = float(y) + dy;
+        const float fxf = floorf(xf), fyf = floorf(yf);
+        const bool near = fxf - float(HALF - 1) >= float(rx0) && fxf + float(HALF) <= float(rx0 + RW - 1) &&
+                          fyf - float(HALF - 1) >= float(ry0) && fyf + float(HALF) <= float(ry0 + RW - 1);
+        if (!near) return false;
+        const float alpha2 = xf - float(f2i(xf)), beta2 = yf - float(f2i(yf));
+        float d2x[N2], d2y[N2], qx[N2], qy[N2];
+#pragma unroll
+        for (int k = 0; k < HALF; ++k) {
+            d2x[2 * k] = float(k) + alpha2;
+            d2x[2 * k + 1] = float(1. + k) - alpha2;
+            d2y[2 * k] = float(k) + beta2;
+            d2y[2 * k + 1] = float(1. + k) - beta2;
+        }
+        const float sum2 = tap_weights<float, HALF>(d2x, d2y, sigma, qx, qy);
+#pragma unroll
+        for (int k = 0; k < N2; ++k) {
+            wx[win_pos(k)] = qx[k];
+            wy[win_pos(k)] = sum2 == 0.f ? qy[k] * 1e8f : qy[k] / sum2;
+        }
+        cb = int(fxf) - (HALF - 1) - rx0;
+        rb = int(fyf) - (HALF - 1) - ry0;
+        return true;
+    }
     __device__ __forceinline__ void region_origin(int tx0, int ty0, int ml, int& rx0, int& ry0) const {
         rx0 = tx0 - ml;
         ry0 = ty0 - ml;
@@ -111,6 +146,10 @@ struct Resample2dScatterGeo {
             }
     }
 };
+
+}  // namespace ffwm
+#include "resample2d_roll.cuh"
+namespace ffwm {
 
 // ---------------------------------------------------------------- forward
 template <typename T, int HALF>
@@ -795,6 +834,15 @@ static int resample2d_forward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, co
     if (in1.h == 0 || in1.w == 0) { set_error("resample2d: empty input1 plane"); return FFWM_ERR_SHAPE; }
     const int half = ks / 2;
     if constexpr (sizeof(T) == 4) {
+        // rolling-strip gather (roll_gather.cuh): kernel_size 2 and 4, dilation 1
+        // measured at the cfg5 point (scripts/roll_ab.py): kernel_size 4 0.89 ms (tiled gather 1.05, direct 1.41);
+        // kernel_size 2 0.67 ms against 0.53 ms for the direct kernel, so 4-tap calls stay direct unless forced
+        if ((half == 2 || (half == 1 && getenv("FFWM_FORCE_ROLL"))) && dil == 1 && in1.n >= out.n &&
+            roll_applicable(out.n, out.c, out.h, out.w, in1, ceil_div(out.c, 32))) {
+            const int rc2 = half == 1 ? launch_fwd_roll<1>(in1, in2, out, st) : launch_fwd_roll<2>(in1, in2, out, st);
+            if (rc2) return rc2;
+            return check_launch("resample2d_forward(roll)");
+        }
         const int hmax = (15 - (2 * half - 1) * dil) / 2;
         // 16-tap kernels only: with 4 taps the direct kernel (0.54 ms at the cfg5 point) beats the
         // tiled one (0.78 ms), whose slab fill then outweighs the gather it saves
@@ -855,14 +903,26 @@ static int resample2d_backward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, c
         if (g1.p && (half == 1 || half == 2) && dil >= 1 && hmax >= 2 && scatter_tiled_applicable(gout, g1)) {
             const int ml = hmax + (half - 1) * dil;
             int rc2;
-            if (half == 1) rc2 = launch_scatter_tiled(Resample2dScatterGeo<1>{in2, dil, in1.h, in1.w}, gout, g1, ml, st);
+            if (dil == 1 && !getenv("FFWM_SCATTER_TILED")) {      // row-owner scatter (scatter_rows.cuh)
+                if (half == 1) rc2 = launch_scatter_rows(Resample2dScatterGeo<1>{in2, dil, in1.h, in1.w}, gout, g1, ml, st);
+                else rc2 = launch_scatter_rows(Resample2dScatterGeo<2>{in2, dil, in1.h, in1.w}, gout, g1, ml, st);
+            } else if (half == 1) rc2 = launch_scatter_tiled(Resample2dScatterGeo<1>{in2, dil, in1.h, in1.w}, gout, g1, ml, st);
             else rc2 = launch_scatter_tiled(Resample2dScatterGeo<2>{in2, dil, in1.h, in1.w}, gout, g1, ml, st);
             if (rc2) return rc2;
             if ((rc2 = check_launch("resample2d_backward(tiled scatter)"))) return rc2;
             if (!g2.p) return FFWM_OK;
             g1.p = nullptr;
         }
-        // flow gradient through the tiled gather
+        // flow gradient through the rolling-strip gather, else the tiled gather
+        // (measured: 1.74 / 1.28 ms for kernel_size 4 / 2 against 1.70 / 1.08 ms for the tiled gather below, so the
+        // rolling flow gradient is opt-in: FFWM_FORCE_ROLL or FFWM_ROLL_GFLOW)
+        if (!g1.p && g2.p && (half == 1 || half == 2) && dil == 1 && !getenv("FFWM_DISABLE_TILED_GFLOW") &&
+            (getenv("FFWM_FORCE_ROLL") || getenv("FFWM_ROLL_GFLOW")) &&
+            roll_applicable(gout.n, gout.c, gout.h, gout.w, in1, ceil_div(gout.h, roll_segment_rows(gout.n, gout.h, gout.w)))) {
+            const int rc2 = half == 1 ? launch_gflow_roll<1>(in1, in2, gout, g2, st) : launch_gflow_roll<2>(in1, in2, gout, g2, st);
+            if (rc2) return rc2;
+            return check_launch("resample2d_backward(roll flow gradient)");
+        }
         if (!g1.p && g2.p && (half == 1 || half == 2) && dil >= 1 && hmax >= 2 &&
             (int64_t)(in1.h - 1) * in1.sh + (int64_t)(in1.w - 1) * in1.sw < (1 << 30) &&
             gather_tiled_applicable(gout.n, gout.c, gout.h, gout.w, in1) && !getenv("FFWM_DISABLE_TILED_GFLOW")) {
