@@ -79,14 +79,14 @@ struct GridWarpScatterGeo {
     View<const float> flow;
     int hi, wi;
     // scatter_rows.cuh: the 2x2 window in region coordinates; column weights (wx1, wx0), row weights (wy1, wy0)
-    __device__ __forceinline__ bool window(int b, int y, int x, int rx0, int ry0, int& cb, int& rb, float* wx, float* wy) const {
+    __device__ __forceinline__ bool window(int b, int y, int x, int rx0, int ry0, int rw, int rh, int& cb, int& rb, float* wx, float* wy) const {
         const float* f = flow.p + b * flow.sb + y * flow.sh + x * flow.sw;
         const float gx = __ldg(f), gy = __ldg(f + flow.sc);
         const float ix = ((gx + 1) * wi - 1) / 2;
         const float iy = ((gy + 1) * hi - 1) / 2;
         const float fx0 = floorf(ix), fy0 = floorf(iy);
-        const bool near = fx0 >= float(rx0) && fx0 + 1.f <= float(rx0 + RW - 1) &&
-                          fy0 >= float(ry0) && fy0 + 1.f <= float(ry0 + RW - 1);
+        const bool near = fx0 >= float(rx0) && fx0 + 1.f <= float(rx0 + rw - 1) &&
+                          fy0 >= float(ry0) && fy0 + 1.f <= float(ry0 + rh - 1);
         if (!near) return false;
         const int x0 = int(fx0), y0 = int(fy0);
         wx[0] = float(x0 + 1) - ix; wx[1] = ix - float(x0);
@@ -422,7 +422,7 @@ static int grid_warp_backward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, co
         // that is a perturbed identity then lands inside the tile's halo)
         if (gi.p && img.h == gout.h && img.w == gout.w && scatter_tiled_applicable(gout, gi)) {
             int rc2 = getenv("FFWM_SCATTER_TILED") ? launch_scatter_tiled(GridWarpScatterGeo{flow, img.h, img.w}, gout, gi, 7, st)
-                                                   : launch_scatter_rows(GridWarpScatterGeo{flow, img.h, img.w}, gout, gi, 7, st);
+                                                   : launch_scatter_rows(GridWarpScatterGeo{flow, img.h, img.w}, gout, gi, st);
             if (rc2) return rc2;
             if ((rc2 = check_launch("grid_warp_backward(tiled scatter)"))) return rc2;
             if (!gf.p) return FFWM_OK;

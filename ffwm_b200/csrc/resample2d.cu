@@ -87,14 +87,14 @@ struct Resample2dScatterGeo {
     static __device__ __forceinline__ constexpr int win_pos(int k) { return (k & 1) ? HALF + (k >> 1) : HALF - 1 - (k >> 1); }
     // scatter_rows.cuh: the NW x NW window of a pixel in region coordinates and its separable K2 weights
     // (column weight, row weight / normaliser; truncation quirk of SURVEY N2 as in taps()).  dilation 1.
-    __device__ __forceinline__ bool window(int b, int y, int x, int rx0, int ry0, int& cb, int& rb, float* wx, float* wy) const {
+    __device__ __forceinline__ bool window(int b, int y, int x, int rx0, int ry0, int rw, int rh, int& cb, int& rb, float* wx, float* wy) const {
         constexpr int N2 = 2 * HALF;
         const float* f = in2.p + b * in2.sb + y * in2.sh + x * in2.sw;
         const float dx = f[0], dy = f[in2.sc], sigma = f[2 * in2.sc];
         const float xf = float(x) + dx, yf = float(y) + dy;
         const float fxf = floorf(xf), fyf = floorf(yf);
-        const bool near = fxf - float(HALF - 1) >= float(rx0) && fxf + float(HALF) <= float(rx0 + RW - 1) &&
-                          fyf - float(HALF - 1) >= float(ry0) && fyf + float(HALF) <= float(ry0 + RW - 1);
+        const bool near = fxf - float(HALF - 1) >= float(rx0) && fxf + float(HALF) <= float(rx0 + rw - 1) &&
+                          fyf - float(HALF - 1) >= float(ry0) && fyf + float(HALF) <= float(ry0 + rh - 1);
         if (!near) return false;
         const float alpha2 = xf - float(f2i(xf)), beta2 = yf - float(f2i(yf));
         float d2x[N2], d2y[N2], qx[N2], qy[N2];
@@ -904,8 +904,8 @@ static int resample2d_backward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, c
             const int ml = hmax + (half - 1) * dil;
             int rc2;
             if (dil == 1 && !getenv("FFWM_SCATTER_TILED")) {      // row-owner scatter (scatter_rows.cuh)
-                if (half == 1) rc2 = launch_scatter_rows(Resample2dScatterGeo<1>{in2, dil, in1.h, in1.w}, gout, g1, ml, st);
-                else rc2 = launch_scatter_rows(Resample2dScatterGeo<2>{in2, dil, in1.h, in1.w}, gout, g1, ml, st);
+                if (half == 1) rc2 = launch_scatter_rows(Resample2dScatterGeo<1>{in2, dil, in1.h, in1.w}, gout, g1, st);
+                else rc2 = launch_scatter_rows(Resample2dScatterGeo<2>{in2, dil, in1.h, in1.w}, gout, g1, st);
             } else if (half == 1) rc2 = launch_scatter_tiled(Resample2dScatterGeo<1>{in2, dil, in1.h, in1.w}, gout, g1, ml, st);
             else rc2 = launch_scatter_tiled(Resample2dScatterGeo<2>{in2, dil, in1.h, in1.w}, gout, g1, ml, st);
             if (rc2) return rc2;
