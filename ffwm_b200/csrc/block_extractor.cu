@@ -8,8 +8,8 @@
 //
 // Execution plans (not the reference's thread-per-element):
 //   forward, k = 2,3 (fp32)  block_extractor_fwd_tiled_kernel: the k*k samples of a flow pixel share a
-//             (k+1)x(k+1) source window held in registers; output rows leave as full 128-byte
-//             stores through a per-warp shared-memory row; source rows are prefetched into L2/L1.
+//             (k+1)x(k+1) source window held in registers; every lane stores its k consecutive floats
+//             of an output row directly; source rows are prefetched into L2/L1.
 //   backward, k = 2,3 (fp32) block_extractor_bwd_window_kernel: the same window folding for the
 //             scatter ((k+1)^2 REDs instead of 4*k*k per flow pixel and channel) and the gather.
 //   any other k / fp64       one thread per output pixel (forward) or per flow pixel x channel
@@ -85,13 +85,16 @@ block_extractor_fwd_kernel(View<const T> src, View<const T> flow, View<T> out, i
     }
 }
 
-// ---- forward, tiled: k is a template parameter -----------------------------------------
+// ---- forward, windowed: k is a template parameter -----------------------------------------
 // A warp owns 32 consecutive flow pixels of one flow row and walks a slice of channels.
 // The k*k samples of one flow pixel share a (k+1)x(k+1) source window (same fractional
 // part, integer offsets 0..k-1), so the window is loaded once into registers — (k+1)^2
-// gathers instead of 4*k*k — and every output row is interleaved through a private
-// shared-memory row so that the k*Wf-wide output rows leave as full 128-byte stores
-// (the output is k*k times larger than the source: this kernel is store-bound).
+// gathers instead of 4*k*k.  The output is k*k times larger than the source, so the kernel is
+// store-bound: every lane stores its k consecutive floats of an output row directly (the warp
+// covers 32*k consecutive floats; k stores of stride k).  Measured at the cfg5 point against
+// transposing each row through shared memory into 128-bit stores: 0.434 vs 0.480 ms for the
+// reference's flow distribution, equal for incoherent flows — the transposition costs three times
+// the L1 wavefronts of the strided stores, and L2 merges the partial sectors.
 // Geometry (weights, clamped indices) is formed per tap with the reference's expressions
 // (block_tap); the shared window is only used when the clamped tap indices really are
 // consecutive, otherwise that pixel gathers its four taps directly.
@@ -100,25 +103,19 @@ constexpr int BE_WARPS = 8;
 template <typename T, int K>
 __global__ void __launch_bounds__(32 * BE_WARPS, 2)
 block_extractor_fwd_tiled_kernel(View<const T> src, View<const T> flow, View<T> out, int chunks, int c_per_block) {
-    __shared__ __align__(16) T stage[BE_WARPS][K * 32];
     const int lane = threadIdx.x, warp = threadIdx.y;
     const int xf0 = blockIdx.x * 32, xf = xf0 + lane;
     const int yf = blockIdx.y * BE_WARPS + warp;
     const int b = blockIdx.z / chunks, chunk = blockIdx.z - b * chunks;
-    if (yf >= flow.h) return;                      // whole warp
-    const int nx = min(32, flow.w - xf0);
-    const bool live = lane < nx;
-    T* row = stage[warp];
+    if (yf >= flow.h || xf >= flow.w) return;
 
     // Separable tap geometry: column part depends on j only, row part on i only.
     int cx[K + 1], cy[K + 1];       // element offsets of the shared window's columns / rows
     T xLP[K], xRP[K], yTP[K], yBP[K];
     bool shared_window = true;
-    T fx_raw = T(0), fy_raw = T(0);
-    if (live) {
-        const T* f = flow.p + b * flow.sb + yf * flow.sh + xf * flow.sw;
-        fx_raw = __ldg(f);
-        fy_raw = __ldg(f + flow.sc);
+    const T* f = flow.p + b * flow.sb + yf * flow.sh + xf * flow.sw;
+    const T fx_raw = __ldg(f), fy_raw = __ldg(f + flow.sc);
+    {
         int prev_xR = 0, prev_yB = 0;
 #pragma unroll
         for (int j = 0; j < K; ++j) {
@@ -135,24 +132,21 @@ block_extractor_fwd_tiled_kernel(View<const T> src, View<const T> flow, View<T> 
     const int c0 = chunk * c_per_block;
     const int c1 = min(c0 + c_per_block, out.c);
     const T* s = src.plane(b, c0);
-    T* obase = out.plane(b, c0) + (yf * K) * out.sh + (xf0 * K) * out.sw;
+    T* obase = out.plane(b, c0) + (yf * K) * out.sh + (xf * K) * out.sw;
     // The first touch of a source row is a DRAM round trip (~1500 cycles under load) and every
     // channel touches new rows: rows are requested far ahead into L2, and the window of channel
     // c+1 is loaded into registers before channel c is computed and stored (software pipeline).
     constexpr int PF_L2 = 16;
-    // full rows of 32 flow pixels leave as 128-bit stores when the layout allows it
-    const bool vec = nx == 32 && out.sw == 1 && (out.sh & 3) == 0 && (out.sc & 3) == 0 && (K * 32) % 4 == 0 &&
-                     (reinterpret_cast<uintptr_t>(out.plane(b, 0) + (yf * K) * out.sh + (xf0 * K)) & 15) == 0;
     T nxt[K + 1][K + 1];
-    if (live && shared_window) {
+    if (shared_window) {
 #pragma unroll
         for (int n = 0; n <= K; ++n)
 #pragma unroll
             for (int m = 0; m <= K; ++m) nxt[n][m] = __ldg(s + cy[n] + cx[m]);
     }
     for (int c = c0; c < c1; ++c, s += src.sc, obase += out.sc) {
-        T win[K + 1][K + 1];
-        if (live && shared_window) {
+        if (shared_window) {
+            T win[K + 1][K + 1];
 #pragma unroll
             for (int n = 0; n <= K; ++n)
 #pragma unroll
@@ -169,47 +163,32 @@ block_extractor_fwd_tiled_kernel(View<const T> src, View<const T> flow, View<T> 
 #pragma unroll
                 for (int n = 0; n <= K; ++n) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + cy[n]));
             }
-        }
 #pragma unroll
-        for (int i = 0; i < K; ++i) {
-            if (live) {
-                if (shared_window) {
+            for (int i = 0; i < K; ++i)
 #pragma unroll
-                    for (int j = 0; j < K; ++j) {
-                        T sample = T(0);
-                        sample += xLP[j] * yTP[i] * win[i][j];
-                        sample += xRP[j] * yTP[i] * win[i][j + 1];
-                        sample += xLP[j] * yBP[i] * win[i + 1][j];
-                        sample += xRP[j] * yBP[i] * win[i + 1][j + 1];
-                        row[lane * K + j] = sample;
-                    }
-                } else {
-                    // rare: the clamped taps of this pixel are not consecutive (float rounding at an
-                    // integer boundary); gather the four taps of every sample directly
+                for (int j = 0; j < K; ++j) {
+                    T sample = T(0);
+                    sample += xLP[j] * yTP[i] * win[i][j];
+                    sample += xRP[j] * yTP[i] * win[i][j + 1];
+                    sample += xLP[j] * yBP[i] * win[i + 1][j];
+                    sample += xRP[j] * yBP[i] * win[i + 1][j + 1];
+                    st_stream(obase + i * out.sh + j * out.sw, sample);
+                }
+        } else {
+            // rare: the clamped taps of this pixel are not consecutive (float rounding at an
+            // integer boundary); gather the four taps of every sample directly
 #pragma unroll 1
-                    for (int j = 0; j < K; ++j) {
-                        const Bilin<T> t = block_tap<T>(fx_raw, fy_raw, xf, yf, j - K / 2, i - K / 2, src.h, src.w);
-                        T sample = T(0);
-                        sample += t.xL_P * t.yT_P * __ldg(s + t.yT * src.sh + t.xL * src.sw);
-                        sample += t.xR_P * t.yT_P * __ldg(s + t.yT * src.sh + t.xR * src.sw);
-                        sample += t.xL_P * t.yB_P * __ldg(s + t.yB * src.sh + t.xL * src.sw);
-                        sample += t.xR_P * t.yB_P * __ldg(s + t.yB * src.sh + t.xR * src.sw);
-                        row[lane * K + j] = sample;
-                    }
+            for (int i = 0; i < K; ++i)
+#pragma unroll 1
+                for (int j = 0; j < K; ++j) {
+                    const Bilin<T> t = block_tap<T>(fx_raw, fy_raw, xf, yf, j - K / 2, i - K / 2, src.h, src.w);
+                    T sample = T(0);
+                    sample += t.xL_P * t.yT_P * __ldg(s + t.yT * src.sh + t.xL * src.sw);
+                    sample += t.xR_P * t.yT_P * __ldg(s + t.yT * src.sh + t.xR * src.sw);
+                    sample += t.xL_P * t.yB_P * __ldg(s + t.yB * src.sh + t.xL * src.sw);
+                    sample += t.xR_P * t.yB_P * __ldg(s + t.yB * src.sh + t.xR * src.sw);
+                    st_stream(obase + i * out.sh + j * out.sw, sample);
                 }
-            }
-            __syncwarp();
-            if (vec) {
-                if (lane < (K * 32) / 4)
-                    __stcs(reinterpret_cast<float4*>(obase + i * out.sh) + lane, reinterpret_cast<const float4*>(row)[lane]);
-            } else {
-#pragma unroll
-                for (int m = 0; m < K; ++m) {
-                    const int idx = m * 32 + lane;
-                    if (idx < nx * K) st_stream(obase + i * out.sh + idx * out.sw, row[idx]);
-                }
-            }
-            __syncwarp();
         }
     }
 }

@@ -28,7 +28,8 @@
 // Pixels whose window leaves the region (|displacement| > ~6 px) keep the per-tap far list of
 // scatter_tiled.cuh (direct REDs, lanes are channels).
 // Measured (ks4 grad_input1, cfg5 point): scatter_tiled 1.73 ms; rows in registers behind a jump
-// table 1.83; read-modify-write rows in shared memory 1.33; sliding window, 32 channels 1.23.
+// table 1.83; read-modify-write rows in shared memory 1.33; sliding window, 32 channels per group and 16 warps
+// 1.23; 64 channels per group: 8 warps 1.23 (latency-bound), 12 warps 1.01, 16 warps (far list cut to fit) 1.01.
 #pragma once
 #include <limits.h>
 #include <stdlib.h>

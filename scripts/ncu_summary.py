@@ -31,9 +31,18 @@ METRICS = [
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor_pipe%"),
     ("sm__inst_executed_pipe_tensor.sum", "tensor_inst"),
 ]
-OPS = {"resample2d_fwd": "resample2d_fwd", "resample2d_bwd": "resample2d_bwd", "block_extractor_fwd": "block_extractor_fwd",
-       "block_extractor_bwd": "block_extractor_bwd", "local_attn_reshape_fwd": "local_attn_reshape_fwd",
-       "local_attn_reshape_bwd": "local_attn_reshape_bwd", "grid_warp_fwd": "grid_warp_fwd", "grid_warp_bwd": "grid_warp_bwd"}
+# kernel-name fragment -> op of the warp microbench; an op launched as several kernels (resample2d_bwd =
+# scatter + flow gradient) gets the SUM of their DRAM bytes (one launch of each)
+KERNEL_OPS = [
+    ("scatter_rows_kernel<Resample2dScatterGeo", "resample2d_bwd"), ("scatter_tiled_kernel<Resample2dScatterGeo", "resample2d_bwd"),
+    ("resample2d_gflow", "resample2d_bwd"), ("resample2d_bwd", "resample2d_bwd"),
+    ("resample2d_fwd", "resample2d_fwd"),
+    ("scatter_rows_kernel<GridWarpScatterGeo", "grid_warp_bwd"), ("scatter_tiled_kernel<GridWarpScatterGeo", "grid_warp_bwd"),
+    ("grid_warp_tiled_kernel<1>", "grid_warp_bwd"), ("grid_warp_roll_kernel<1>", "grid_warp_bwd"), ("grid_warp_bwd", "grid_warp_bwd"),
+    ("grid_warp_fwd", "grid_warp_fwd"), ("grid_warp_tiled_kernel<0>", "grid_warp_fwd"), ("grid_warp_roll_kernel<0>", "grid_warp_fwd"),
+    ("block_extractor_fwd", "block_extractor_fwd"), ("block_extractor_bwd", "block_extractor_bwd"),
+    ("lar_tiled_kernel<float, 3, 1>", "local_attn_reshape_fwd"), ("lar_tiled_kernel<float, 3, 0>", "local_attn_reshape_bwd"),
+]
 
 
 def to_bytes(v, unit):
@@ -52,6 +61,7 @@ def main():
            "# columns: " + " ".join(n for _, n in METRICS)]
     traffic_path = os.path.join(outdir, "traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
+    per_kernel = {}
     for r in body:
         name = r[col["Kernel Name"]]
         short = name.split("(")[0].replace("void ", "").replace("ffwm::", "")
@@ -60,11 +70,14 @@ def main():
             if m in col:
                 vals.append("%s=%s%s" % (n, r[col[m]], units[col[m]] if units[col[m]] not in ("%", "") else ""))
         out.append("%-48s grid=%s block=%s  %s" % (short[:48], r[col["Grid Size"]], r[col["Block Size"]], "  ".join(vals)))
-        for key in OPS:
-            if key in name.replace("_kernel", ""):
+        for frag, key in KERNEL_OPS:
+            if frag in short.replace("(int)", ""):
                 rd = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]])
                 wr = to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
-                traffic[key] = rd + wr
+                per_kernel.setdefault(key, {})[short[:48]] = rd + wr      # last launch of each kernel wins
+                break
+    for key, d in per_kernel.items():
+        traffic[key] = sum(d.values())
     traffic["_source"] = "profiles/%s_ncu_summary.txt" % tag
     open(os.path.join(outdir, "%s_ncu_summary.txt" % tag), "w").write("\n".join(out) + "\n")
     json.dump(traffic, open(traffic_path, "w"), indent=1)
