@@ -26,6 +26,7 @@
 #include "gather_tiled.cuh"
 #include "scatter_tiled.cuh"
 #include "scatter_rows.cuh"
+#include "gather_quad.cuh"
 
 namespace ffwm {
 
@@ -141,6 +142,50 @@ grid_warp_fwd_kernel(View<const T> img, View<const T> flow, View<T> out, int c_p
         st_stream(d, v);
     }
 }
+
+// ---- flow gradient, accumulate-then-weigh (gather_quad.cuh): M = sum_c grad_output[c] * (nw, ne, sw, se), then
+// d out / d ix = -wy1 nw + wy1 ne - wy0 sw + wy0 se,  d out / d iy = -wx1 nw - wx0 ne + wx1 sw + wx0 se  once per pixel.
+struct GwQuadPolicy {
+    static constexpr int NW = 2;
+    static constexpr bool PAD_ZERO = true;                   // zeros padding
+    View<const float> img, flow, go;
+    View<float> gflow;
+    __host__ __device__ __forceinline__ const View<const float>& src() const { return img; }
+    __host__ __device__ __forceinline__ const View<const float>& gout() const { return go; }
+    // record: [1] x0 [2] y0 (bounded), [3] wx0 [4] wx1 [5] wy0 [6] wy1
+    __device__ __forceinline__ int geometry(int b, int y, int x, int rx0, int ry0, float* rec) const {
+        const float* f = flow.p + b * flow.sb + y * flow.sh + x * flow.sw;
+        const float gx = __ldg(f), gy = __ldg(f + flow.sc);
+        const float ix = ((gx + 1) * img.w - 1) / 2;
+        const float iy = ((gy + 1) * img.h - 1) / 2;
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        const int x0 = f2i(fx0), y0 = f2i(fy0);
+        int* ri = reinterpret_cast<int*>(rec);
+        ri[1] = min(max(x0, -8), img.w + 8);
+        ri[2] = min(max(y0, -8), img.h + 8);
+        rec[3] = ix - float(x0);                 // wx0
+        rec[4] = float(x0 + 1) - ix;             // wx1
+        rec[5] = iy - float(y0);                 // wy0
+        rec[6] = float(y0 + 1) - iy;             // wy1
+        const bool near = fx0 >= float(rx0) && fx0 + 1.f <= float(rx0 + GQ_RW - 1) &&
+                          fy0 >= float(ry0) && fy0 + 1.f <= float(ry0 + GQ_RH - 1);
+        return near ? (y0 - ry0) * GQ_RW + (x0 - rx0) : -1;
+    }
+    __device__ __forceinline__ float far_tap(int iy, int ix, const float* plane) const {
+        return ((unsigned)iy < (unsigned)img.h && (unsigned)ix < (unsigned)img.w) ? __ldg(plane + iy * img.sh + ix * img.sw) : 0.f;
+    }
+    __device__ __forceinline__ void finish(const float* M, const float* rec, int b, int y, int x) const {
+        const float wx0 = rec[3], wx1 = rec[4], wy0 = rec[5], wy1 = rec[6];
+        float gix = 0.f, giy = 0.f;
+        gix -= M[0] * wy1; giy -= M[0] * wx1;
+        gix += M[1] * wy1; giy -= M[1] * wx0;
+        gix -= M[2] * wy0; giy += M[2] * wx1;
+        gix += M[3] * wy0; giy += M[3] * wx0;
+        float* o = gflow.p + b * gflow.sb + y * gflow.sh + x * gflow.sw;
+        o[0] = (float(img.w) / 2) * gix;
+        o[gflow.sc] = (float(img.h) / 2) * giy;
+    }
+};
 
 // ---- tiled gathers (gather_tiled.cuh): lanes are channels, the image's halo region in a slab ----
 // MODE 0: forward.  MODE 1: flow gradient (grad_images comes from the tiled scatter).
@@ -429,6 +474,12 @@ static int grid_warp_backward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, co
             if ((rc2 = check_launch("grid_warp_backward(tiled scatter)"))) return rc2;
             if (!gf.p) return FFWM_OK;
             gi.p = nullptr;
+        }
+        if (!gi.p && gf.p && img.h == gout.h && img.w == gout.w && !getenv("FFWM_DISABLE_TILED_GFLOW") &&
+            gather_quad_applicable(gout.n, gout.c, gout.h, gout.w, img)) {
+            const int rc2 = launch_gather_quad(GwQuadPolicy{img, flow, gout, gf}, gout.n, gout.h, gout.w, st);
+            if (rc2) return rc2;
+            return check_launch("grid_warp_backward(quad flow gradient)");
         }
         if (!gi.p && gf.p && img.h == gout.h && img.w == gout.w && !getenv("FFWM_DISABLE_TILED_GFLOW") &&
             (getenv("FFWM_FORCE_ROLL") || getenv("FFWM_ROLL_GFLOW")) &&     // 0.95 ms against 0.90 ms tiled: opt-in

@@ -24,6 +24,7 @@
 #include "gather_tiled.cuh"
 #include "scatter_tiled.cuh"
 #include "scatter_rows.cuh"
+#include "gather_quad.cuh"
 
 namespace ffwm {
 
@@ -557,6 +558,95 @@ static int launch_gflow_tiled(const View<const float>& in1, const View<const flo
     return FFWM_OK;
 }
 
+// --------------------------------------------------------------- flow gradient, accumulate-then-weigh
+// K3 on gather_quad.cuh: M[i][j] = sum_c grad_output[c] * input1[c, window(i,j)] per pixel (window positions,
+// left/top to right/bottom), then the direct kernel's four partial sums A0, A1, A2, Bs as bilinear forms of M and
+// the reference's final SAFE_DIV expressions, once per pixel.  Weights with the reference's double-precision exp.
+template <int HALF>
+struct RsQuadPolicy {
+    static constexpr int NW = 2 * HALF;
+    static constexpr bool PAD_ZERO = false;                  // the reference clamps every tap index: edge replication
+    View<const float> in1, in2, go;
+    View<float> gin2;
+    __host__ __device__ __forceinline__ const View<const float>& src() const { return in1; }
+    __host__ __device__ __forceinline__ const View<const float>& gout() const { return go; }
+    static __device__ __forceinline__ constexpr int win_pos(int k) { return (k & 1) ? HALF + (k >> 1) : HALF - 1 - (k >> 1); }
+
+    // record: [1] [2] first window column / row (unclamped, bounded), [3] sigma [4] alpha [5] beta [6] sum,
+    // [8 .. 8+N2) wx, [8+N2 .. 8+2*N2) wy (reference tap-index order)
+    __device__ __forceinline__ int geometry(int b, int y, int x, int rx0, int ry0, float* rec) const {
+        constexpr int N2 = 2 * HALF;
+        const float* f = in2.p + b * in2.sb + y * in2.sh + x * in2.sw;
+        const float dx = f[0], dy = f[in2.sc], sigma = f[2 * in2.sc];
+        const float xf = float(x) + dx, yf = float(y) + dy;
+        const float fxf = floorf(xf), fyf = floorf(yf);
+        const float alpha = xf - fxf, beta = yf - fyf;
+        float dxs[N2], dys[N2], wx[N2], wy[N2];
+#pragma unroll
+        for (int k = 0; k < HALF; ++k) {
+            dxs[2 * k] = float(k) + alpha;
+            dxs[2 * k + 1] = float(1. + k) - alpha;
+            dys[2 * k] = float(k) + beta;
+            dys[2 * k + 1] = float(1. + k) - beta;
+        }
+        const float sum = tap_weights<float, HALF>(dxs, dys, sigma, wx, wy);
+        int* ri = reinterpret_cast<int*>(rec);
+        ri[1] = min(max(f2i(fxf - float(HALF - 1)), -8), in1.w + 8);
+        ri[2] = min(max(f2i(fyf - float(HALF - 1)), -8), in1.h + 8);
+        rec[3] = sigma; rec[4] = alpha; rec[5] = beta; rec[6] = sum;
+#pragma unroll
+        for (int k = 0; k < N2; ++k) { rec[8 + k] = wx[k]; rec[8 + N2 + k] = wy[k]; }
+        const bool near = fxf - float(HALF - 1) >= float(rx0) && fxf + float(HALF) <= float(rx0 + GQ_RW - 1) &&
+                          fyf - float(HALF - 1) >= float(ry0) && fyf + float(HALF) <= float(ry0 + GQ_RH - 1);
+        return near ? (ri[2] - ry0) * GQ_RW + (ri[1] - rx0) : -1;
+    }
+    __device__ __forceinline__ float far_tap(int iy, int ix, const float* plane) const {
+        return __ldg(plane + clampi(iy, in1.h - 1) * in1.sh + clampi(ix, in1.w - 1) * in1.sw);
+    }
+    __device__ __forceinline__ void finish(const float* M, const float* rec, int b, int y, int x) const {
+        constexpr int N2 = 2 * HALF;
+        const float sigma = rec[3], alpha = rec[4], beta = rec[5], sum = rec[6];
+        float wx[N2], wy[N2];
+#pragma unroll
+        for (int k = 0; k < N2; ++k) { wx[k] = rec[8 + k]; wy[k] = rec[8 + N2 + k]; }
+        RsGradCoef<HALF> co;
+        rs_grad_coef<HALF>(alpha, beta, wx, wy, co);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, bs = 0.f;
+        float Wx = 0.f, Wy = 0.f, AX = 0.f, AY = 0.f, BX = 0.f, BY = 0.f;
+#pragma unroll
+        for (int ki = 0; ki < N2; ++ki) {
+            const float* Mi = M + win_pos(ki) * NW;
+            float r0 = 0.f, rB = 0.f, r2 = 0.f;
+#pragma unroll
+            for (int kj = 0; kj < N2; ++kj) {
+                const float m = Mi[win_pos(kj)];
+                r0 += co.ax[kj] * m;
+                rB += wx[kj] * m;
+                r2 += co.bx[kj] * m;
+            }
+            a0 += wy[ki] * r0;
+            a1 += co.ay[ki] * rB;
+            a2 += co.by[ki] * rB + wy[ki] * r2;
+            bs += wy[ki] * rB;
+            Wx += wx[ki]; Wy += wy[ki];
+            AX += co.ax[ki]; AY += co.ay[ki];
+            BX += co.bx[ki]; BY += co.by[ki];
+        }
+        const float ms2 = -sigma * sigma, s3 = sigma * sigma * sigma;
+        const float G0 = float(safe_div<float>(Wy * AX, ms2));
+        const float G1 = float(safe_div<float>(AY * Wx, ms2));
+        const float G2 = float(safe_div<float>(BY * Wx + Wy * BX, s3));
+        const float g10 = float(safe_div<float>(a0, ms2));
+        const float g11 = float(safe_div<float>(a1, ms2));
+        const float g12 = float(safe_div<float>(a2, s3));
+        const float ss = sum * sum;
+        float* o = gin2.p + b * gin2.sb + y * gin2.sh + x * gin2.sw;
+        o[0] = float(safe_div<float>(g10, sum) - safe_div<float>(G0 * bs, ss));
+        if (gin2.c > 1) o[gin2.sc] = float(safe_div<float>(g11, sum) - safe_div<float>(G1 * bs, ss));
+        if (gin2.c > 2) o[2 * gin2.sc] = float(safe_div<float>(g12, sum) - safe_div<float>(G2 * bs, ss));
+    }
+};
+
 // --------------------------------------------------------------- backward
 // CTA = PX pixels x SL channel slices (PX*SL = 256).  Slice s owns channels
 // s, s+SL, s+2SL, ...  Per channel and tap: one gather of input1, one RED
@@ -912,6 +1002,14 @@ static int resample2d_backward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, c
             if ((rc2 = check_launch("resample2d_backward(tiled scatter)"))) return rc2;
             if (!g2.p) return FFWM_OK;
             g1.p = nullptr;
+        }
+        // flow gradient: accumulate-then-weigh gather (gather_quad.cuh)
+        if (!g1.p && g2.p && (half == 1 || half == 2) && dil == 1 && !getenv("FFWM_DISABLE_TILED_GFLOW") &&
+            gather_quad_applicable(gout.n, gout.c, gout.h, gout.w, in1)) {
+            const int rc2 = half == 1 ? launch_gather_quad(RsQuadPolicy<1>{in1, in2, gout, g2}, gout.n, gout.h, gout.w, st)
+                                      : launch_gather_quad(RsQuadPolicy<2>{in1, in2, gout, g2}, gout.n, gout.h, gout.w, st);
+            if (rc2) return rc2;
+            return check_launch("resample2d_backward(quad flow gradient)");
         }
         // flow gradient through the rolling-strip gather, else the tiled gather
         // (measured: 1.74 / 1.28 ms for kernel_size 4 / 2 against 1.70 / 1.08 ms for the tiled gather below, so the

@@ -77,7 +77,7 @@ def main():
     rs = dict(B=B, C=c, H=r, W=r, Hi=r, Wi=r)
     be = dict(B=shapes["Bb"], C=c, Hs=r, Ws=r, Hf=r, Wf=r, k=3)
     disp2 = t["disp"].clone()
-    variants = [("new", {}), ("old", {"FFWM_DISABLE_ROLL": "1", "FFWM_SCATTER_TILED": "1"})]
+    variants = [("new", {}), ("old", {"FFWM_DISABLE_ROLL": "1", "FFWM_SCATTER_TILED": "1", "FFWM_DISABLE_QUAD": "1"})]
     if os.environ.get("AB_DIRECT"):
         variants.append(("direct", {"FFWM_DISABLE_TILED": "1"}))
     e = torch.empty_like
