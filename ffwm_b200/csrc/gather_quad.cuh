@@ -11,8 +11,9 @@
 // i.e. ONE FFMA per tap and channel into NW*NW per-pixel accumulators M, and F — the Gaussian /
 // bilinear weights, the normaliser, the reference's SAFE_DIVs — once per pixel at the very end.
 //
-// Execution: a CTA owns a 16x16 tile of the output grid (512 threads, one CTA per SM) and stages, per
-// group of 32 channels, the 31 x 32 halo region of the source — PADDED the way the op pads (edge
+// Execution: a CTA owns a 16x16 tile of the output grid (512 threads, one CTA per SM) and stages, 16 channels
+// at a time and double-buffered (the copies of the next 16 channels fly while these are accumulated), the
+// 31 x 32 halo region of the source — PADDED the way the op pads (edge
 // replication / zeros), so windows inside the region need no per-tap clamping: tap (i,j) is
 // `base + i*32 + j` — with 128-bit cp.async where the layout allows.  A warp owns one tile row (16
 // pixels); its lanes are 8 channels x 4 pixels: lane (c8, p4) accumulates M for the pixels 4q + p4,
@@ -42,70 +43,68 @@ __device__ __forceinline__ unsigned gq_smem_u32(const void* p) { return (unsigne
 // vec: unit column stride, rows 16-byte aligned and width % 4 == 0 -> a 4-column chunk is entirely inside or
 // outside the image and goes with one 16-byte cp.async; lane -> (row lane/8 of four, chunk lane%8).
 template <bool PAD_ZERO>
-__device__ __forceinline__ void gq_fill_slab(float* slab, const View<const float>& src, int b, int c0, int nch,
+__device__ __forceinline__ void gq_fill_half(float* slab, const View<const float>& src, int b, int c0, int nch,
                                              int rx0, int ry0, int warp, int lane, bool vec) {
-#pragma unroll 1
-    for (int cc = 0; cc < 32 / GQ_WARPS; ++cc) {
-        const int c = warp * (32 / GQ_WARPS) + cc;
-        const float* plane = src.p + b * src.sb + (int64_t)(c0 + min(c, nch - 1)) * src.sc;   // channels past nch repeat the last one
-        float* sc = slab + c * GQ_CHP;
-        if (vec) {
-            const int rsub = lane >> 3, ch4 = lane & 7;
-            const int gx4 = rx0 + 4 * ch4;
-            const bool col_in = (unsigned)gx4 < (unsigned)src.w;
-            const int gxb = gx4 < 0 ? 0 : src.w - 1;
+    // one HALF of a channel group: 16 channels, warp w copies channel c0 + w
+    const int c = warp;
+    const float* plane = src.p + b * src.sb + (int64_t)(c0 + min(c, max(nch, 1) - 1)) * src.sc;   // channels past nch repeat the last one
+    float* sc = slab + c * GQ_CHP;
+    if (vec) {
+        const int rsub = lane >> 3, ch4 = lane & 7;
+        const int gx4 = rx0 + 4 * ch4;
+        const bool col_in = (unsigned)gx4 < (unsigned)src.w;
+        const int gxb = gx4 < 0 ? 0 : src.w - 1;
 #pragma unroll 2
-            for (int r = rsub; r < GQ_RH; r += 4) {
-                const int gy = ry0 + r;
-                const bool row_in = (unsigned)gy < (unsigned)src.h;
-                float* d = sc + r * GQ_RW + 4 * ch4;
-                if (PAD_ZERO) {
-                    if (row_in && col_in)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(gq_smem_u32(d)), "l"(plane + gy * src.sh + gx4) : "memory");
-                    else
-                        *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = rsub; r < GQ_RH; r += 4) {
+            const int gy = ry0 + r;
+            const bool row_in = (unsigned)gy < (unsigned)src.h;
+            float* d = sc + r * GQ_RW + 4 * ch4;
+            if (PAD_ZERO) {
+                if (row_in && col_in)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(gq_smem_u32(d)), "l"(plane + gy * src.sh + gx4) : "memory");
+                else
+                    *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                const float* rowp = plane + min(max(gy, 0), src.h - 1) * src.sh;
+                if (col_in) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(gq_smem_u32(d)), "l"(rowp + gx4) : "memory");
                 } else {
-                    const float* rowp = plane + min(max(gy, 0), src.h - 1) * src.sh;
-                    if (col_in) {
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(gq_smem_u32(d)), "l"(rowp + gx4) : "memory");
-                    } else {
-                        const float v = __ldg(rowp + gxb);
-                        *reinterpret_cast<float4*>(d) = make_float4(v, v, v, v);
-                    }
+                    const float v = __ldg(rowp + gxb);
+                    *reinterpret_cast<float4*>(d) = make_float4(v, v, v, v);
                 }
             }
-        } else {
-            const int gx = rx0 + lane;
-            const bool col_in = (unsigned)gx < (unsigned)src.w;
-            const int gxc = min(max(gx, 0), src.w - 1);
+        }
+    } else {
+        const int gx = rx0 + lane;
+        const bool col_in = (unsigned)gx < (unsigned)src.w;
+        const int gxc = min(max(gx, 0), src.w - 1);
 #pragma unroll 2
-            for (int r = 0; r < GQ_RH; ++r) {
-                const int gy = ry0 + r;
-                float* d = sc + r * GQ_RW + lane;
-                if (PAD_ZERO) {
-                    if (col_in && (unsigned)gy < (unsigned)src.h)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(gq_smem_u32(d)), "l"(plane + gy * src.sh + gx * src.sw) : "memory");
-                    else
-                        *d = 0.f;
-                } else {
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(gq_smem_u32(d)),
-                                 "l"(plane + min(max(gy, 0), src.h - 1) * src.sh + gxc * src.sw) : "memory");
-                }
+        for (int r = 0; r < GQ_RH; ++r) {
+            const int gy = ry0 + r;
+            float* d = sc + r * GQ_RW + lane;
+            if (PAD_ZERO) {
+                if (col_in && (unsigned)gy < (unsigned)src.h)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(gq_smem_u32(d)), "l"(plane + gy * src.sh + gx * src.sw) : "memory");
+                else
+                    *d = 0.f;
+            } else {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(gq_smem_u32(d)),
+                             "l"(plane + min(max(gy, 0), src.h - 1) * src.sh + gxc * src.sw) : "memory");
             }
         }
     }
 }
 
-// G[c][260] <- t[b, c0+c, tile]; thread -> (channel tid/16, column tid%16), 16 rows; zeros outside.
-__device__ __forceinline__ void gq_fill_tile(float* G, const View<const float>& t, int b, int c0, int nch,
-                                             int ty0, int tx0, int tid) {
-    const int c = tid / GQ_TW, x = tid % GQ_TW;
+// G[c][260] <- t[b, c0+c, tile] for 16 channels; warp -> channel, lane -> (column lane%16, row parity lane/16); zeros outside.
+__device__ __forceinline__ void gq_fill_tile_half(float* G, const View<const float>& t, int b, int c0, int nch,
+                                                  int ty0, int tx0, int warp, int lane) {
+    const int c = warp, x = lane & 15, r0 = lane >> 4;
     const bool ok = c < nch && tx0 + x < t.w;
-    const float* gp = t.p + b * t.sb + (int64_t)(c0 + min(c, nch - 1)) * t.sc + (tx0 + x) * t.sw;
+    const float* gp = t.p + b * t.sb + (int64_t)(c0 + min(c, max(nch, 1) - 1)) * t.sc + (tx0 + x) * t.sw;
     float* d = G + c * GQ_GP + x;
-#pragma unroll 4
-    for (int r = 0; r < GQ_TH; ++r) {
-        const int y = ty0 + r;
+#pragma unroll
+    for (int k = 0; k < GQ_TH / 2; ++k) {
+        const int r = r0 + 2 * k, y = ty0 + r;
         if (ok && y < t.h) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(gq_smem_u32(d + r * GQ_TW)), "l"(gp + y * t.sh) : "memory");
         else d[r * GQ_TW] = 0.f;
     }
@@ -153,40 +152,67 @@ gather_quad_kernel(P pol, int vec) {
     for (int q = 0; q < 4; ++q)
 #pragma unroll
         for (int t = 0; t < NT; ++t) M[q][t] = 0.f;
+    const bool all_near = __all_sync(0xffffffffu, off[0] >= 0 && off[1] >= 0 && off[2] >= 0 && off[3] >= 0);
 
-    for (int c0 = 0; c0 < gout.c; c0 += 32) {
-        const int nch = min(32, gout.c - c0);
-        __syncthreads();                                                 // previous group consumed
-        gq_fill_slab<P::PAD_ZERO>(slab, src, b, c0, nch, rx0, ry0, warp, lane, vec != 0);
-        gq_fill_tile(G, gout, b, c0, nch, ty0, tx0, tid);
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncthreads();
+    // Channel groups go through the shared memory in HALVES of 16 channels, double-buffered: while half h is
+    // accumulated, the cp.asyncs of half h+1 are in flight and those of half h+2 are issued as soon as h is done.
+    const int nhalf = (gout.c + 15) / 16;
+    auto issue = [&](int h) {                                            // fill buffer h & 1 with channels [16h, 16h+16)
+        if (h < nhalf) {
+            const int c0 = 16 * h, nch = min(16, gout.c - c0);
+            gq_fill_half<P::PAD_ZERO>(slab + (h & 1) * 16 * GQ_CHP, src, b, c0, nch, rx0, ry0, warp, lane, vec != 0);
+            gq_fill_tile_half(G + (h & 1) * 16 * GQ_GP, gout, b, c0, nch, ty0, tx0, warp, lane);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");             // one group per half, empty past the end
+    };
+    issue(0);
+    issue(1);
+    for (int h = 0; h < nhalf; ++h) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");             // this thread's copies of half h have landed
+        __syncthreads();                                                 // ... and everybody else's
+        const int c0 = 16 * h, nch = min(16, gout.c - c0);
+        const float* slab_h = slab + (h & 1) * 16 * GQ_CHP;
+        const float* G_h = G + (h & 1) * 16 * GQ_GP;
 #pragma unroll 1
-        for (int s = 0; s < 4; ++s) {
+        for (int s = 0; s < 2; ++s) {
             const int ch = s * 8 + c8;
-            const float* sl = slab + ch * GQ_CHP;
-            const float* gl = G + ch * GQ_GP + warp * GQ_TW + p4;
-            const float* plane = src.p + b * src.sb + (int64_t)(c0 + min(ch, nch - 1)) * src.sc;
+            const float* sl = slab_h + ch * GQ_CHP;
+            const float* gl = G_h + ch * GQ_GP + warp * GQ_TW + p4;
+            if (all_near) {                                              // warp-uniform: no per-pixel branches
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float g = gl[4 * q];                               // zero for channels past nch / pixels outside
-                if (off[q] >= 0) {
+                for (int q = 0; q < 4; ++q) {
+                    const float g = gl[4 * q];                           // zero for channels past nch
                     const float* w = sl + off[q];
 #pragma unroll
                     for (int i = 0; i < NW; ++i)
 #pragma unroll
                         for (int j = 0; j < NW; ++j) M[q][i * NW + j] = fmaf(g, w[i * GQ_RW + j], M[q][i * NW + j]);
-                } else if (off[q] == -1) {
-                    const int* rec = reinterpret_cast<const int*>(recs + (warp * GQ_TW + 4 * q + p4) * GQ_REC);
-                    const int ifx = rec[1], ify = rec[2];
+                }
+            } else {
 #pragma unroll
-                    for (int i = 0; i < NW; ++i)                         // fully unrolled: M must stay in registers
+                for (int q = 0; q < 4; ++q) {
+                    const float g = gl[4 * q];                           // zero for channels past nch / pixels outside
+                    if (off[q] >= 0) {
+                        const float* w = sl + off[q];
 #pragma unroll
-                        for (int j = 0; j < NW; ++j)
-                            M[q][i * NW + j] = fmaf(g, pol.far_tap(ify + i, ifx + j, plane), M[q][i * NW + j]);
+                        for (int i = 0; i < NW; ++i)
+#pragma unroll
+                            for (int j = 0; j < NW; ++j) M[q][i * NW + j] = fmaf(g, w[i * GQ_RW + j], M[q][i * NW + j]);
+                    } else if (off[q] == -1) {
+                        const int* rec = reinterpret_cast<const int*>(recs + (warp * GQ_TW + 4 * q + p4) * GQ_REC);
+                        const int ifx = rec[1], ify = rec[2];
+                        const float* plane = src.p + b * src.sb + (int64_t)(c0 + min(ch, nch - 1)) * src.sc;
+#pragma unroll
+                        for (int i = 0; i < NW; ++i)                     // fully unrolled: M must stay in registers
+#pragma unroll
+                            for (int j = 0; j < NW; ++j)
+                                M[q][i * NW + j] = fmaf(g, pol.far_tap(ify + i, ifx + j, plane), M[q][i * NW + j]);
+                    }
                 }
             }
         }
+        __syncthreads();                                                 // buffer h & 1 is free again
+        issue(h + 2);
     }
     // sum over the 8 channel lanes; lane c8 == 0 finishes pixel 4q + p4
 #pragma unroll
@@ -200,12 +226,21 @@ gather_quad_kernel(P pol, int vec) {
             M[q][t] = v;
         }
     }
-    if (c8 == 0 && y < gout.h) {
+    // the 16 pixels of the row are finished by 16 lanes in parallel: totals go through the (now idle) slab
+    __syncthreads();                                                     // every warp is done with the slab
+    float* tot = slab + warp * (GQ_TW * (NT + 1));                       // [16 pixels][NT + 1]
+    if (c8 == 0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int x = tx0 + 4 * q + p4;
-            if (x < gout.w) pol.finish(M[q], recs + (warp * GQ_TW + 4 * q + p4) * GQ_REC, b, y, x);
-        }
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int t = 0; t < NT; ++t) tot[(4 * q + p4) * (NT + 1) + t] = M[q][t];
+    }
+    __syncwarp();
+    if (lane < GQ_TW && y < gout.h && tx0 + lane < gout.w) {
+        float Mp[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) Mp[t] = tot[lane * (NT + 1) + t];
+        pol.finish(Mp, recs + (warp * GQ_TW + lane) * GQ_REC, b, y, tx0 + lane);
     }
 }
 

@@ -73,6 +73,31 @@ __device__ __forceinline__ T tap_weights(const T* dxs, const T* dys, T sigma, T*
     return sum;
 }
 
+// tap_weights with the single-precision expf (<= 2 ulp) instead of the reference's double-precision exp rounded to
+// float: used by the tiled fp32 kernels that form the geometry of a pixel once per tile and channel
+// group, where the double-precision evaluation (16 exps per pixel) was 11-13 % of all instructions executed.  The
+// difference (1e-7 relative) is far inside the path's 1e-5 / 1e-4 tolerances; the direct kernels keep the double exp.
+__device__ __forceinline__ float gauss_fast(float d, float sigma) {
+    const float num = -d * d, den = 2.f * sigma * sigma;
+    return expf(den == 0.f ? num * 1e8f : num / den);
+}
+template <int HALF>
+__device__ __forceinline__ float tap_weights_fast(const float* dxs, const float* dys, float sigma, float* wx, float* wy) {
+#pragma unroll
+    for (int i = 0; i < 2 * HALF; ++i) {
+        wx[i] = gauss_fast(dxs[i], sigma);
+        wy[i] = gauss_fast(dys[i], sigma);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int fy = 0; fy < HALF; ++fy)
+#pragma unroll
+        for (int fx = 0; fx < HALF; ++fx)
+            sum += (wy[2 * fy] * wx[2 * fx] + wy[2 * fy] * wx[2 * fx + 1] +
+                    wy[2 * fy + 1] * wx[2 * fx] + wy[2 * fy + 1] * wx[2 * fx + 1]);
+    return sum;
+}
+
 // Tap list of one pixel for the tiled scatter (scatter_tiled.cuh): destinations are the clamped
 // tap indices, weights are K2's SAFE_DIV(w, sum) with the truncation quirk of SURVEY N2 —
 // exactly the values the direct kernel below REDs.
@@ -106,7 +131,7 @@ struct Resample2dScatterGeo {
             d2y[2 * k] = float(k) + beta2;
             d2y[2 * k + 1] = float(1. + k) - beta2;
         }
-        const float sum2 = tap_weights<float, HALF>(d2x, d2y, sigma, qx, qy);
+        const float sum2 = tap_weights_fast<HALF>(d2x, d2y, sigma, qx, qy);
 #pragma unroll
         for (int k = 0; k < N2; ++k) {
             wx[win_pos(k)] = qx[k];
@@ -561,7 +586,7 @@ static int launch_gflow_tiled(const View<const float>& in1, const View<const flo
 // --------------------------------------------------------------- flow gradient, accumulate-then-weigh
 // K3 on gather_quad.cuh: M[i][j] = sum_c grad_output[c] * input1[c, window(i,j)] per pixel (window positions,
 // left/top to right/bottom), then the direct kernel's four partial sums A0, A1, A2, Bs as bilinear forms of M and
-// the reference's final SAFE_DIV expressions, once per pixel.  Weights with the reference's double-precision exp.
+// the reference's final SAFE_DIV expressions, once per pixel.
 template <int HALF>
 struct RsQuadPolicy {
     static constexpr int NW = 2 * HALF;
@@ -589,7 +614,7 @@ struct RsQuadPolicy {
             dys[2 * k] = float(k) + beta;
             dys[2 * k + 1] = float(1. + k) - beta;
         }
-        const float sum = tap_weights<float, HALF>(dxs, dys, sigma, wx, wy);
+        const float sum = tap_weights_fast<HALF>(dxs, dys, sigma, wx, wy);
         int* ri = reinterpret_cast<int*>(rec);
         ri[1] = min(max(f2i(fxf - float(HALF - 1)), -8), in1.w + 8);
         ri[2] = min(max(f2i(fyf - float(HALF - 1)), -8), in1.h + 8);
