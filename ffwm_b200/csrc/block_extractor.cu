@@ -50,10 +50,6 @@ __device__ __forceinline__ Bilin<T> block_tap(T flow_x_raw, T flow_y_raw, int xf
     return r;
 }
 
-}  // namespace ffwm
-#include "block_extractor_roll.cuh"
-namespace ffwm {
-
 template <typename T>
 __global__ void __launch_bounds__(256)
 block_extractor_fwd_kernel(View<const T> src, View<const T> flow, View<T> out, int k, int c_per_block) {
@@ -423,13 +419,8 @@ static int block_extractor_forward_t(const ffwm_tensor4* a, const ffwm_tensor4* 
     if (out.n > 65535) { set_error("block_extractor: batch %d > 65535", out.n); return FFWM_ERR_TOO_LARGE; }
     if (src.h == 0 || src.w == 0) { set_error("block_extractor: empty source plane"); return FFWM_ERR_SHAPE; }
     if constexpr (sizeof(T) == 4) if (k == 2 || k == 3) {
-        // rolling-strip gather (roll_gather.cuh) when there are enough strips to fill the GPU
-        // (measured at the cfg5 point: 0.64 ms against 0.48 ms for the register-window kernel below: opt-in)
-        if (getenv("FFWM_FORCE_ROLL") && roll_applicable(out.n, out.c, flow.h, flow.w, src, ceil_div(out.c, 32))) {
-            const int rc2 = k == 2 ? launch_be_fwd_roll<2>(src, flow, out, st) : launch_be_fwd_roll<3>(src, flow, out, st);
-            if (rc2) return rc2;
-            return check_launch("block_extractor_forward(roll)");
-        }
+        // (a rolling-strip channel-lane variant with the source staged in shared memory was measured at 0.64 ms
+        // against 0.30 ms for this kernel at the cfg5 point and removed)
         const int tx = ceil_div(flow.w, 32), ty = ceil_div(flow.h, BE_WARPS);
         // ~8 CTAs per SM overall, at least 4 channels per CTA so the per-pixel geometry stays amortised
         int64_t want = (int64_t)8 * sm_count();

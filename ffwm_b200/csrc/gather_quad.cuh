@@ -261,8 +261,10 @@ inline bool gather_quad_applicable(int n, int c, int h, int w, const View<const 
     if (getenv("FFWM_DISABLE_TILED") || getenv("FFWM_DISABLE_QUAD")) return false;
     if (src.sh < 0 || src.sw < 0 || c < 16 || n > 65535) return false;
     if ((int64_t)(src.h - 1) * src.sh + (int64_t)(src.w - 1) * src.sw >= (1 << 30)) return false;
+    if (ceil_div(h, GQ_TH) > 65535) return false;
+    if (getenv("FFWM_FORCE_TILED")) return true;          // tests: small ragged shapes through the tiled kernels
     const int64_t tiles = (int64_t)ceil_div(w, GQ_TW) * ceil_div(h, GQ_TH) * n;
-    return tiles >= sm_count() / 2 && ceil_div(h, GQ_TH) <= 65535;
+    return tiles >= sm_count() / 2;
 }
 
 }  // namespace ffwm

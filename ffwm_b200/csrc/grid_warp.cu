@@ -23,7 +23,6 @@
 //   shared memory and stored once (ATen does the same per-pixel reduction but
 //   serially over all C in one thread).
 #include "common.cuh"
-#include "gather_tiled.cuh"
 #include "scatter_tiled.cuh"
 #include "scatter_rows.cuh"
 #include "gather_quad.cuh"
@@ -65,10 +64,6 @@ __device__ __forceinline__ void corner_offsets(const Corner<T>& c, int sh, int s
     o[2] = c.v[2] ? y1 * sh + x0 * sw : 0;
     o[3] = c.v[3] ? y1 * sh + x1 * sw : 0;
 }
-
-}  // namespace ffwm
-#include "grid_warp_roll.cuh"
-namespace ffwm {
 
 // Tap list of one output pixel for the tiled scatter (scatter_tiled.cuh): the four bilinear
 // corners; corners outside the image are skipped (zeros padding).
@@ -187,136 +182,6 @@ struct GwQuadPolicy {
     }
 };
 
-// ---- tiled gathers (gather_tiled.cuh): lanes are channels, the image's halo region in a slab ----
-// MODE 0: forward.  MODE 1: flow gradient (grad_images comes from the tiled scatter).
-// Per-pixel parameters: 4 tap offsets (INT_MIN for a corner outside the image: zeros padding) and
-// either the 4 bilinear weights (forward) or the d/dix, d/diy coefficient of each corner (gradient).
-constexpr int GW_PW = 16;     // 4 offsets | 4 weights or d/dix coefficients | 4 d/diy coefficients | far flag, pad
-
-template <int MODE>
-__global__ void __launch_bounds__(GT_THREADS, 1)
-grid_warp_tiled_kernel(View<const float> img, View<const float> flow, View<const float> gout, View<float> dst) {
-    extern __shared__ __align__(16) unsigned char gt_smem_raw[];
-    float* slab = reinterpret_cast<float*>(gt_smem_raw);               // [32][961]
-    float* prm = slab + 32 * GT_RPX;                                   // [256][16]
-    float* accs = prm + GT_NPX * GW_PW;                                // grad: [16 warps][16 px][2]
-    float* aux = accs + GT_WARPS * GT_TW * 2;                          // fwd: staging [16][32][17]; grad: G [32][257]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tx0 = blockIdx.x * GT_TW, ty0 = blockIdx.y * GT_TH, b = blockIdx.z;
-    const int rx0 = tx0 - 7, ry0 = ty0 - 7;
-    const int oh = MODE == 0 ? dst.h : gout.h, ow = MODE == 0 ? dst.w : gout.w;
-    const int nc = MODE == 0 ? dst.c : gout.c;
-
-    for (int i = tid; i < GT_WARPS * GT_TW * 2; i += GT_THREADS) accs[i] = 0.f;
-    if (tid < GT_NPX) {
-        const int y = ty0 + tid / GT_TW, x = tx0 + tid % GT_TW;
-        if (y < oh && x < ow) {
-            const float* f = flow.p + b * flow.sb + y * flow.sh + x * flow.sw;
-            const Corner<float> cr = corners<float>(__ldg(f), __ldg(f + flow.sc), img.h, img.w);
-            const int y0 = cr.o[0], x0 = cr.o[1], y1 = cr.o[2], x1 = cr.o[3];
-            float* P = prm + tid * GW_PW;
-            int* Pi = reinterpret_cast<int*>(P);
-            Pi[0] = cr.v[0] ? gt_tap_offset(y0, x0, ry0, rx0, img.sh, img.sw) : INT_MIN;
-            Pi[1] = cr.v[1] ? gt_tap_offset(y0, x1, ry0, rx0, img.sh, img.sw) : INT_MIN;
-            Pi[2] = cr.v[2] ? gt_tap_offset(y1, x0, ry0, rx0, img.sh, img.sw) : INT_MIN;
-            Pi[3] = cr.v[3] ? gt_tap_offset(y1, x1, ry0, rx0, img.sh, img.sw) : INT_MIN;
-            int anyfar = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) anyfar |= (Pi[k] < 0 && Pi[k] != INT_MIN);
-            if (MODE == 0) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) P[4 + k] = cr.v[k] ? cr.w[k] : 0.f;
-            } else {
-                P[4] = -cr.wy1; P[5] = cr.wy1; P[6] = -cr.wy0; P[7] = cr.wy0;      // d out / d ix per corner
-                P[8] = -cr.wx1; P[9] = -cr.wx0; P[10] = cr.wx1; P[11] = cr.wx0;    // d out / d iy per corner
-            }
-            Pi[12] = anyfar;
-        }
-    }
-    float* acc = accs + warp * (GT_TW * 2);
-    const int y = ty0 + warp;
-    for (int c0 = 0; c0 < nc; c0 += 32) {
-        const int nch = min(32, nc - c0);
-        __syncthreads();
-        gt_fill_slab(slab, img, b, c0, nch, ry0, rx0, warp, lane);
-        if (MODE == 1) gt_fill_tile(aux, gout, b, c0, nch, ty0, tx0, tid);
-        gt_fill_wait();
-        __syncthreads();
-        if (y < oh) {
-            const float* slab_lane = slab + lane * GT_RPX;
-            const float* plane_lane = img.p + b * img.sb + (int64_t)(c0 + min(lane, nch - 1)) * img.sc;
-            float* stage = aux + warp * (32 * GT_SPITCH);
-            const float* G_lane = aux + lane * GT_GPITCH + warp * GT_TW;
-#pragma unroll 1
-            for (int p4 = 0; p4 < GT_TW / 4; ++p4) {
-                float red[8];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int px = p4 * 4 + k;
-                    red[2 * k] = red[2 * k + 1] = 0.f;
-                    if (tx0 + px < ow) {                                    // warp-uniform
-                        const float4* P4 = reinterpret_cast<const float4*>(prm + (warp * GT_TW + px) * GW_PW);
-                        const float4 o4 = P4[0], w4 = P4[1];
-                        const int off[4] = {__float_as_int(o4.x), __float_as_int(o4.y), __float_as_int(o4.z), __float_as_int(o4.w)};
-                        float v[4];
-                        if (reinterpret_cast<const int*>(P4)[12] == 0) {
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) v[t] = off[t] == INT_MIN ? 0.f : slab_lane[off[t]];
-                        } else {
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) v[t] = off[t] == INT_MIN ? 0.f : gt_load(slab_lane, plane_lane, off[t]);
-                        }
-                        if (MODE == 0) {
-                            float r = 0.f;
-                            r += v[0] * w4.x;
-                            r += v[1] * w4.y;
-                            r += v[2] * w4.z;
-                            r += v[3] * w4.w;
-                            stage[lane * GT_SPITCH + px] = r;
-                        } else {
-                            const float4 y4 = P4[2];
-                            const float g = lane < nch ? G_lane[px] : 0.f;
-                            float gx = 0.f, gy = 0.f;
-                            gx += v[0] * w4.x * g; gy += v[0] * y4.x * g;
-                            gx += v[1] * w4.y * g; gy += v[1] * y4.y * g;
-                            gx += v[2] * w4.z * g; gy += v[2] * y4.z * g;
-                            gx += v[3] * w4.w * g; gy += v[3] * y4.w * g;
-                            red[2 * k] = gx; red[2 * k + 1] = gy;
-                        }
-                    }
-                }
-                if (MODE == 1) {
-                    const float tot = gt_packed_reduce<8>(red, lane);        // lane l: value index l >> 2
-                    if ((lane & 3) == 0) acc[p4 * 8 + (lane >> 2)] += tot;
-                }
-            }
-            if (MODE == 0) {
-                __syncwarp();
-                gt_store_row(stage, dst, b, c0, nch, y, tx0, lane);
-                __syncwarp();
-            }
-        }
-    }
-    if (MODE == 0 || y >= oh) return;
-    __syncwarp();
-    const int x = tx0 + lane;
-    if (lane >= GT_TW || x >= ow) return;
-    float* o = dst.p + b * dst.sb + y * dst.sh + x * dst.sw;
-    o[0] = (float(img.w) / 2) * acc[lane * 2];
-    o[dst.sc] = (float(img.h) / 2) * acc[lane * 2 + 1];
-}
-
-template <int MODE>
-static int launch_grid_warp_tiled(const View<const float>& img, const View<const float>& flow,
-                                  const View<const float>& gout, const View<float>& dst, int n, int h, int w, cudaStream_t st) {
-    const size_t smem = sizeof(float) * (32 * GT_RPX + GT_NPX * GW_PW + GT_WARPS * GT_TW * 2 + (MODE == 0 ? GT_WARPS * 32 * GT_SPITCH : 32 * GT_GPITCH));
-    cudaError_t e = cudaFuncSetAttribute(grid_warp_tiled_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("grid_warp_tiled: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
-    dim3 grid(ceil_div(w, GT_TW), ceil_div(h, GT_TH), n);
-    grid_warp_tiled_kernel<MODE><<<grid, GT_THREADS, smem, st>>>(img, flow, gout, dst);
-    return FFWM_OK;
-}
-
 template <typename T, int SL>
 __global__ void __launch_bounds__(256)
 grid_warp_bwd_kernel(View<const T> img, View<const T> flow, View<const T> gout,
@@ -407,26 +272,9 @@ static int grid_warp_forward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, con
     }
     if ((int64_t)out.n * out.c * out.h * out.w == 0) return FFWM_OK;
     if (out.n > 65535) { set_error("grid_warp: batch %d > 65535", out.n); return FFWM_ERR_TOO_LARGE; }
-    if constexpr (sizeof(T) == 4) {
-        // rolling-strip gather (roll_gather.cuh) for maps of equal size sampled near the identity
-        // (measured at the cfg5 point: 0.59 ms against 0.37 ms for the direct kernel — with four taps the ring fill
-        // costs more than the gather saves — so it is opt-in: FFWM_FORCE_ROLL)
-        if (img.h == out.h && img.w == out.w && getenv("FFWM_FORCE_ROLL") &&
-            roll_applicable(out.n, out.c, out.h, out.w, img, ceil_div(out.c, 32))) {
-            const int rc2 = launch_grid_warp_roll<0>(img, flow, View<const float>{}, out, out.n, out.c, out.h, out.w, st);
-            if (rc2) return rc2;
-            return check_launch("grid_warp_forward(roll)");
-        }
-        // measured at the cfg5 point: direct 0.38 ms (43 % of HBM) vs tiled 0.68 ms — with only four
-        // taps the slab fill costs more than the gather saves, so the tiled forward is opt-in
-        if (getenv("FFWM_GRID_WARP_TILED_FWD") && img.h == out.h && img.w == out.w &&
-            (int64_t)(img.h - 1) * img.sh + (int64_t)(img.w - 1) * img.sw < (1 << 30) &&
-            gather_tiled_applicable(out.n, out.c, out.h, out.w, img)) {
-            const int rc2 = launch_grid_warp_tiled<0>(img, flow, View<const float>{}, out, out.n, out.h, out.w, st);
-            if (rc2) return rc2;
-            return check_launch("grid_warp_forward(tiled)");
-        }
-    }
+    // Measured alternatives at the cfg5 point (0.37 ms direct): channel-lane gathers from a shared-memory slab —
+    // tiled 0.68 ms, rolling strip 0.59 ms — and 128-bit corner-pair gathers 0.65 ms; with four taps the staging
+    // costs more than the gather saves, so the forward pass is the direct kernel.
     const int pix_blocks = ceil_div((int64_t)out.h * out.w, 256);
     int64_t want = (int64_t)8 * sm_count();
     int chunks = int((want + (int64_t)pix_blocks * out.n - 1) / ((int64_t)pix_blocks * out.n));
@@ -434,8 +282,6 @@ static int grid_warp_forward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, con
     const int c_per_block = ceil_div(out.c, chunks);
     chunks = ceil_div(out.c, c_per_block);
     dim3 grid(pix_blocks, chunks, out.n);
-    // (a variant gathering each corner pair with one aligned LDG.128 was measured slower for near-identity grids:
-    // 0.65 vs 0.38 ms at the cfg5 point — the kernel is bound by L1 sectors moved, not by instructions)
     grid_warp_fwd_kernel<T><<<grid, 256, 0, st>>>(img, flow, out, c_per_block);
     return check_launch("grid_warp_forward");
 }
@@ -480,20 +326,6 @@ static int grid_warp_backward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, co
             const int rc2 = launch_gather_quad(GwQuadPolicy{img, flow, gout, gf}, gout.n, gout.h, gout.w, st);
             if (rc2) return rc2;
             return check_launch("grid_warp_backward(quad flow gradient)");
-        }
-        if (!gi.p && gf.p && img.h == gout.h && img.w == gout.w && !getenv("FFWM_DISABLE_TILED_GFLOW") &&
-            (getenv("FFWM_FORCE_ROLL") || getenv("FFWM_ROLL_GFLOW")) &&     // 0.95 ms against 0.90 ms tiled: opt-in
-            roll_applicable(gout.n, gout.c, gout.h, gout.w, img, ceil_div(gout.h, roll_segment_rows(gout.n, gout.h, gout.w)))) {
-            const int rc2 = launch_grid_warp_roll<1>(img, flow, gout, gf, gout.n, gout.c, gout.h, gout.w, st);
-            if (rc2) return rc2;
-            return check_launch("grid_warp_backward(roll flow gradient)");
-        }
-        if (!gi.p && gf.p && img.h == gout.h && img.w == gout.w && !getenv("FFWM_DISABLE_TILED_GFLOW") &&
-            (int64_t)(img.h - 1) * img.sh + (int64_t)(img.w - 1) * img.sw < (1 << 30) &&
-            gather_tiled_applicable(gout.n, gout.c, gout.h, gout.w, img)) {
-            const int rc2 = launch_grid_warp_tiled<1>(img, flow, gout, gf, gout.n, gout.h, gout.w, st);
-            if (rc2) return rc2;
-            return check_launch("grid_warp_backward(tiled flow gradient)");
         }
     }
     const int c = gout.c;

@@ -1036,16 +1036,7 @@ static int resample2d_backward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, c
             if (rc2) return rc2;
             return check_launch("resample2d_backward(quad flow gradient)");
         }
-        // flow gradient through the rolling-strip gather, else the tiled gather
-        // (measured: 1.74 / 1.28 ms for kernel_size 4 / 2 against 1.70 / 1.08 ms for the tiled gather below, so the
-        // rolling flow gradient is opt-in: FFWM_FORCE_ROLL or FFWM_ROLL_GFLOW)
-        if (!g1.p && g2.p && (half == 1 || half == 2) && dil == 1 && !getenv("FFWM_DISABLE_TILED_GFLOW") &&
-            (getenv("FFWM_FORCE_ROLL") || getenv("FFWM_ROLL_GFLOW")) &&
-            roll_applicable(gout.n, gout.c, gout.h, gout.w, in1, ceil_div(gout.h, roll_segment_rows(gout.n, gout.h, gout.w)))) {
-            const int rc2 = half == 1 ? launch_gflow_roll<1>(in1, in2, gout, g2, st) : launch_gflow_roll<2>(in1, in2, gout, g2, st);
-            if (rc2) return rc2;
-            return check_launch("resample2d_backward(roll flow gradient)");
-        }
+        // dilation > 1: the tiled gather
         if (!g1.p && g2.p && (half == 1 || half == 2) && dil >= 1 && hmax >= 2 &&
             (int64_t)(in1.h - 1) * in1.sh + (int64_t)(in1.w - 1) * in1.sw < (1 << 30) &&
             gather_tiled_applicable(gout.n, gout.c, gout.h, gout.w, in1) && !getenv("FFWM_DISABLE_TILED_GFLOW")) {

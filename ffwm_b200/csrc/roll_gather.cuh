@@ -39,7 +39,6 @@ constexpr int RG_THREADS = 512, RG_WARPS = 16;
 constexpr int RG_PXW = 8;                         // pixels per warp and step
 constexpr int RG_BLK = 4;                         // steps per geometry block (RG_BLK * RG_PXW = 32 lanes)
 constexpr int RG_SPITCH = RG_PXW + 1;             // per-warp staging [32 channels][9]
-constexpr int RG_SEG = 128;                       // most rows per CTA segment in the flow-gradient kernels
 
 __device__ __forceinline__ unsigned rg_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void rg_cp_async4(unsigned dst, const float* src) {
@@ -87,38 +86,12 @@ __device__ __forceinline__ void rg_store_row(const float* stage, const View<floa
     }
 }
 
-// g[8] <- t[b, c0 + it*4 + lane/8, y, xw0 + lane%8] (zeros outside); the transposed view of rg_store_row
-__device__ __forceinline__ void rg_load_row(float (&g)[8], const View<const float>& t, int b, int c0, int nch,
-                                            int y, int xw0, int lane) {
-    const int px = lane & 7, csub = lane >> 3;
-    const bool ok = y < t.h && xw0 + px < t.w;
-    const float* gp = t.p + b * t.sb + (int64_t)c0 * t.sc + y * t.sh + (xw0 + px) * t.sw;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int c = it * 4 + csub;
-        g[it] = (ok && c < nch) ? ld_stream(gp + (int64_t)c * t.sc) : 0.f;
-    }
-}
-__device__ __forceinline__ void rg_stage_row(float* stage, const float (&g)[8], int lane) {
-    const int px = lane & 7, csub = lane >> 3;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) stage[(it * 4 + csub) * RG_SPITCH + px] = g[it];
-}
-
 // Applicability of the rolling kernels: fp32, non-negative strides, enough strips to fill the GPU.
-// Rows per segment for the flow-gradient kernels: the largest of 128/64/32 that still gives one CTA per SM.
-inline int roll_segment_rows(int n, int h, int w) {
-    const int64_t strips = (int64_t)ceil_div(w, RG_SW) * n;
-    int seg = RG_SEG;
-    while (seg > 32 && strips * ceil_div(h, seg) < sm_count()) seg >>= 1;
-    return seg;
-}
-
 inline bool roll_applicable(int n, int c, int h, int w, const View<const float>& src, int ctas_per_strip) {
     if (getenv("FFWM_DISABLE_ROLL") || getenv("FFWM_DISABLE_TILED")) return false;
     if (src.sh < 0 || src.sw < 0 || c < 16 || n > 65535 || h < 32) return false;
     if ((int64_t)(src.h - 1) * src.sh + (int64_t)(src.w - 1) * src.sw >= (1 << 30)) return false;
-    if (getenv("FFWM_FORCE_ROLL")) return true;           // tests: small shapes through the rolling kernels
+    if (getenv("FFWM_FORCE_ROLL") || getenv("FFWM_FORCE_TILED")) return true;   // tests: small shapes through the rolling kernels
     const int64_t ctas = (int64_t)ceil_div(w, RG_SW) * n * ctas_per_strip;
     return ctas >= sm_count() / 2;
 }

@@ -470,7 +470,7 @@ def test_block_extractor_tiled_paths_match_direct_and_oracle(ops, oracle_warp, k
     assert rel_err(gs_t.cpu(), ws) <= 1e-4 and rel_err(gf_t.cpu(), wf) <= 1e-4
 
 
-# --------------------------------- rolling-strip kernels (roll_gather.cuh) vs the direct kernels and the oracle
+# --------------------------------- tiled kernel generations on small ragged shapes (forced) vs direct kernels / oracle
 class _env:
     def __init__(self, **kv):
         self.kv = kv
@@ -494,11 +494,12 @@ class _env:
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(2, 48, 100, 90), (1, 32, 33, 16), (3, 17, 40, 21)])
 @pytest.mark.parametrize("ks,fscale", [(2, 2.0), (4, 2.0), (4, 12.0)])
-def test_resample2d_roll_matches_direct_and_oracle(ops, oracle_warp, ks, fscale, shape):
-    """FFWM_FORCE_ROLL sends small ragged shapes (partial strips, partial channel groups, heights that
-    are not a multiple of the 8-row step) through the rolling kernels; fscale=12 px pushes most windows
-    out of the ring (per-lane path) and against the border (edge replication = the reference's clamps).
-    expf instead of the double exp: 1e-6-level differences from the direct kernels."""
+def test_resample2d_forced_tiled_matches_direct_and_oracle(ops, oracle_warp, ks, fscale, shape):
+    """FFWM_FORCE_TILED sends small ragged shapes (partial strips / tiles, partial channel groups, heights that
+    are not a multiple of the 8-row step) through the rolling forward (roll_gather.cuh), the row-owner scatter
+    (scatter_rows.cuh) and the accumulate-then-weigh flow gradient (gather_quad.cuh); fscale=12 px pushes most
+    windows out of the staged region (far paths) and against the border (padding = the reference's clamps).
+    These kernels use expf instead of the double exp: 1e-6-level differences from the direct kernels."""
     g = torch.Generator().manual_seed(ks * 10 + int(fscale) + shape[1])
     b, c, h, w = shape
     in1 = torch.rand(b, c, h, w, generator=g) * 2 - 1
@@ -506,24 +507,32 @@ def test_resample2d_roll_matches_direct_and_oracle(ops, oracle_warp, ks, fscale,
     go = torch.randn(b, c, h, w, generator=g)
     d = [t.to(DEV) for t in (in1, in2, go)]
     out_r, out_d = torch.empty_like(d[0]), torch.empty_like(d[0])
+    g1_r, g1_d = torch.zeros_like(d[0]), torch.zeros_like(d[0])
     g2_r, g2_d = torch.empty_like(d[1]), torch.empty_like(d[1])
-    with _env(FFWM_FORCE_ROLL="1"):
+    with _env(FFWM_FORCE_TILED="1"):
         ops.resample2d_forward(d[0], d[1], out_r, ks, 1)
-        ops.resample2d_backward(d[0], d[1], d[2], None, g2_r, ks, 1)
+        ops.resample2d_backward(d[0], d[1], d[2], g1_r, g2_r, ks, 1)
     with _env(FFWM_DISABLE_TILED="1"):
         ops.resample2d_forward(d[0], d[1], out_d, ks, 1)
-        ops.resample2d_backward(d[0], d[1], d[2], None, g2_d, ks, 1)
+        ops.resample2d_backward(d[0], d[1], d[2], g1_d, g2_d, ks, 1)
     assert rel_err(out_r, out_d) <= 3e-6
+    assert rel_err(g1_r, g1_d) <= 2e-5
     assert rel_err(g2_r, g2_d) <= 5e-5
     assert rel_err(out_r.cpu(), oracle_warp.resample2d_forward(in1, in2, ks, 1)) <= 1e-5
-    _, w2 = oracle_warp.resample2d_backward(in1, in2, go, ks, 1)
+    w1, w2 = oracle_warp.resample2d_backward(in1, in2, go, ks, 1)
+    assert rel_err(g1_r.cpu(), w1) <= 1e-4
     assert rel_err(g2_r.cpu(), w2) <= 1e-4
+    # a strided (channels-last) grad_input1 takes the scalar flush of the scatter
+    g1_s = torch.zeros(b, h, w, c, device=DEV).permute(0, 3, 1, 2)
+    with _env(FFWM_FORCE_TILED="1"):
+        ops.resample2d_backward(d[0], d[1], d[2], g1_s, None, ks, 1)
+    assert rel_err(g1_s, g1_d) <= 2e-5
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [(2, 40, 96, 112), (1, 33, 37, 50)])
+@pytest.mark.parametrize("shape", [(2, 40, 96, 112), (1, 33, 37, 50), (2, 16, 20, 24)])
 @pytest.mark.parametrize("noise", [0.03, 0.6])
-def test_grid_warp_roll_matches_direct_and_torch(ops, noise, shape):
+def test_grid_warp_forced_tiled_matches_direct_and_torch(ops, noise, shape):
     g = torch.Generator().manual_seed(7 + shape[1])
     b, c, h, w = shape
     img = torch.rand(b, c, h, w, generator=g)
@@ -531,30 +540,25 @@ def test_grid_warp_roll_matches_direct_and_torch(ops, noise, shape):
     grid = torch.stack((xs, ys), 0).unsqueeze(0).repeat(b, 1, 1, 1) + noise * torch.randn(b, 2, h, w, generator=g)
     go = torch.randn(b, c, h, w, generator=g)
     d = [t.to(DEV) for t in (img, grid, go)]
-    out_r, out_d = torch.empty_like(d[0]), torch.empty_like(d[0])
+    gi_r, gi_d = torch.zeros_like(d[0]), torch.zeros_like(d[0])
     gf_r, gf_d = torch.empty_like(d[1]), torch.empty_like(d[1])
-    with _env(FFWM_FORCE_ROLL="1"):
-        ops.grid_warp_forward(d[0], d[1], out_r)
-        ops.grid_warp_backward(d[0], d[1], d[2], None, gf_r)
+    with _env(FFWM_FORCE_TILED="1"):
+        ops.grid_warp_backward(d[0], d[1], d[2], gi_r, gf_r)
     with _env(FFWM_DISABLE_TILED="1"):
-        ops.grid_warp_forward(d[0], d[1], out_d)
-        ops.grid_warp_backward(d[0], d[1], d[2], None, gf_d)
-    assert rel_err(out_r, out_d) <= 1e-6
+        ops.grid_warp_backward(d[0], d[1], d[2], gi_d, gf_d)
+    assert rel_err(gi_r, gi_d) <= 2e-5
     assert rel_err(gf_r, gf_d) <= 5e-5
     x = img.double().requires_grad_(True)
     gr = grid.double().requires_grad_(True)
-    want = torch.nn.functional.grid_sample(x, gr.permute(0, 2, 3, 1), align_corners=False)
-    want.backward(go.double())
-    # fp32 evaluation of ix = ((g+1)*W-1)/2 on a 112-wide map against float64: 1.03e-5 measured, identical
-    # (0.0 difference) to the direct kernel above, which is the one held to 1e-5 against the oracle
-    assert rel_err(out_r.cpu().double(), want.detach()) <= 2e-5
+    torch.nn.functional.grid_sample(x, gr.permute(0, 2, 3, 1), align_corners=False).backward(go.double())
+    assert rel_err(gi_r.cpu().double(), x.grad) <= 1e-5
     assert rel_err(gf_r.cpu().double(), gr.grad) <= 1e-4
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(2, 24, 40, 37), (1, 40, 33, 64)])
 @pytest.mark.parametrize("k,mode", [(3, "rand1.8"), (3, "randn2"), (3, "wild"), (2, "rand1.8"), (2, "wild")])
-def test_block_extractor_roll_forward_matches_oracle(ops, oracle_warp, k, mode, shape):
+def test_block_extractor_window_forward_matches_oracle(ops, oracle_warp, k, mode, shape):
     g = torch.Generator().manual_seed(31 + k + shape[1])
     b, c, h, w = shape
     src = torch.rand(b, c, h, w, generator=g)
@@ -563,19 +567,15 @@ def test_block_extractor_roll_forward_matches_oracle(ops, oracle_warp, k, mode, 
             "wild": lambda: torch.randn(b, 2, h, w, generator=g) * 9}[mode]()
     d = [t.to(DEV) for t in (src, flow)]
     out_r = torch.empty(b, c, k * h, k * w, device=DEV)
-    with _env(FFWM_FORCE_ROLL="1"):
-        ops.block_extractor_forward(d[0], d[1], out_r, k)
+    ops.block_extractor_forward(d[0], d[1], out_r, k)
     assert rel_err(out_r.cpu(), oracle_warp.block_extractor_forward(src, flow, k)) <= 1e-6
     # integer flow: bit-exact unfold (the live use in the reference)
     iflow = torch.full((b, 2, h, w), float(k // 2), device=DEV)
-    with _env(FFWM_FORCE_ROLL="1"):
-        ops.block_extractor_forward(d[0], iflow, out_r, k)
-    out_d = torch.empty_like(out_r)
-    with _env(FFWM_DISABLE_TILED="1"):
-        ops.block_extractor_forward(d[0], iflow, out_d, k)
-    assert torch.equal(out_r, out_d)
-    # a strided (channels-last) output takes the scalar store path
+    ops.block_extractor_forward(d[0], iflow, out_r, k)
+    want = F.unfold(F.pad(d[0], (0, k - 1, 0, k - 1), mode="replicate"), k).view(b, c, k, k, h, w)   # taps x+j clamp at the edge
+    want = want.permute(0, 1, 4, 2, 5, 3).reshape(b, c, k * h, k * w)
+    assert torch.equal(out_r, want)
+    # a strided (channels-last) output
     out_s = torch.empty(b, k * h, k * w, c, device=DEV).permute(0, 3, 1, 2)
-    with _env(FFWM_FORCE_ROLL="1"):
-        ops.block_extractor_forward(d[0], d[1], out_s, k)
+    ops.block_extractor_forward(d[0], d[1], out_s, k)
     assert rel_err(out_s.cpu(), oracle_warp.block_extractor_forward(src, flow, k)) <= 1e-6
