@@ -12,15 +12,15 @@ timeout 1200 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$T
 [[ $SKIP == *tf32* ]] || { FFWM_BENCH_TF32=1 timeout 600 python bench.py --no-cpu-baseline --no-warp > gpurun_out/bench_tf32_$TAG.json 2>> gpurun_out/bench_$TAG.err; echo "bench tf32 rc=$?"; cat gpurun_out/bench_tf32_$TAG.json; }
 [[ $SKIP == *warpbench* ]] || { timeout 600 python bench.py --workload warp > gpurun_out/bench_warp_$TAG.json 2>> gpurun_out/bench_$TAG.err; echo "bench warp rc=$?"; }
 [[ $SKIP == *sweep* ]] || { timeout 1200 python -m benchmarks.sweep --out gpurun_out/sweep_$TAG.json > gpurun_out/sweep_$TAG.txt 2>&1; echo "sweep rc=$?"; cat gpurun_out/sweep_$TAG.txt; }
-KR='regex:resample2d|block_extractor|lar_tiled|local_attn|grid_warp|scatter_tiled|scatter_rows'
+KR='regex:resample2d|block_extractor|lar_tiled|local_attn|grid_warp|scatter_tiled|scatter_rows|gather_quad'
 [[ $SKIP == *ncu* ]] || {
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_warp_$TAG.csv \
     python bench.py --workload warp --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launches_$TAG.log 2>&1; echo "ncu launches rc=$?"
-timeout 1500 ncu --set full --clock-control none --import-source on -k "$KR" -s 11 -c 11 -f -o gpurun_out/prof_$TAG \
+timeout 1500 ncu --set full --clock-control none --import-source on -k "$KR" -s 10 -c 10 -f -o gpurun_out/prof_$TAG \
     python bench.py --workload warp --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
 # reduce the report on the box (gpurun_out is capped at 64 MiB) and drop the .ncu-rep unless KEEP_REP=1
 python scripts/ncu_summary.py gpurun_out/prof_$TAG.ncu-rep $TAG gpurun_out > /dev/null 2>&1
-for k in resample2d_fwd_roll resample2d_gflow scatter_rows block_extractor_fwd block_extractor_bwd grid_warp_tiled; do python scripts/ncu_hot.py gpurun_out/prof_$TAG.ncu-rep $k 0x400 >> gpurun_out/${TAG}_ncu_hot.txt 2>/dev/null; done
+for k in resample2d_fwd_roll gather_quad scatter_rows block_extractor_fwd block_extractor_bwd; do python scripts/ncu_hot.py gpurun_out/prof_$TAG.ncu-rep $k 0x400 >> gpurun_out/${TAG}_ncu_hot.txt 2>/dev/null; done
 [[ -n "$KEEP_REP" ]] || rm -f gpurun_out/prof_$TAG.ncu-rep
 [[ $SKIP == *trainlaunch* ]] || FFWM_BENCH_GRAPH=0 FFWM_BENCH_NCU_RANGE=1 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 40000 --csv --log-file gpurun_out/launches_train_$TAG.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-warp > gpurun_out/ncu_launches_train_$TAG.log 2>&1; echo "ncu train launches rc=$?"

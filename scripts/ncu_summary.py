@@ -35,10 +35,10 @@ METRICS = [
 # scatter + flow gradient) gets the SUM of their DRAM bytes (one launch of each)
 KERNEL_OPS = [
     ("scatter_rows_kernel<Resample2dScatterGeo", "resample2d_bwd"), ("scatter_tiled_kernel<Resample2dScatterGeo", "resample2d_bwd"),
-    ("resample2d_gflow", "resample2d_bwd"), ("resample2d_bwd", "resample2d_bwd"),
+    ("gather_quad_kernel<RsQuadPolicy", "resample2d_bwd"), ("resample2d_gflow", "resample2d_bwd"), ("resample2d_bwd", "resample2d_bwd"),
     ("resample2d_fwd", "resample2d_fwd"),
     ("scatter_rows_kernel<GridWarpScatterGeo", "grid_warp_bwd"), ("scatter_tiled_kernel<GridWarpScatterGeo", "grid_warp_bwd"),
-    ("grid_warp_tiled_kernel<1>", "grid_warp_bwd"), ("grid_warp_roll_kernel<1>", "grid_warp_bwd"), ("grid_warp_bwd", "grid_warp_bwd"),
+    ("gather_quad_kernel<GwQuadPolicy", "grid_warp_bwd"), ("grid_warp_tiled_kernel<1>", "grid_warp_bwd"), ("grid_warp_roll_kernel<1>", "grid_warp_bwd"), ("grid_warp_bwd", "grid_warp_bwd"),
     ("grid_warp_fwd", "grid_warp_fwd"), ("grid_warp_tiled_kernel<0>", "grid_warp_fwd"), ("grid_warp_roll_kernel<0>", "grid_warp_fwd"),
     ("block_extractor_fwd", "block_extractor_fwd"), ("block_extractor_bwd", "block_extractor_bwd"),
     ("lar_tiled_kernel<float, 3, 1>", "local_attn_reshape_fwd"), ("lar_tiled_kernel<float, 3, 0>", "local_attn_reshape_bwd"),
