@@ -141,12 +141,34 @@ gather_quad_kernel(P pol, int vec) {
     }
     __syncthreads();
 
-    // lane -> (channel c8 of eight, pixel p4 of four); the warp's tile row holds pixels 4q + p4
+    // lane -> (channel c8 of eight, pixel slot p4 of four); the warp's tile row is processed as 4 quads of pixels.
+    // The 4 pixels of a quad hit the same bank when their window offsets agree mod 4 (the 8 channels sit 4 banks
+    // apart), so the row's 16 pixels are dealt into the quads by (rank inside their offset class, class): a quad
+    // then holds one pixel of each class as long as the classes last (smooth flows: consecutive pixels already do).
     const int c8 = lane & 7, p4 = lane >> 3;
     const int y = ty0 + warp;
-    int off[4];
+    int* perm = reinterpret_cast<int*>(slab + 32 * GQ_CHP + 32 * GQ_GP + GQ_NPX * GQ_REC) + warp * GQ_TW;   // [16 warps][16]
+    {
+        const int myoff = lane < GQ_TW ? reinterpret_cast<const int*>(recs + (warp * GQ_TW + lane) * GQ_REC)[0] : -2;
+        const int cls = (myoff >= 0 ? myoff : lane) & 3;
+        unsigned m[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) off[q] = reinterpret_cast<const int*>(recs + (warp * GQ_TW + 4 * q + p4) * GQ_REC)[0];
+        for (int k = 0; k < 4; ++k) m[k] = __ballot_sync(0xffffffffu, lane < GQ_TW && cls == k);
+        const unsigned below = (1u << lane) - 1u;
+        const unsigned mine = cls == 0 ? m[0] : cls == 1 ? m[1] : cls == 2 ? m[2] : m[3];
+        const int rank = __popc(mine & below);
+        int pos = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pos += min(__popc(m[k]), rank) + ((k < cls && __popc(m[k]) > rank) ? 1 : 0);
+        if (lane < GQ_TW) perm[pos] = lane;
+    }
+    __syncwarp();
+    int off[4], pix[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        pix[q] = perm[4 * q + p4];
+        off[q] = reinterpret_cast<const int*>(recs + (warp * GQ_TW + pix[q]) * GQ_REC)[0];
+    }
     float M[4][NT];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -177,11 +199,11 @@ gather_quad_kernel(P pol, int vec) {
         for (int s = 0; s < 2; ++s) {
             const int ch = s * 8 + c8;
             const float* sl = slab_h + ch * GQ_CHP;
-            const float* gl = G_h + ch * GQ_GP + warp * GQ_TW + p4;
+            const float* gl = G_h + ch * GQ_GP + warp * GQ_TW;
             if (all_near) {                                              // warp-uniform: no per-pixel branches
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float g = gl[4 * q];                           // zero for channels past nch
+                    const float g = gl[pix[q]];                          // zero for channels past nch
                     const float* w = sl + off[q];
 #pragma unroll
                     for (int i = 0; i < NW; ++i)
@@ -191,7 +213,7 @@ gather_quad_kernel(P pol, int vec) {
             } else {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float g = gl[4 * q];                           // zero for channels past nch / pixels outside
+                    const float g = gl[pix[q]];                          // zero for channels past nch / pixels outside
                     if (off[q] >= 0) {
                         const float* w = sl + off[q];
 #pragma unroll
@@ -199,7 +221,7 @@ gather_quad_kernel(P pol, int vec) {
 #pragma unroll
                             for (int j = 0; j < NW; ++j) M[q][i * NW + j] = fmaf(g, w[i * GQ_RW + j], M[q][i * NW + j]);
                     } else if (off[q] == -1) {
-                        const int* rec = reinterpret_cast<const int*>(recs + (warp * GQ_TW + 4 * q + p4) * GQ_REC);
+                        const int* rec = reinterpret_cast<const int*>(recs + (warp * GQ_TW + pix[q]) * GQ_REC);
                         const int ifx = rec[1], ify = rec[2];
                         const float* plane = src.p + b * src.sb + (int64_t)(c0 + min(ch, nch - 1)) * src.sc;
 #pragma unroll
@@ -233,7 +255,7 @@ gather_quad_kernel(P pol, int vec) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int t = 0; t < NT; ++t) tot[(4 * q + p4) * (NT + 1) + t] = M[q][t];
+            for (int t = 0; t < NT; ++t) tot[pix[q] * (NT + 1) + t] = M[q][t];
     }
     __syncwarp();
     if (lane < GQ_TW && y < gout.h && tx0 + lane < gout.w) {
@@ -246,7 +268,7 @@ gather_quad_kernel(P pol, int vec) {
 
 template <class P>
 static int launch_gather_quad(const P& pol, int n, int h, int w, cudaStream_t st) {
-    const size_t smem = sizeof(float) * (32 * GQ_CHP + 32 * GQ_GP + GQ_NPX * GQ_REC);
+    const size_t smem = sizeof(float) * (32 * GQ_CHP + 32 * GQ_GP + GQ_NPX * GQ_REC + GQ_WARPS * GQ_TW);
     cudaError_t e = cudaFuncSetAttribute(gather_quad_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("gather_quad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
     const View<const float>& src = pol.src();
