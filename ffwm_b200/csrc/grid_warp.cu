@@ -11,11 +11,11 @@
 //
 // Execution plan: the flow is read straight from the network's (B,2,H,W)
 // layout (no permuted copy).
-//   Large fp32 maps of equal input/output size — TILED backward: grid_warp_tiled_kernel<1> (flow
-//   gradient) is a channel-lane gather (gather_tiled.cuh); grad_images is the destination-sorted
-//   scatter (scatter_tiled.cuh).  The tiled forward (<0>) exists but loses to the direct kernel
-//   for four taps and is opt-in (FFWM_GRID_WARP_TILED_FWD).  The model's own maps
-//   ((8,64,128,128), (8,64,64,64)) take this path, the 32x32 crops do not.
+//   Large fp32 maps of equal input/output size — TILED backward: grad_images is the row-owner
+//   scatter (scatter_rows.cuh), the flow gradient the accumulate-then-weigh gather
+//   (gather_quad.cuh).  The model's own maps ((8,64,128,128), (8,64,64,64)) take this path, the
+//   32x32 crops do not.  The forward pass is always the direct kernel (nothing measured beats it
+//   for four taps, see grid_warp_forward_t).
 //   Otherwise — DIRECT kernels: one thread owns one output pixel and walks a
 //   slice of channels with the four weights/offsets/validity bits in registers.
 //   Backward is one fused pass: grad_images is a scatter (RED.ADD), grad_flow

@@ -4,13 +4,17 @@
 // reference (K1 :20-95, K2 :98-202, K3 :204-330) including its numerics
 // quirks.  The execution plans are different.
 //
-// Large fp32 maps (>= ~74 tiles of 16x16, >= 16 channels, kernel_size 2 or 4) — TILED kernels:
-//   forward        resample2d_fwd_tiled_kernel     channel-lane gather (gather_tiled.cuh); kernel_size 4
-//                  only — with 4 taps the direct kernel is faster (measured, profiles/README.md)
-//   grad_input1    scatter_tiled_kernel<Resample2dScatterGeo>  destination-sorted scatter, no
-//                  scattered REDs (scatter_tiled.cuh)
-//   grad_input2    resample2d_gflow_tiled_kernel   channel-lane gather of input1 + a packed warp
-//                  reduction over channels; deterministic, one store per pixel
+// Large fp32 maps (>= ~74 tiles of 16x16, >= 16 channels, kernel_size 2 or 4, dilation 1) — TILED kernels:
+//   forward        resample2d_fwd_roll_kernel      rolling-strip channel-lane gather (roll_gather.cuh,
+//                  resample2d_roll.cuh); kernel_size 4 only — with 4 taps the direct kernel is faster
+//                  (measured, profiles/README.md)
+//   grad_input1    scatter_rows_kernel<Resample2dScatterGeo>   row-owner scatter: window rows bucketed by
+//                  destination row, sliding register window, vector REDs (scatter_rows.cuh)
+//   grad_input2    gather_quad_kernel<RsQuadPolicy>            accumulate-then-weigh: one FFMA per tap and
+//                  channel into per-pixel window accumulators, weights once per pixel (gather_quad.cuh);
+//                  deterministic, one store per output element
+//   dilation > 1 keeps the previous generation (gather_tiled.cuh, scatter_tiled.cuh), also reachable with
+//   FFWM_DISABLE_ROLL / FFWM_SCATTER_TILED / FFWM_DISABLE_QUAD for A/B runs (scripts/roll_ab.py).
 // Everything else (small maps, fp64, other kernel sizes, FFWM_DISABLE_TILED=1) — DIRECT kernels:
 //   * one thread owns one output PIXEL and walks a slice of the channels, so
 //     (dx,dy,sigma), the 4*(ks/2) double-precision exps, the tap offsets and
