@@ -279,6 +279,12 @@ static int launch_gather_quad(const P& pol, int n, int h, int w, cudaStream_t st
     return FFWM_OK;
 }
 
+// (A FORWARD kernel on the same staging — the NW*NW tap weights of a lane's four pixels in registers, one shared
+// load + one FFMA per tap, outputs stored straight from the (8 channels x 4 pixels) lanes — was parity-green but
+// slower than the rolling forward at the cfg5 point: 1.00 vs 0.89 ms for 16 taps, 0.62 vs 0.52 ms (direct) for 4;
+// its 4-byte stores scatter over 8 channel planes.  Removed; a version that transposes the outputs through shared
+// memory is round-2 work.)
+
 inline bool gather_quad_applicable(int n, int c, int h, int w, const View<const float>& src) {
     if (getenv("FFWM_DISABLE_TILED") || getenv("FFWM_DISABLE_QUAD")) return false;
     if (src.sh < 0 || src.sw < 0 || c < 16 || n > 65535) return false;
