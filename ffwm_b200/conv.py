@@ -9,11 +9,16 @@ maps of 16x16 and below) stays on cuDNN (library).
 
     forward        conv3x3_tc (implicit GEMM, 3xTF32 split: fp32-level accuracy)
     grad input     the same kernel with the weights packed transposed + flipped
-    grad weight    cuDNN (`aten.convolution_backward`, weight/bias outputs only) — not hand-written yet
+    grad weight    cuDNN (`aten.convolution_backward`, weight/bias outputs only) by default;
+                   FFWM_WGRAD_TC=1 opts in to the tcgen05 weight-gradient kernel (csrc/conv3x3_wgrad_tc.cu),
+                   which is EXPERIMENTAL: written after the round-1 GPU budget was spent, checked by a CPU
+                   emulation of its indexing only, not yet run or measured on a B200
 
 The module is a drop-in `nn.Conv2d`: same parameters, same state_dict keys, spectral norm hooks work
 unchanged (the weight is re-packed on every call: 0.02 ms).
 """
+import os
+
 import torch
 import torch.nn as nn
 from torch.autograd import Function
@@ -24,6 +29,7 @@ ENABLED = True          # set False to force cuDNN everywhere (A/B measurements)
 # The kernel also handles width 16, but there a map is one or two CTAs per (image, channel tile) with a
 # long serial K loop: measured slower than cuDNN inside the train step (98.4 -> 101.8 ms), so it is off.
 WIDTHS = (128, 64, 32)
+WGRAD_TC = os.environ.get("FFWM_WGRAD_TC", "0") == "1"     # experimental, unmeasured: off unless asked for
 
 
 def eligible(x, weight, stride, padding, dilation, groups, padding_mode="zeros"):
@@ -50,7 +56,13 @@ class Conv3x3TCFunction(Function):
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
             ops.conv3x3_forward(grad_out, ops.conv3x3_pack_weights(weight, dgrad=True), None, gx)
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+        if WGRAD_TC:
+            if ctx.needs_input_grad[1]:
+                gw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
+                ops.conv3x3_wgrad(x, grad_out, gw)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                gb = grad_out.sum((0, 2, 3))
+        elif ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             _, gw, gb = torch.ops.aten.convolution_backward(
                 grad_out, x, weight, [weight.size(0)] if ctx.has_bias else None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
                 [False, bool(ctx.needs_input_grad[1]), bool(ctx.has_bias and ctx.needs_input_grad[2])])

@@ -34,6 +34,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace ffwm {
 
@@ -67,48 +68,6 @@ struct CvGeo {
 constexpr int CV_B_CHUNK = CV_NT * 16;                    // one k-chunk of one tap: 64 co x 4 ci
 constexpr int CV_B_TAP = 2 * CV_B_CHUNK;                  // both k-chunks
 constexpr int CV_B_STAGE = 2 * 9 * CV_B_TAP;              // layout: [tap][hl][kchunk][co][4]
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address,
-// leading byte offset (between the two 16-byte k-chunks), stride byte offset (between 8-row
-// groups), all in 16-byte units; version 1 (Blackwell); layout type 0 (SWIZZLE_NONE).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46);
-}
-
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major.
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
-        : "memory");
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-
-// Bounded wait: a protocol error traps instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t a = smem_u32(bar);
-    for (uint32_t spin = 0;; ++spin) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(done)
-            : "r"(a), "r"(parity)
-            : "memory");
-        if (done) return;
-        if (spin > (1u << 26)) __trap();
-    }
-}
 
 // ---------------------------------------------------------------- weight packing
 // w (Cout, Cin, 3, 3) -> packed[cob][kb][tap][hl][kchunk][co_local 64][4 ci]  (hl: 0 = hi, 1 = lo)
@@ -148,23 +107,6 @@ __global__ void conv3x3_pack_kernel(const float* __restrict__ w, float* __restri
 // lane 0 copies the packed weights with one bulk async copy per K block and issues the MMAs.
 // Pipeline state lives in mbarriers: fullA[2] (256 producer arrivals), fullB[2] (bulk-copy
 // transaction bytes), empty[2] (tcgen05.commit of the MMAs that read the buffer).
-__device__ __forceinline__ void umma_tf32_acc(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc)
-        : "memory");
-}
-
-__device__ __forceinline__ void split_store(unsigned char* d, int part_bytes, const float* v) {
-    float4 hi, lo;
-    hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u); lo.x = v[0] - hi.x;
-    hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u); lo.y = v[1] - hi.y;
-    hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u); lo.z = v[2] - hi.z;
-    hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u); lo.w = v[3] - hi.w;
-    *reinterpret_cast<float4*>(d) = hi;
-    *reinterpret_cast<float4*>(d + part_bytes) = lo;
-}
-
 template <int WI>
 __global__ void __launch_bounds__(CV_PRODUCERS + 32, 1)
 conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const float* __restrict__ bias,

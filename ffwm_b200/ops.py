@@ -70,3 +70,10 @@ def conv3x3_forward(x, packed, bias, out):
     dev = L.require_cuda(x, packed, out)
     L.call("ffwm_conv3x3_forward", dev, L.t4(x), ctypes.c_void_p(packed.data_ptr()),
            ctypes.c_void_p(bias.data_ptr() if bias is not None else None), L.t4(out))
+
+
+def conv3x3_wgrad(x, grad_out, grad_weight):
+    """grad_weight (Cout,Cin,3,3, zero-filled by the caller) += weight gradient of the 3x3/s1/p1 convolution.
+    EXPERIMENTAL (not yet run on a B200): see csrc/conv3x3_wgrad_tc.cu."""
+    dev = L.require_cuda(x, grad_out, grad_weight)
+    L.call("ffwm_conv3x3_wgrad", dev, L.t4(x), L.t4(grad_out), L.t4(grad_weight))

@@ -136,6 +136,14 @@ int ffwm_conv3x3_pack_weights(const ffwm_tensor4* weight, int dgrad, float* pack
 /* out (B,Cout,H,W) = conv2d(x (B,Cin,H,W), weight, bias, stride 1, padding 1), W in {128,64,32,16}; bias may be NULL. */
 int ffwm_conv3x3_forward(const ffwm_tensor4* x, const float* packed, const float* bias, const ffwm_tensor4* out, void* stream);
 
+/* Weight gradient of the same convolution (the grad_weight output of aten::convolution_backward behind
+ * nn.Conv2d(Cin, Cout, 3, 1, 1), models/base_networks.py:218-222,235-246), tcgen05, 3xTF32:
+ *   grad_weight (Cout,Cin,3,3) += sum_{b,y,x} grad_out[b,co,y,x] * x[b,ci,y+ky-1,x+kx-1]   (zero padding)
+ * grad_weight accumulates (zero-fill it: the K splits arrive as fp32 REDs); x (B,Cin,H,W), grad_out (B,Cout,H,W),
+ * W % 32 == 0, any strides.  EXPERIMENTAL: compiled and checked by a CPU emulation of its indexing, not yet run on
+ * a B200 (written after the round-1 GPU budget was spent) — callers opt in with FFWM_WGRAD_TC=1. */
+int ffwm_conv3x3_wgrad(const ffwm_tensor4* x, const ffwm_tensor4* grad_out, const ffwm_tensor4* grad_weight, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

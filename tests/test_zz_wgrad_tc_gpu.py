@@ -1,0 +1,68 @@
+"""tcgen05 weight gradient (ffwm_b200/csrc/conv3x3_wgrad_tc.cu) against PyTorch float64.
+
+OPT-IN: the kernel was written after the round-1 GPU budget was spent and has not run on a B200 yet, so
+these tests only run with FFWM_EXPERIMENTAL=1 (the file sorts last so that a trap in an unproven kernel
+cannot poison the CUDA context of the established suite).  The first gpurun call of round 2 is
+`FFWM_EXPERIMENTAL=1 python -m pytest tests/test_zz_wgrad_tc_gpu.py -x -q`.
+Tolerance: 2e-5 of max|ref| (5e-5 when more than 2^17 pixels are summed), the forward kernel's contract."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("FFWM_EXPERIMENTAL", "0") != "1",
+                                 reason="experimental kernel, not yet validated on a B200: set FFWM_EXPERIMENTAL=1")]
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("b,cin,cout,h,w", [(1, 8, 16, 1, 32), (2, 5, 3, 3, 32), (1, 50, 130, 2, 64), (2, 48, 128, 8, 128),
+                                            (1, 3, 64, 128, 128), (2, 195, 195, 16, 128), (8, 128, 128, 128, 128),
+                                            (2, 195, 256, 64, 64), (2, 384, 384, 32, 32), (1, 64, 3, 7, 128), (1, 20, 66, 11, 96)])
+def test_conv3x3_wgrad_matches_fp64(b, cin, cout, h, w):
+    from ffwm_b200 import ops
+    g = torch.Generator().manual_seed(cin * 1000 + cout + w)
+    x = torch.randn(b, cin, h, w, generator=g)
+    go = torch.randn(b, cout, h, w, generator=g)
+    xd, gd = x.to(DEV), go.to(DEV)
+    wt = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, device=DEV, requires_grad=True)
+    F.conv2d(xd.double(), wt, None, padding=1).backward(gd.double())
+    gw = torch.zeros(cout, cin, 3, 3, device=DEV)
+    ops.conv3x3_wgrad(xd, gd, gw)
+    torch.cuda.synchronize()
+    assert rel(gw, wt.grad) <= (2e-5 if b * h * w <= (1 << 17) else 5e-5)
+    # accumulates into the caller's buffer
+    ops.conv3x3_wgrad(xd, gd, gw)
+    assert rel(gw, 2 * wt.grad) <= 5e-5
+
+
+def test_conv3x3_wgrad_strided_views():
+    from ffwm_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    xb = torch.randn(2, 40, 6, 64, generator=g).to(DEV)
+    gb = torch.randn(2, 70, 6, 64, generator=g).to(DEV)
+    x, go = xb[:, 4:28], gb[:, ::2]                                  # channel-offset / channel-strided views
+    wt = torch.zeros(35, 24, 3, 3, dtype=torch.float64, device=DEV, requires_grad=True)
+    F.conv2d(x.double(), wt, None, padding=1).backward(go.double())
+    gw = torch.zeros(35, 24, 3, 3, device=DEV)
+    ops.conv3x3_wgrad(x, go, gw)
+    assert rel(gw, wt.grad) <= 2e-5
+
+
+def test_conv_module_with_tc_wgrad(monkeypatch):
+    from ffwm_b200 import conv
+    monkeypatch.setattr(conv, "WGRAD_TC", True)
+    g = torch.Generator().manual_seed(9)
+    m = conv.Conv2d(24, 70, 3, 1, 1).to(DEV)
+    x = torch.randn(2, 24, 9, 64, generator=g).to(DEV).requires_grad_()
+    go = torch.randn(2, 70, 9, 64, generator=g).to(DEV)
+    m(x).backward(go)
+    x64 = x.detach().double().requires_grad_()
+    w64, b64 = m.weight.detach().double().requires_grad_(), m.bias.detach().double().requires_grad_()
+    F.conv2d(x64, w64, b64, padding=1).backward(go.double())
+    assert rel(m.weight.grad, w64.grad) <= 2e-5 and rel(m.bias.grad, b64.grad) <= 1e-5 and rel(x.grad, x64.grad) <= 2e-5
