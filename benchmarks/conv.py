@@ -2,6 +2,7 @@
 in strict fp32 and in TF32, on the generator's dominant shapes, B = 8, 128x128.
 
     python -m benchmarks.conv [--out gpurun_out/conv.json]
+    python -m benchmarks.conv --wgrad [--out gpurun_out/conv_wgrad.json]     (experimental weight-gradient kernel)
 """
 import argparse
 import json
@@ -28,18 +29,72 @@ def timeit(fn, iters=20):
     return e0.elapsed_time(e1) / iters
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "conv.json"))
-    args = ap.parse_args()
+SHAPES = (("dres2 195->195 @128", 195, 195, 128), ("att2 128->128 @128", 128, 128, 128),
+          ("e0 res 64->64 @128", 64, 64, 128), ("dres1 195->195 @64", 195, 195, 64),
+          ("d2 195->256 @64", 195, 256, 64), ("vgg 128->128 @64", 128, 128, 64),
+          ("dres0 384->384 @32", 384, 384, 32), ("vgg 256->256 @32", 256, 256, 32))
+
+
+def wgrad_bench(out_path):
+    """tcgen05 weight gradient (csrc/conv3x3_wgrad_tc.cu, incl. the zero fill of its target) vs cuDNN's strict-fp32
+    and TF32 weight gradients on the same shapes; errors against float64."""
     from ffwm_b200 import ops
     dev = torch.device("cuda", 0)
     torch.backends.cudnn.benchmark = True
     rows = []
-    for name, cin, cout, r in (("dres2 195->195 @128", 195, 195, 128), ("att2 128->128 @128", 128, 128, 128),
-                               ("e0 res 64->64 @128", 64, 64, 128), ("dres1 195->195 @64", 195, 195, 64),
-                               ("d2 195->256 @64", 195, 256, 64), ("vgg 128->128 @64", 128, 128, 64),
-                               ("dres0 384->384 @32", 384, 384, 32), ("vgg 256->256 @32", 256, 256, 32)):
+
+    def cudnn_wgrad(go, x, w):
+        return torch.ops.aten.convolution_backward(go, x, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
+                                                   [False, True, False])[1]
+
+    for name, cin, cout, r in SHAPES:
+        x = torch.randn(8, cin, r, r, device=dev)
+        go = torch.randn(8, cout, r, r, device=dev)
+        w = torch.zeros(cout, cin, 3, 3, device=dev)
+        gw = torch.zeros_like(w)
+        flop = 2.0 * 8 * r * r * cin * cout * 9
+
+        def mine():
+            gw.zero_()
+            ops.conv3x3_wgrad(x, go, gw)
+
+        t_mine = timeit(mine)
+        w64 = w.double().requires_grad_()
+        F.conv2d(x.double(), w64, None, padding=1).backward(go.double())
+        ref = w64.grad
+        err_mine = float((gw.double() - ref).abs().max() / ref.abs().max())
+        torch.backends.cudnn.allow_tf32 = False
+        t_fp32 = timeit(lambda: cudnn_wgrad(go, x, w))
+        err_fp32 = float((cudnn_wgrad(go, x, w).double() - ref).abs().max() / ref.abs().max())
+        torch.backends.cudnn.allow_tf32 = True
+        t_tf32 = timeit(lambda: cudnn_wgrad(go, x, w))
+        err_tf32 = float((cudnn_wgrad(go, x, w).double() - ref).abs().max() / ref.abs().max())
+        rows.append(dict(shape=name, cin=cin, cout=cout, gflop=flop / 1e9, ms_tcgen05=t_mine, ms_cudnn_fp32=t_fp32,
+                         ms_cudnn_tf32=t_tf32, tflops_tcgen05=flop / t_mine / 1e9, err_tcgen05=err_mine,
+                         err_cudnn_fp32=err_fp32, err_cudnn_tf32=err_tf32))
+        del ref, w64
+    os.makedirs(os.path.dirname(out_path), exist_ok=True)
+    json.dump(rows, open(out_path, "w"), indent=1)
+    print("%-22s %8s %8s %8s %8s %9s %9s %9s" % ("wgrad shape", "tc ms", "fp32 ms", "tf32 ms", "TF/s", "err tc", "err fp32", "err tf32"))
+    for r in rows:
+        print("%-22s %8.3f %8.3f %8.3f %8.1f %9.1e %9.1e %9.1e" % (
+            r["shape"], r["ms_tcgen05"], r["ms_cudnn_fp32"], r["ms_cudnn_tf32"], r["tflops_tcgen05"],
+            r["err_tcgen05"], r["err_cudnn_fp32"], r["err_cudnn_tf32"]))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--wgrad", action="store_true", help="measure the experimental tcgen05 weight gradient instead")
+    args = ap.parse_args()
+    if args.wgrad:
+        return wgrad_bench(args.out or os.path.join(ROOT, "gpurun_out", "conv_wgrad.json"))
+    args.out = args.out or os.path.join(ROOT, "gpurun_out", "conv.json")
+    from ffwm_b200 import ops
+    dev = torch.device("cuda", 0)
+    torch.backends.cudnn.benchmark = True
+    rows = []
+    for name, cin, cout, r in SHAPES:
         x = torch.randn(8, cin, r, r, device=dev)
         w = torch.randn(cout, cin, 3, 3, device=dev) / (cin * 9) ** 0.5
         b = torch.randn(cout, device=dev)

@@ -30,6 +30,9 @@ ENABLED = True          # set False to force cuDNN everywhere (A/B measurements)
 # long serial K loop: measured slower than cuDNN inside the train step (98.4 -> 101.8 ms), so it is off.
 WIDTHS = (128, 64, 32)
 WGRAD_TC = os.environ.get("FFWM_WGRAD_TC", "0") == "1"     # experimental, unmeasured: off unless asked for
+# its CTA tile is 128 output x 48 input channels: layers far below that (flow heads, RGB reconstructions,
+# the first convolutions on 3 channels: 0.7 % of the weight-gradient FLOPs of the step) stay on cuDNN
+WGRAD_MIN_COUT, WGRAD_MIN_CIN = 32, 16
 
 
 def eligible(x, weight, stride, padding, dilation, groups, padding_mode="zeros"):
@@ -56,7 +59,7 @@ class Conv3x3TCFunction(Function):
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
             ops.conv3x3_forward(grad_out, ops.conv3x3_pack_weights(weight, dgrad=True), None, gx)
-        if WGRAD_TC:
+        if WGRAD_TC and weight.size(0) >= WGRAD_MIN_COUT and weight.size(1) >= WGRAD_MIN_CIN:
             if ctx.needs_input_grad[1]:
                 gw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
                 ops.conv3x3_wgrad(x, grad_out, gw)

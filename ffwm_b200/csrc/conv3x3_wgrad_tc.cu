@@ -24,8 +24,9 @@
 //   * per MMA the tensor core reads A (128 rows x 32 B = 4 KB) and B (144 x 32 B = 4.5 KB) from shared
 //     memory: ~67 clk at 128 B/clk against ~74 clk of tf32 math, which is why N packs the vertical taps —
 //     nine separate N = 48 MMAs per K step would re-read A nine times and be shared-memory bound.
-//   * split-K over (image, row, 32-pixel block) stages, one CTA per SM; partial sums are reduced with
-//     fp32 REDs into the caller's zero-filled dW (once per CTA, 128 x 432 values).
+//   * split-K over (image, row, 32-pixel block) stages, one CTA per SM, at most WG_MAX_STAGES stages per CTA
+//     (bounds the truncating fp32 accumulation chain); partial sums are reduced with fp32 REDs into the
+//     caller's zero-filled dW (once per CTA, 128 x 432 values).
 //   * warp-specialised 2-stage mbarrier pipeline as in conv3x3_tc.cu: 8 producer warps stage (split
 //     hi/lo, 16-byte conflict-free stores), lane 0 of warp 8 issues 36 MMAs per stage and commits.
 #include <stdint.h>
@@ -51,6 +52,11 @@ constexpr int WG_SMEM = 2 * WG_STAGE + 64;              // + 4 mbarriers + tmem 
 constexpr int WG_TMEM_COLS = 512;
 constexpr int WG_A_ITEMS = WG_MT / 8;                   // producer work items: 8 rows x all chunks of a stage
 constexpr int WG_ITEMS = WG_A_ITEMS + WG_N / 8;
+// Longest accumulation chain of one CTA, in stages (12 accumulator updates each).  The tensor core adds into its
+// fp32 accumulators with truncation, so the error grows linearly with the number of updates: ~2e-5 of max|dW|
+// after 768 updates (the forward kernel's measured 1-2e-5 at 675 updates; simulated: 1e-4 at 4096, 1.4e-3 at the
+// 49152 a whole 8x128x128 batch would need).  Partial sums of the splits meet in fp32 REDs (round to nearest).
+constexpr int WG_MAX_STAGES = 64;
 constexpr int WG_ITEMS_PER_WARP = (WG_ITEMS + WG_PRODUCERS / 32 - 1) / (WG_PRODUCERS / 32);
 static_assert(WG_A_LBO % 128 == 0 && WG_B_LBO % 128 == 0 && WG_STAGE % 128 == 0, "operand tiles stay 128-byte aligned");
 static_assert(3 * WG_N <= WG_TMEM_COLS && WG_N % 16 == 0 && WG_N <= 256, "three accumulators of N columns");
@@ -238,9 +244,10 @@ extern "C" int ffwm_conv3x3_wgrad(const ffwm_tensor4* x, const ffwm_tensor4* gra
     const int64_t stages = (int64_t)xv.n * xv.h * g.ncb;
     if (stages > 0x7fffffffLL || tiles > 0x7fffffffLL) { set_error("conv3x3_wgrad: problem too large"); return FFWM_ERR_TOO_LARGE; }
     g.stages_total = (int)stages;
-    // one wave of CTAs: split the pixel range until tiles x splits fills the SMs
+    // split the pixel range until tiles x splits fills the SMs, and further until no CTA accumulates more than
+    // WG_MAX_STAGES stages (accuracy, see above; the extra CTAs run as further waves)
     int64_t splits = std::max<int64_t>(1, std::min<int64_t>(stages, sm_count() / tiles));
-    g.stages_per_split = ceil_div(stages, splits);
+    g.stages_per_split = std::min(ceil_div(stages, splits), WG_MAX_STAGES);
     splits = ceil_div(stages, g.stages_per_split);                            // every split owns >= 1 stage
     if (splits > 65535) { set_error("conv3x3_wgrad: grid too large"); return FFWM_ERR_TOO_LARGE; }
     cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);

@@ -1,0 +1,28 @@
+#!/bin/bash
+# First GPU call of round 2: validate and measure what was written blind at the end of round 1
+# (the tcgen05 weight-gradient kernel), without touching the established suite's context.
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash scripts/r02_first_call.sh'
+# Each step runs in its own process under its own timeout: a trap in the unproven kernel ends that step only.
+mkdir -p gpurun_out
+FFWM_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_zz_wgrad_tc_gpu.py -x -q > gpurun_out/r02_wgrad_pytest.log 2>&1; echo "wgrad pytest rc=$?"
+tail -25 gpurun_out/r02_wgrad_pytest.log
+timeout 300 python -m benchmarks.conv --wgrad --out gpurun_out/r02_conv_wgrad.json > gpurun_out/r02_conv_wgrad.txt 2>&1; echo "wgrad bench rc=$?"
+cat gpurun_out/r02_conv_wgrad.txt | tail -12
+# A/B on the headline: the train step with cuDNN weight gradients (default) and with the tcgen05 ones
+timeout 600 python bench.py --no-cpu-baseline --no-warp > gpurun_out/r02_bench_cudnn_wgrad.json 2> gpurun_out/r02_bench_a.err; echo "bench (cuDNN wgrad) rc=$?"
+FFWM_WGRAD_TC=1 timeout 600 python bench.py --no-cpu-baseline --no-warp > gpurun_out/r02_bench_tc_wgrad.json 2> gpurun_out/r02_bench_b.err; echo "bench (tcgen05 wgrad) rc=$?"
+python - <<'PY'
+import json
+for f in ("r02_bench_cudnn_wgrad", "r02_bench_tc_wgrad"):
+    try:
+        d = json.loads(open("gpurun_out/%s.json" % f).read().strip().splitlines()[-1])
+        print(f, d["value"], d["unit"], d["ms_per_step"], "ms/step")
+    except Exception as e:
+        print(f, "unreadable:", e)
+PY
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv3x3_wgrad -s 2 -c 3 -f -o gpurun_out/prof_r02_wgrad \
+    python -m benchmarks.conv --wgrad --out gpurun_out/conv_ncu_tmp.json > gpurun_out/r02_ncu_wgrad.log 2>&1; echo "ncu wgrad rc=$?"
+python scripts/ncu_summary.py gpurun_out/prof_r02_wgrad.ncu-rep r02_wgrad gpurun_out > /dev/null 2>&1
+python scripts/ncu_hot.py gpurun_out/prof_r02_wgrad.ncu-rep conv3x3_wgrad 0x400 > gpurun_out/r02_wgrad_ncu_hot.txt 2>/dev/null
+[[ -n "$KEEP_REP" ]] || rm -f gpurun_out/prof_r02_wgrad.ncu-rep; rm -f gpurun_out/conv_ncu_tmp.json
+ls -la gpurun_out | tail -12

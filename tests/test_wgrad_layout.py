@@ -21,7 +21,7 @@ CU = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "
 def constants():
     src = open(CU).read()
     c = {}
-    for name in ("WG_MT", "WG_NCI", "WG_CH", "WG_PRODUCERS"):
+    for name in ("WG_MT", "WG_NCI", "WG_CH", "WG_PRODUCERS", "WG_MAX_STAGES"):
         c[name] = int(re.search(r"constexpr int %s = (\d+);" % name, src).group(1))
     c["WG_N"] = 3 * c["WG_NCI"]
     c["A_LBO"] = c["WG_MT"] * 16
@@ -60,7 +60,7 @@ def emulate(x, go, splits_hint):
     tiles = -(-cout // MT) * n_ci_tiles
     stages_total = B * H * ncb
     splits = max(1, min(stages_total, splits_hint // tiles))
-    per = -(-stages_total // splits)
+    per = min(-(-stages_total // splits), c["WG_MAX_STAGES"])
     splits = -(-stages_total // per)
     dw = np.zeros((cout, cin, 3, 3), np.float64)
     for tile in range(tiles):
@@ -131,7 +131,8 @@ def emulate(x, go, splits_hint):
     return dw
 
 
-@pytest.mark.parametrize("b,cin,cout,h,w,splits_hint", [(2, 5, 3, 3, 32, 148), (1, 50, 130, 2, 64, 7), (1, 3, 8, 1, 32, 1)])
+@pytest.mark.parametrize("b,cin,cout,h,w,splits_hint", [(2, 5, 3, 3, 32, 148), (1, 50, 130, 2, 64, 7), (1, 3, 8, 1, 32, 1),
+                                                        (1, 2, 2, 70, 32, 1)])
 def test_wgrad_plan_matches_torch(b, cin, cout, h, w, splits_hint):
     g = torch.Generator().manual_seed(cin * 100 + cout)
     x = torch.randn(b, cin, h, w, generator=g)

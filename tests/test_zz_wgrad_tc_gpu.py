@@ -4,7 +4,8 @@ OPT-IN: the kernel was written after the round-1 GPU budget was spent and has no
 these tests only run with FFWM_EXPERIMENTAL=1 (the file sorts last so that a trap in an unproven kernel
 cannot poison the CUDA context of the established suite).  The first gpurun call of round 2 is
 `FFWM_EXPERIMENTAL=1 python -m pytest tests/test_zz_wgrad_tc_gpu.py -x -q`.
-Tolerance: 2e-5 of max|ref| (5e-5 when more than 2^17 pixels are summed), the forward kernel's contract."""
+Tolerance: 4e-5 of max|ref|: a CTA's accumulation chain is capped at 768 truncating tensor-core updates (~2e-5,
+the forward kernel's measured error at the same chain length); the path's contract is 1e-4."""
 import os
 
 import pytest
@@ -35,10 +36,10 @@ def test_conv3x3_wgrad_matches_fp64(b, cin, cout, h, w):
     gw = torch.zeros(cout, cin, 3, 3, device=DEV)
     ops.conv3x3_wgrad(xd, gd, gw)
     torch.cuda.synchronize()
-    assert rel(gw, wt.grad) <= (2e-5 if b * h * w <= (1 << 17) else 5e-5)
+    assert rel(gw, wt.grad) <= 4e-5
     # accumulates into the caller's buffer
     ops.conv3x3_wgrad(xd, gd, gw)
-    assert rel(gw, 2 * wt.grad) <= 5e-5
+    assert rel(gw, 2 * wt.grad) <= 4e-5
 
 
 def test_conv3x3_wgrad_strided_views():
@@ -51,7 +52,7 @@ def test_conv3x3_wgrad_strided_views():
     F.conv2d(x.double(), wt, None, padding=1).backward(go.double())
     gw = torch.zeros(35, 24, 3, 3, device=DEV)
     ops.conv3x3_wgrad(x, go, gw)
-    assert rel(gw, wt.grad) <= 2e-5
+    assert rel(gw, wt.grad) <= 4e-5
 
 
 def test_conv_module_with_tc_wgrad(monkeypatch):
@@ -65,4 +66,4 @@ def test_conv_module_with_tc_wgrad(monkeypatch):
     x64 = x.detach().double().requires_grad_()
     w64, b64 = m.weight.detach().double().requires_grad_(), m.bias.detach().double().requires_grad_()
     F.conv2d(x64, w64, b64, padding=1).backward(go.double())
-    assert rel(m.weight.grad, w64.grad) <= 2e-5 and rel(m.bias.grad, b64.grad) <= 1e-5 and rel(x.grad, x64.grad) <= 2e-5
+    assert rel(m.weight.grad, w64.grad) <= 4e-5 and rel(m.bias.grad, b64.grad) <= 1e-5 and rel(x.grad, x64.grad) <= 2e-5
