@@ -30,6 +30,7 @@
 //   * warp-specialised 2-stage mbarrier pipeline as in conv3x3_tc.cu: 8 producer warps stage (split
 //     hi/lo, 16-byte conflict-free stores), lane 0 of warp 8 issues 36 MMAs per stage and commits.
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -57,10 +58,12 @@ constexpr int WG_ITEMS = WG_A_ITEMS + WG_N / 8;
 // after 768 updates (the forward kernel's measured 1-2e-5 at 675 updates; simulated: 1e-4 at 4096, 1.4e-3 at the
 // 49152 a whole 8x128x128 batch would need).  Partial sums of the splits meet in fp32 REDs (round to nearest).
 constexpr int WG_MAX_STAGES = 64;
+constexpr int WG_EPI_PITCH = 9 * WG_NCI + 1;             // floats per row of the epilogue tile (odd: conflict-free columns)
 constexpr int WG_ITEMS_PER_WARP = (WG_ITEMS + WG_PRODUCERS / 32 - 1) / (WG_PRODUCERS / 32);
 static_assert(WG_A_LBO % 128 == 0 && WG_B_LBO % 128 == 0 && WG_STAGE % 128 == 0, "operand tiles stay 128-byte aligned");
 static_assert(3 * WG_N <= WG_TMEM_COLS && WG_N % 16 == 0 && WG_N <= 256, "three accumulators of N columns");
 static_assert(WG_SMEM <= 227 * 1024, "shared memory");
+static_assert(64 * WG_EPI_PITCH * 4 <= 2 * WG_STAGE, "the epilogue tile reuses the stage buffers");
 
 struct WgGeo {
     int cout, cin, h, w;
@@ -69,6 +72,7 @@ struct WgGeo {
     int n_ci_tiles;
     int stages_total;    // B * H * ncb
     int stages_per_split;
+    int direct_epilogue; // 1: REDs straight from the TMEM registers (FFWM_WGRAD_DIRECT_EPILOGUE, A/B and fallback)
 };
 
 __global__ void __launch_bounds__(WG_PRODUCERS + 32, 1)
@@ -186,30 +190,64 @@ conv3x3_wgrad_tc_kernel(View<const float> x, View<const float> go, float* __rest
         }
     }
 
-    // ---- epilogue (producer warps): TMEM -> registers -> REDs into dW (lanes = output channels)
+    // ---- epilogue (producer warps).  All MMAs have completed when the last commit arrives, so the stage buffers
+    // are free.  Default: the accumulators go through shared memory in dW's own (ci, ky, kx) order, 64 output
+    // channels at a time, and leave as REDs whose lanes are consecutive addresses of one dW row (a CTA's partial
+    // result is 128 rows of up to 432 contiguous floats); g.direct_epilogue issues the REDs straight from the
+    // TMEM registers instead (lanes = output channels: one 32-byte sector per lane and instruction).
     if (warp < WG_PRODUCERS / 32) {
         mbar_wait(&bars[2 + ((nst - 1) & 1)], ((nst - 1) >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3, half = warp >> 2;
-        const int co = cot * WG_MT + q * 32 + lane;
+        float* tile = reinterpret_cast<float*>(wg_smem);                     // [64 rows][WG_EPI_PITCH]
 #pragma unroll 1
-        for (int blk = half; blk < 3 * WG_N / 16; blk += 2) {
-            const int c0 = blk * 16;
-            uint32_t v[16];
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int kx = c0 / WG_N, n0 = c0 % WG_N, ky = n0 / WG_NCI, ci0 = cit * WG_NCI + n0 % WG_NCI;
-            if (co < g.cout) {
-                float* dp = dw + (int64_t)co * s_co + ky * s_ky + kx * s_kx;
+        for (int pass = 0; pass < 2; ++pass) {
+            // every warp walks its TMEM blocks in both passes (tcgen05.ld is warp-collective and cheap); a warp
+            // whose lane quarter belongs to the other half of the output channels keeps nothing
+            const bool mine = g.direct_epilogue ? pass == 0 : (q >> 1) == pass;
+            if (g.direct_epilogue && pass == 1) break;
+            const int co = cot * WG_MT + q * 32 + lane;
+#pragma unroll 1
+            for (int blk = half; blk < 3 * WG_N / 16; blk += 2) {
+                if (!mine) continue;                                         // warp-uniform
+                const int c0 = blk * 16;
+                uint32_t v[16];
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int kx = c0 / WG_N, n0 = c0 % WG_N, ky = n0 / WG_NCI, cil = n0 % WG_NCI;
+                if (g.direct_epilogue) {
+                    if (co < g.cout) {
+                        float* dp = dw + (int64_t)co * s_co + ky * s_ky + kx * s_kx;
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (ci0 + j < g.cin) red_add(dp + (int64_t)(ci0 + j) * s_ci, __uint_as_float(v[j]));
+                        for (int j = 0; j < 16; ++j)
+                            if (cit * WG_NCI + cil + j < g.cin) red_add(dp + (int64_t)(cit * WG_NCI + cil + j) * s_ci, __uint_as_float(v[j]));
+                    }
+                } else {
+                    float* tp = tile + ((q & 1) * 32 + lane) * WG_EPI_PITCH + ky * 3 + kx;   // odd pitch: lanes -> distinct banks
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) tp[(cil + j) * 9] = __uint_as_float(v[j]);
+                }
             }
+            if (g.direct_epilogue) break;
+            asm volatile("bar.sync 1, %0;" ::"n"(WG_PRODUCERS) : "memory");  // tile complete (producer warps only)
+            const int nci = min(WG_NCI, g.cin - cit * WG_NCI);               // valid input channels of this tile
+#pragma unroll 1
+            for (int r = warp; r < 64; r += WG_PRODUCERS / 32) {
+                const int co_r = cot * WG_MT + pass * 64 + r;
+                if (co_r >= g.cout) break;                                   // warp-uniform; rows are ascending
+                float* dp = dw + (int64_t)co_r * s_co + (int64_t)(cit * WG_NCI) * s_ci;
+                const float* tr = tile + r * WG_EPI_PITCH;
+                for (int e = lane; e < nci * 9; e += 32) {
+                    const int ci_l = e / 9, t9 = e - ci_l * 9, ky = t9 / 3, kx = t9 - ky * 3;
+                    red_add(dp + (int64_t)ci_l * s_ci + ky * s_ky + kx * s_kx, tr[e]);
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(WG_PRODUCERS) : "memory");  // tile drained before the next pass refills it
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -249,6 +287,7 @@ extern "C" int ffwm_conv3x3_wgrad(const ffwm_tensor4* x, const ffwm_tensor4* gra
     int64_t splits = std::max<int64_t>(1, std::min<int64_t>(stages, sm_count() / tiles));
     g.stages_per_split = std::min(ceil_div(stages, splits), WG_MAX_STAGES);
     splits = ceil_div(stages, g.stages_per_split);                            // every split owns >= 1 stage
+    g.direct_epilogue = getenv("FFWM_WGRAD_DIRECT_EPILOGUE") ? 1 : 0;
     if (splits > 65535) { set_error("conv3x3_wgrad: grid too large"); return FFWM_ERR_TOO_LARGE; }
     cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
     if (e != cudaSuccess) { set_error("conv3x3_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }

@@ -6,6 +6,11 @@
 mkdir -p gpurun_out
 FFWM_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_zz_wgrad_tc_gpu.py -x -q > gpurun_out/r02_wgrad_pytest.log 2>&1; echo "wgrad pytest rc=$?"
 tail -25 gpurun_out/r02_wgrad_pytest.log
+# fallback / A-B: REDs straight from the TMEM registers instead of the shared-memory transposition
+FFWM_WGRAD_DIRECT_EPILOGUE=1 FFWM_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_zz_wgrad_tc_gpu.py -x -q > gpurun_out/r02_wgrad_pytest_direct.log 2>&1; echo "wgrad pytest (direct epilogue) rc=$?"
+tail -5 gpurun_out/r02_wgrad_pytest_direct.log
+FFWM_WGRAD_DIRECT_EPILOGUE=1 timeout 300 python -m benchmarks.conv --wgrad --out gpurun_out/r02_conv_wgrad_direct.json > gpurun_out/r02_conv_wgrad_direct.txt 2>&1; echo "wgrad bench (direct epilogue) rc=$?"
+tail -10 gpurun_out/r02_conv_wgrad_direct.txt
 timeout 300 python -m benchmarks.conv --wgrad --out gpurun_out/r02_conv_wgrad.json > gpurun_out/r02_conv_wgrad.txt 2>&1; echo "wgrad bench rc=$?"
 cat gpurun_out/r02_conv_wgrad.txt | tail -12
 # A/B on the headline: the train step with cuDNN weight gradients (default) and with the tcgen05 ones

@@ -116,18 +116,32 @@ def emulate(x, go, splits_hint):
                         b_hi = operand(smem, sB + (2 * t + kx) * c["B_LBO"], N, c["B_LBO"]).astype(np.float64)
                         b_lo = operand(smem, sB + c["B_PART"] + (2 * t + kx) * c["B_LBO"], N, c["B_LBO"]).astype(np.float64)
                         acc[:, kx * N:(kx + 1) * N] += a_hi @ b_hi.T + a_hi @ b_lo.T + a_lo @ b_hi.T
-            # ---- epilogue: column block c0 -> (kx, ky, ci0); lane -> co
-            for c0 in range(0, 3 * N, 16):
-                kx, n0 = divmod(c0, N)
-                ky, cil = divmod(n0, NCI)
-                for j in range(16):
-                    ci = cit * NCI + cil + j
-                    if ci >= cin:
+            # ---- epilogue: two passes of 64 output channels through a [64][9*NCI+1] tile in dW's (ci, ky, kx) order
+            pitch = 9 * NCI + 1
+            assert "constexpr int WG_EPI_PITCH = 9 * WG_NCI + 1;" in open(CU).read()
+            for ps in range(2):
+                tile = np.full(64 * pitch, np.nan)
+                for warp in range(8):
+                    q, half = warp & 3, warp >> 2
+                    if (q >> 1) != ps:
                         continue
-                    for lane in range(MT):
-                        co = cot * MT + lane
-                        if co < cout:
-                            dw[co, ci, ky, kx] += acc[lane, c0 + j]
+                    for blk in range(half, 3 * N // 16, 2):
+                        c0 = blk * 16
+                        kx, n0 = divmod(c0, N)
+                        ky, cil = divmod(n0, NCI)
+                        for lane in range(32):
+                            for j in range(16):
+                                tile[((q & 1) * 32 + lane) * pitch + (cil + j) * 9 + ky * 3 + kx] = acc[q * 32 + lane, c0 + j]
+                nci = min(NCI, cin - cit * NCI)
+                for r in range(64):
+                    co = cot * MT + ps * 64 + r
+                    if co >= cout:
+                        break
+                    for e in range(nci * 9):
+                        ci_l, t9 = divmod(e, 9)
+                        ky, kx = divmod(t9, 3)
+                        assert not np.isnan(tile[r * pitch + e])
+                        dw[co, cit * NCI + ci_l, ky, kx] += tile[r * pitch + e]
     return dw
 
 
