@@ -82,13 +82,41 @@ def wgrad_bench(out_path):
             r["err_tcgen05"], r["err_cudnn_fp32"], r["err_cudnn_tf32"]))
 
 
+def nt128_bench(out_path):
+    """conv3x3_tc_kernel<128, 64> (validated) vs <128, 128> (experimental) on the W = 128 shapes with > 64 output channels."""
+    from ffwm_b200 import ops
+    dev = torch.device("cuda", 0)
+    rows = []
+    for name, cin, cout, r in SHAPES:
+        if r != 128 or cout <= 64:
+            continue
+        x = torch.randn(8, cin, r, r, device=dev)
+        w = torch.randn(cout, cin, 3, 3, device=dev) / (cin * 9) ** 0.5
+        b = torch.randn(cout, device=dev)
+        o64, o128 = torch.empty(8, cout, r, r, device=dev), torch.empty(8, cout, r, r, device=dev)
+        p64, p128 = ops.conv3x3_pack_weights(w), ops.conv3x3_pack_weights(w, nt=128)
+        t64 = timeit(lambda: ops.conv3x3_forward(x, p64, b, o64))
+        t128 = timeit(lambda: ops.conv3x3_forward(x, p128, b, o128, nt=128))
+        flop = 2.0 * 8 * r * r * cin * cout * 9
+        rows.append(dict(shape=name, ms_nt64=t64, ms_nt128=t128, tflops_nt64=flop / t64 / 1e9, tflops_nt128=flop / t128 / 1e9,
+                         max_abs_diff=float((o64 - o128).abs().max())))
+    os.makedirs(os.path.dirname(out_path), exist_ok=True)
+    json.dump(rows, open(out_path, "w"), indent=1)
+    for r in rows:
+        print("%-22s nt64 %.3f ms (%.1f TF/s)   nt128 %.3f ms (%.1f TF/s)   max|diff| %.1e" % (
+            r["shape"], r["ms_nt64"], r["tflops_nt64"], r["ms_nt128"], r["tflops_nt128"], r["max_abs_diff"]))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--wgrad", action="store_true", help="measure the experimental tcgen05 weight gradient instead")
+    ap.add_argument("--nt128", action="store_true", help="A/B the experimental 128-channel CTA tile on the W = 128 shapes")
     args = ap.parse_args()
     if args.wgrad:
         return wgrad_bench(args.out or os.path.join(ROOT, "gpurun_out", "conv_wgrad.json"))
+    if args.nt128:
+        return nt128_bench(args.out or os.path.join(ROOT, "gpurun_out", "conv_nt128.json"))
     args.out = args.out or os.path.join(ROOT, "gpurun_out", "conv.json")
     from ffwm_b200 import ops
     dev = torch.device("cuda", 0)

@@ -43,6 +43,9 @@ SIGNATURES = {
     "ffwm_conv3x3_pack_weights": [_T4P, _I, _VP, ctypes.c_int64, _VP],
     "ffwm_conv3x3_forward": [_T4P, _VP, _VP, _T4P, _VP],
     "ffwm_conv3x3_wgrad": [_T4P, _T4P, _T4P, _VP],
+    "ffwm_conv3x3_packed_floats_nt": [_I, _I, _I],
+    "ffwm_conv3x3_pack_weights_nt": [_T4P, _I, _VP, ctypes.c_int64, _I, _VP],
+    "ffwm_conv3x3_forward_nt": [_T4P, _VP, _VP, _T4P, _I, _VP],
 }
 
 _lib = None
@@ -67,7 +70,8 @@ def lib():
             fn = getattr(l, name)          # AttributeError if the symbol is not exported
             fn.argtypes = argtypes
             fn.restype = {"ffwm_last_error": ctypes.c_char_p, "ffwm_kernel_launches": ctypes.c_ulonglong,
-                          "ffwm_conv3x3_packed_floats": ctypes.c_int64}.get(name, ctypes.c_int)
+                          "ffwm_conv3x3_packed_floats": ctypes.c_int64,
+                          "ffwm_conv3x3_packed_floats_nt": ctypes.c_int64}.get(name, ctypes.c_int)
         if l.ffwm_abi_version() != ABI_VERSION:
             raise ImportError("ffwm_b200: ABI version mismatch (library %d, binding %d)"
                               % (l.ffwm_abi_version(), ABI_VERSION))

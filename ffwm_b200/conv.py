@@ -13,6 +13,8 @@ maps of 16x16 and below) stays on cuDNN (library).
                    FFWM_WGRAD_TC=1 opts in to the tcgen05 weight-gradient kernel (csrc/conv3x3_wgrad_tc.cu),
                    which is EXPERIMENTAL: written after the round-1 GPU budget was spent, checked by a CPU
                    emulation of its indexing only, not yet run or measured on a B200
+FFWM_CONV_NT128=1 selects 128 (instead of 64) output channels per CTA for the W = 128 layers with more than
+64 output channels — also experimental and unmeasured; the validated kernels are bit-identical either way.
 
 The module is a drop-in `nn.Conv2d`: same parameters, same state_dict keys, spectral norm hooks work
 unchanged (the weight is re-packed on every call: 0.02 ms).
@@ -33,6 +35,12 @@ WGRAD_TC = os.environ.get("FFWM_WGRAD_TC", "0") == "1"     # experimental, unmea
 # its CTA tile is 128 output x 48 input channels: layers far below that (flow heads, RGB reconstructions,
 # the first convolutions on 3 channels: 0.7 % of the weight-gradient FLOPs of the step) stay on cuDNN
 WGRAD_MIN_COUT, WGRAD_MIN_CIN = 32, 16
+# experimental, unmeasured: 128 output channels per CTA for the W = 128 layers with more than 64 of them
+NT128 = os.environ.get("FFWM_CONV_NT128", "0") == "1"
+
+
+def _nt(width, n_out):
+    return 128 if (NT128 and width == 128 and n_out > 64) else 64
 
 
 def eligible(x, weight, stride, padding, dilation, groups, padding_mode="zeros"):
@@ -48,7 +56,8 @@ class Conv3x3TCFunction(Function):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         out = x.new_empty((x.size(0), weight.size(0), x.size(2), x.size(3)))
-        ops.conv3x3_forward(x, ops.conv3x3_pack_weights(weight), bias, out)
+        nt = _nt(x.size(3), weight.size(0))
+        ops.conv3x3_forward(x, ops.conv3x3_pack_weights(weight, nt=nt), bias, out, nt=nt)
         return out
 
     @staticmethod
@@ -58,7 +67,8 @@ class Conv3x3TCFunction(Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
-            ops.conv3x3_forward(grad_out, ops.conv3x3_pack_weights(weight, dgrad=True), None, gx)
+            nt = _nt(grad_out.size(3), weight.size(1))
+            ops.conv3x3_forward(grad_out, ops.conv3x3_pack_weights(weight, dgrad=True, nt=nt), None, gx, nt=nt)
         if WGRAD_TC and weight.size(0) >= WGRAD_MIN_COUT and weight.size(1) >= WGRAD_MIN_CIN:
             if ctx.needs_input_grad[1]:
                 gw = torch.zeros_like(weight, memory_format=torch.contiguous_format)

@@ -38,7 +38,11 @@
 
 namespace ffwm {
 
-constexpr int CV_NT = 64;              // output channels per CTA = MMA N
+// Output channels per CTA = MMA N: 64, or 128 for W = 128 (NT is a template parameter).  With N = 64 an MMA reads
+// 4 KB of A and 2 KB of B from shared memory for 33 clk of math (48 clk at 128 B/clk: shared-memory bound, ncu
+// l1tex 72 % / tensor pipe 48 %); N = 128 reads 4 + 4 KB for 66 clk of math.  The N = 128 variant is EXPERIMENTAL
+// (written after the round-1 GPU budget was spent, not yet run): callers opt in per call (nt argument of the
+// *_nt entry points; ffwm_b200/conv.py: FFWM_CONV_NT128=1).
 constexpr int CV_KB = 8;               // input channels per K block = one tf32 MMA K
 constexpr int CV_PRODUCERS = 256;
 
@@ -49,10 +53,10 @@ constexpr int CV_PRODUCERS = 256;
 //             so a horizontal shift cannot be expressed by the start address across the row
 //             seam; three copies are staged instead, copy kx holding in[.., x + kx - 1] with zeros
 //             at the border; vertical taps = descriptor start + ky * WI * 16 bytes.
-template <int WI>
+template <int WI, int NT>
 struct CvGeo {
     static constexpr int RPT = 128 / WI;                       // image rows per M tile
-    static constexpr int MT = WI == 128 ? 4 : 2;               // M tiles (accumulators) per CTA
+    static constexpr int MT = (WI == 128 && NT == 64) ? 4 : 2; // M tiles (accumulators) per CTA
     static constexpr int ROWS = MT * RPT;                      // output rows per CTA
     static constexpr int IN_ROWS = ROWS + 2;
     static constexpr int NCOPY = WI == 128 ? 1 : 3;
@@ -61,32 +65,34 @@ struct CvGeo {
     static constexpr int A_COPY = 2 * A_CHUNK;                 // both k-chunks
     static constexpr int A_PART = NCOPY * A_COPY;              // hi or lo
     static constexpr int A_STAGE = 2 * A_PART;
-    static constexpr int STAGE = A_STAGE + 2 * 9 * 2 * CV_NT * 16;
+    static constexpr int B_CHUNK = NT * 16;                    // one k-chunk of one tap: NT co x 4 ci
+    static constexpr int B_TAP = 2 * B_CHUNK;                  // both k-chunks
+    static constexpr int B_STAGE = 2 * 9 * B_TAP;              // layout: [tap][hl][kchunk][co][4]
+    static constexpr int STAGE = A_STAGE + B_STAGE;
     static constexpr int SMEM = 2 * STAGE + 64;                // + 6 mbarriers + tmem address
     static constexpr int TMEM_COLS = 256;
+    static_assert(MT * NT <= TMEM_COLS && SMEM <= 227 * 1024, "TMEM columns / shared memory");
 };
-constexpr int CV_B_CHUNK = CV_NT * 16;                    // one k-chunk of one tap: 64 co x 4 ci
-constexpr int CV_B_TAP = 2 * CV_B_CHUNK;                  // both k-chunks
-constexpr int CV_B_STAGE = 2 * 9 * CV_B_TAP;              // layout: [tap][hl][kchunk][co][4]
 
 // ---------------------------------------------------------------- weight packing
-// w (Cout, Cin, 3, 3) -> packed[cob][kb][tap][hl][kchunk][co_local 64][4 ci]  (hl: 0 = hi, 1 = lo)
+// w (Cout, Cin, 3, 3) -> packed[cob][kb][tap][hl][kchunk][co_local NT][4 ci]  (hl: 0 = hi, 1 = lo; NT = nt)
 // dgrad = 1 packs the weights of the data-gradient convolution: roles of Cout/Cin swapped and the
 // taps flipped, so that conv3x3(grad_output, packed) = grad_input.
+template <int nt>
 __global__ void conv3x3_pack_kernel(const float* __restrict__ w, float* __restrict__ packed, int cout, int cin, int dgrad,
                                     int64_t s_co, int64_t s_ci, int64_t s_ky, int64_t s_kx) {
     const int n_out = dgrad ? cin : cout, n_in = dgrad ? cout : cin;     // of the convolution being packed
-    const int ncob = (n_out + CV_NT - 1) / CV_NT, nkb = (n_in + CV_KB - 1) / CV_KB;
-    const int64_t total = (int64_t)ncob * nkb * 9 * 2 * CV_NT * 4;       // (hi,lo) pairs are written together
+    const int ncob = (n_out + nt - 1) / nt, nkb = (n_in + CV_KB - 1) / CV_KB;
+    const int64_t total = (int64_t)ncob * nkb * 9 * 2 * nt * 4;       // (hi,lo) pairs are written together
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = i;
         const int j = r % 4; r /= 4;
-        const int col = r % CV_NT; r /= CV_NT;
+        const int col = r % nt; r /= nt;
         const int kc = r % 2; r /= 2;
         const int tap = r % 9; r /= 9;
         const int kb = r % nkb; r /= nkb;
         const int cob = (int)r;
-        const int o = cob * CV_NT + col, c = kb * CV_KB + kc * 4 + j;
+        const int o = cob * nt + col, c = kb * CV_KB + kc * 4 + j;
         float v = 0.f;
         if (o < n_out && c < n_in) {
             const int ky = tap / 3, kx = tap % 3;
@@ -95,10 +101,10 @@ __global__ void conv3x3_pack_kernel(const float* __restrict__ w, float* __restri
         }
         const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
         const float lo = v - hi;
-        const int64_t base = ((((int64_t)cob * nkb + kb) * 9 + tap) * 2) * (2 * CV_NT * 4);
-        const int64_t within = ((int64_t)kc * CV_NT + col) * 4 + j;
+        const int64_t base = ((((int64_t)cob * nkb + kb) * 9 + tap) * 2) * (2 * nt * 4);
+        const int64_t within = ((int64_t)kc * nt + col) * 4 + j;
         packed[base + within] = hi;
-        packed[base + 2 * CV_NT * 4 + within] = lo;
+        packed[base + 2 * nt * 4 + within] = lo;
     }
 }
 
@@ -107,11 +113,11 @@ __global__ void conv3x3_pack_kernel(const float* __restrict__ w, float* __restri
 // lane 0 copies the packed weights with one bulk async copy per K block and issues the MMAs.
 // Pipeline state lives in mbarriers: fullA[2] (256 producer arrivals), fullB[2] (bulk-copy
 // transaction bytes), empty[2] (tcgen05.commit of the MMAs that read the buffer).
-template <int WI>
+template <int WI, int NT>
 __global__ void __launch_bounds__(CV_PRODUCERS + 32, 1)
 conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const float* __restrict__ bias,
                   View<float> out, int nkb) {
-    using G = CvGeo<WI>;
+    using G = CvGeo<WI, NT>;
     extern __shared__ __align__(128) unsigned char cv_smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(cv_smem + 2 * G::STAGE);    // fullA[0,1] fullB[2,3] empty[4,5]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cv_smem + 2 * G::STAGE + 48);
@@ -139,7 +145,7 @@ conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const f
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
-    const float* pk_base = packed + ((int64_t)cob * nkb) * (CV_B_STAGE / 4);
+    const float* pk_base = packed + ((int64_t)cob * nkb) * (G::B_STAGE / 4);
 
     if (warp < CV_PRODUCERS / 32) {
         // ================= producers: activations of K block kb -> stage buffer kb & 1 =================
@@ -182,14 +188,14 @@ conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const f
         }
     } else if (lane == 0) {
         // ================= issuer: weight copies + MMAs =================
-        constexpr uint32_t IDESC = umma_idesc_tf32(128, CV_NT);
+        constexpr uint32_t IDESC = umma_idesc_tf32(128, NT);
         auto copy_b = [&](int kb) {
             const int buf = kb & 1;
             const uint32_t bar = smem_u32(&bars[2 + buf]);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(CV_B_STAGE) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(G::B_STAGE) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              smem_u32(cv_smem + buf * G::STAGE + G::A_STAGE)),
-                         "l"(pk_base + (int64_t)kb * (CV_B_STAGE / 4)), "r"(CV_B_STAGE), "r"(bar)
+                         "l"(pk_base + (int64_t)kb * (G::B_STAGE / 4)), "r"(G::B_STAGE), "r"(bar)
                          : "memory");
         };
         copy_b(0);
@@ -199,7 +205,7 @@ conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const f
             mbar_wait(&bars[2 + buf], (kb >> 1) & 1);        // weights landed
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sA = smem_u32(cv_smem + buf * G::STAGE), sB = sA + G::A_STAGE;
-            const uint64_t dA0 = umma_desc(sA, G::A_CHUNK, 128), dB0 = umma_desc(sB, CV_B_CHUNK, 128);
+            const uint64_t dA0 = umma_desc(sA, G::A_CHUNK, 128), dB0 = umma_desc(sB, G::B_CHUNK, 128);
 #pragma unroll
             for (int t = 0; t < G::MT; ++t) {
 #pragma unroll
@@ -208,8 +214,8 @@ conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const f
                     const int a_off = WI == 128 ? ((t + ky) * G::ROW_SLOTS + kx) * 16
                                                 : kx * G::A_COPY + (t * G::RPT + ky) * WI * 16;
                     const uint64_t dA_hi = dA0 + (uint64_t)(a_off >> 4), dA_lo = dA_hi + (G::A_PART >> 4);
-                    const uint64_t dB_hi = dB0 + (uint64_t)((tap * 2 * CV_B_TAP) >> 4), dB_lo = dB_hi + (CV_B_TAP >> 4);
-                    const uint32_t d = tmem + t * CV_NT;
+                    const uint64_t dB_hi = dB0 + (uint64_t)((tap * 2 * G::B_TAP) >> 4), dB_lo = dB_hi + (G::B_TAP >> 4);
+                    const uint32_t d = tmem + t * NT;
                     if (tap == 0) umma_tf32(d, dA_hi, dB_hi, IDESC, kb > 0);
                     else umma_tf32_acc(d, dA_hi, dB_hi, IDESC);
                     umma_tf32_acc(d, dA_hi, dB_lo, IDESC);
@@ -235,10 +241,10 @@ conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const f
         for (int t = 0; t < G::MT; ++t) {
             const int y = y0 + t * G::RPT + yo;
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const int col0 = half * 32 + cc * 16;
+            for (int cc = 0; cc < NT / 32; ++cc) {
+                const int col0 = half * (NT / 2) + cc * 16;
                 uint32_t v[16];
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * CV_NT + col0);
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * NT + col0);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
@@ -248,7 +254,7 @@ conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const f
                 if (y < out.h) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const int co = cob * CV_NT + col0 + j;
+                        const int co = cob * NT + col0 + j;
                         if (co < out.c) {
                             float o = __uint_as_float(v[j]);
                             if (bias) o += __ldg(bias + co);
@@ -264,42 +270,54 @@ conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const f
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(G::TMEM_COLS) : "memory");
 }
 
-template <int WI>
+template <int WI, int NT = 64>
 static int launch_conv3x3(const View<const float>& xv, const float* packed, const float* bias, const View<float>& ov, cudaStream_t st) {
-    using G = CvGeo<WI>;
-    const int ncob = ceil_div(ov.c, CV_NT), nkb = ceil_div(xv.c, CV_KB);
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<WI>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+    using G = CvGeo<WI, NT>;
+    const int ncob = ceil_div(ov.c, NT), nkb = ceil_div(xv.c, CV_KB);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<WI, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
     if (e != cudaSuccess) { set_error("conv3x3_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
     dim3 grid(ceil_div(ov.h, G::ROWS), ncob, ov.n);
-    conv3x3_tc_kernel<WI><<<grid, CV_PRODUCERS + 32, G::SMEM, st>>>(xv, packed, bias, ov, nkb);
+    conv3x3_tc_kernel<WI, NT><<<grid, CV_PRODUCERS + 32, G::SMEM, st>>>(xv, packed, bias, ov, nkb);
     return FFWM_OK;
 }
 
 }  // namespace ffwm
 
-extern "C" int64_t ffwm_conv3x3_packed_floats(int cout, int cin) {
-    if (cout <= 0 || cin <= 0) return 0;
-    const int64_t ncob = (cout + ffwm::CV_NT - 1) / ffwm::CV_NT, nkb = (cin + ffwm::CV_KB - 1) / ffwm::CV_KB;
-    return ncob * nkb * (ffwm::CV_B_STAGE / 4);
-}
+static bool cv_nt_ok(int nt) { return nt == 64 || nt == 128; }
 
-extern "C" int ffwm_conv3x3_pack_weights(const ffwm_tensor4* weight, int dgrad, float* packed, int64_t packed_floats, void* stream) {
+extern "C" int64_t ffwm_conv3x3_packed_floats_nt(int cout, int cin, int nt) {
+    if (cout <= 0 || cin <= 0 || !cv_nt_ok(nt)) return 0;
+    const int64_t ncob = (cout + nt - 1) / nt, nkb = (cin + ffwm::CV_KB - 1) / ffwm::CV_KB;
+    return ncob * nkb * (2 * 9 * 2 * nt * 4);                                 // CvGeo::B_STAGE / 4 floats per (cob, kb)
+}
+extern "C" int64_t ffwm_conv3x3_packed_floats(int cout, int cin) { return ffwm_conv3x3_packed_floats_nt(cout, cin, 64); }
+
+extern "C" int ffwm_conv3x3_pack_weights_nt(const ffwm_tensor4* weight, int dgrad, float* packed, int64_t packed_floats, int nt, void* stream) {
     using namespace ffwm;
     if (!weight || !weight->data || !packed) { set_error("conv3x3_pack_weights: null pointer"); return FFWM_ERR_NULL; }
     if (weight->size[2] != 3 || weight->size[3] != 3) { set_error("conv3x3_pack_weights: kernel must be 3x3"); return FFWM_ERR_SHAPE; }
+    if (!cv_nt_ok(nt)) { set_error("conv3x3_pack_weights: nt must be 64 or 128 (got %d)", nt); return FFWM_ERR_ARG; }
     const int cout = (int)weight->size[0], cin = (int)weight->size[1];
-    const int64_t need = dgrad ? ffwm_conv3x3_packed_floats(cin, cout) : ffwm_conv3x3_packed_floats(cout, cin);
+    const int64_t need = dgrad ? ffwm_conv3x3_packed_floats_nt(cin, cout, nt) : ffwm_conv3x3_packed_floats_nt(cout, cin, nt);
     if (packed_floats < need) { set_error("conv3x3_pack_weights: packed buffer too small (%lld < %lld floats)", (long long)packed_floats, (long long)need); return FFWM_ERR_SHAPE; }
     const int64_t pairs = need / 2;
     const int blocks = (int)std::min<int64_t>((pairs + 255) / 256, 4096);
-    conv3x3_pack_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const float*>(weight->data), packed, cout, cin, dgrad, weight->stride[0], weight->stride[1], weight->stride[2], weight->stride[3]);
+    const float* wp = static_cast<const float*>(weight->data);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (nt == 64)
+        conv3x3_pack_kernel<64><<<blocks, 256, 0, st>>>(wp, packed, cout, cin, dgrad, weight->stride[0], weight->stride[1], weight->stride[2], weight->stride[3]);
+    else
+        conv3x3_pack_kernel<128><<<blocks, 256, 0, st>>>(wp, packed, cout, cin, dgrad, weight->stride[0], weight->stride[1], weight->stride[2], weight->stride[3]);
     return check_launch("conv3x3_pack_weights");
+}
+extern "C" int ffwm_conv3x3_pack_weights(const ffwm_tensor4* weight, int dgrad, float* packed, int64_t packed_floats, void* stream) {
+    return ffwm_conv3x3_pack_weights_nt(weight, dgrad, packed, packed_floats, 64, stream);
 }
 
 // conv2d(x, w, bias, stride 1, padding 1) for 3x3 kernels with `packed` = pack_weights(w): x (B,Cin,H,W) fp32,
 // out (B,Cout,H,W) fp32, W in {128, 64, 32, 16}.  Replaces the cuDNN call behind nn.Conv2d(…, 3, 1, 1) for those shapes.
-extern "C" int ffwm_conv3x3_forward(const ffwm_tensor4* x, const float* packed, const float* bias, const ffwm_tensor4* out, void* stream) {
+// nt = output channels per CTA the weights were packed for: 64, or 128 (W = 128 only, experimental).
+extern "C" int ffwm_conv3x3_forward_nt(const ffwm_tensor4* x, const float* packed, const float* bias, const ffwm_tensor4* out, int nt, void* stream) {
     using namespace ffwm;
     View<const float> xv;
     View<float> ov;
@@ -311,13 +329,18 @@ extern "C" int ffwm_conv3x3_forward(const ffwm_tensor4* x, const float* packed, 
         set_error("conv3x3_forward: needs W in {128,64,32,16} and equal N,H,W (x %dx%dx%dx%d, out %dx%dx%dx%d)", xv.n, xv.c, xv.h, xv.w, ov.n, ov.c, ov.h, ov.w);
         return FFWM_ERR_SHAPE;
     }
+    if (nt != 64 && !(nt == 128 && xv.w == 128)) { set_error("conv3x3_forward: nt must be 64, or 128 with W = 128 (got nt %d, W %d)", nt, xv.w); return FFWM_ERR_ARG; }
     if ((int64_t)ov.n * ov.c * ov.h == 0) return FFWM_OK;
-    if (ov.n > 65535 || ceil_div(ov.c, CV_NT) > 65535) { set_error("conv3x3_forward: grid too large"); return FFWM_ERR_TOO_LARGE; }
+    if (ov.n > 65535 || ceil_div(ov.c, nt) > 65535) { set_error("conv3x3_forward: grid too large"); return FFWM_ERR_TOO_LARGE; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    rc = xv.w == 128  ? launch_conv3x3<128>(xv, packed, bias, ov, st)
+    rc = nt == 128    ? launch_conv3x3<128, 128>(xv, packed, bias, ov, st)
+         : xv.w == 128 ? launch_conv3x3<128>(xv, packed, bias, ov, st)
          : xv.w == 64 ? launch_conv3x3<64>(xv, packed, bias, ov, st)
          : xv.w == 32 ? launch_conv3x3<32>(xv, packed, bias, ov, st)
                       : launch_conv3x3<16>(xv, packed, bias, ov, st);
     if (rc) return rc;
     return check_launch("conv3x3_forward");
+}
+extern "C" int ffwm_conv3x3_forward(const ffwm_tensor4* x, const float* packed, const float* bias, const ffwm_tensor4* out, void* stream) {
+    return ffwm_conv3x3_forward_nt(x, packed, bias, out, 64, stream);
 }

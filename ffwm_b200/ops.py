@@ -53,23 +53,27 @@ def grid_warp_backward(images, flow, grad_output, grad_images, grad_flow):
            L.t4(grad_images), L.t4(grad_flow), L.dtype_code(images))
 
 
-def conv3x3_pack_weights(weight, dgrad=False):
-    """(Cout,Cin,3,3) fp32 CUDA weight -> packed image for conv3x3_forward (dgrad: for the data gradient)."""
+def conv3x3_pack_weights(weight, dgrad=False, nt=64):
+    """(Cout,Cin,3,3) fp32 CUDA weight -> packed image for conv3x3_forward (dgrad: for the data gradient).
+    nt: output channels per CTA the image is laid out for (64; 128 is experimental, W = 128 only)."""
     import ctypes
     import torch
     dev = L.require_cuda(weight)
     cout, cin = weight.shape[:2]
-    n = L.lib().ffwm_conv3x3_packed_floats(int(cin if dgrad else cout), int(cout if dgrad else cin))
+    n = L.lib().ffwm_conv3x3_packed_floats_nt(int(cin if dgrad else cout), int(cout if dgrad else cin), int(nt))
+    if n <= 0:
+        raise ValueError("conv3x3_pack_weights: bad shape or nt (cout %d, cin %d, nt %d)" % (cout, cin, nt))
     packed = torch.empty(n, dtype=torch.float32, device=weight.device)
-    L.call("ffwm_conv3x3_pack_weights", dev, L.t4(weight), int(bool(dgrad)), ctypes.c_void_p(packed.data_ptr()), ctypes.c_int64(n))
+    L.call("ffwm_conv3x3_pack_weights_nt", dev, L.t4(weight), int(bool(dgrad)), ctypes.c_void_p(packed.data_ptr()),
+           ctypes.c_int64(n), int(nt))
     return packed
 
 
-def conv3x3_forward(x, packed, bias, out):
+def conv3x3_forward(x, packed, bias, out, nt=64):
     import ctypes
     dev = L.require_cuda(x, packed, out)
-    L.call("ffwm_conv3x3_forward", dev, L.t4(x), ctypes.c_void_p(packed.data_ptr()),
-           ctypes.c_void_p(bias.data_ptr() if bias is not None else None), L.t4(out))
+    L.call("ffwm_conv3x3_forward_nt", dev, L.t4(x), ctypes.c_void_p(packed.data_ptr()),
+           ctypes.c_void_p(bias.data_ptr() if bias is not None else None), L.t4(out), int(nt))
 
 
 def conv3x3_wgrad(x, grad_out, grad_weight):

@@ -136,6 +136,14 @@ int ffwm_conv3x3_pack_weights(const ffwm_tensor4* weight, int dgrad, float* pack
 /* out (B,Cout,H,W) = conv2d(x (B,Cin,H,W), weight, bias, stride 1, padding 1), W in {128,64,32,16}; bias may be NULL. */
 int ffwm_conv3x3_forward(const ffwm_tensor4* x, const float* packed, const float* bias, const ffwm_tensor4* out, void* stream);
 
+/* The same three with an explicit CTA tile: nt = output channels per CTA (the MMA N) the weights are packed for.
+ * nt = 64 is what the functions above use.  nt = 128 (W = 128 only) halves the shared-memory operand traffic per
+ * FLOP; it is EXPERIMENTAL — written after the round-1 GPU budget was spent, not yet run on a B200 — and nothing
+ * selects it unless asked to (ffwm_b200/conv.py: FFWM_CONV_NT128=1). */
+int64_t ffwm_conv3x3_packed_floats_nt(int cout, int cin, int nt);
+int ffwm_conv3x3_pack_weights_nt(const ffwm_tensor4* weight, int dgrad, float* packed, int64_t packed_floats, int nt, void* stream);
+int ffwm_conv3x3_forward_nt(const ffwm_tensor4* x, const float* packed, const float* bias, const ffwm_tensor4* out, int nt, void* stream);
+
 /* Weight gradient of the same convolution (the grad_weight output of aten::convolution_backward behind
  * nn.Conv2d(Cin, Cout, 3, 1, 1), models/base_networks.py:218-222,235-246), tcgen05, 3xTF32:
  *   grad_weight (Cout,Cin,3,3) += sum_{b,y,x} grad_out[b,co,y,x] * x[b,ci,y+ky-1,x+kx-1]   (zero padding)

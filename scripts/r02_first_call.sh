@@ -13,12 +13,18 @@ FFWM_WGRAD_DIRECT_EPILOGUE=1 timeout 300 python -m benchmarks.conv --wgrad --out
 tail -10 gpurun_out/r02_conv_wgrad_direct.txt
 timeout 300 python -m benchmarks.conv --wgrad --out gpurun_out/r02_conv_wgrad.json > gpurun_out/r02_conv_wgrad.txt 2>&1; echo "wgrad bench rc=$?"
 cat gpurun_out/r02_conv_wgrad.txt | tail -12
+# the 128-channel CTA tile of the forward / data-gradient kernel (W = 128)
+FFWM_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_zz_conv_nt128_gpu.py -x -q > gpurun_out/r02_nt128_pytest.log 2>&1; echo "nt128 pytest rc=$?"
+tail -8 gpurun_out/r02_nt128_pytest.log
+timeout 300 python -m benchmarks.conv --nt128 --out gpurun_out/r02_conv_nt128.json > gpurun_out/r02_conv_nt128.txt 2>&1; echo "nt128 bench rc=$?"
+cat gpurun_out/r02_conv_nt128.txt | tail -6
 # A/B on the headline: the train step with cuDNN weight gradients (default) and with the tcgen05 ones
 timeout 600 python bench.py --no-cpu-baseline --no-warp > gpurun_out/r02_bench_cudnn_wgrad.json 2> gpurun_out/r02_bench_a.err; echo "bench (cuDNN wgrad) rc=$?"
 FFWM_WGRAD_TC=1 timeout 600 python bench.py --no-cpu-baseline --no-warp > gpurun_out/r02_bench_tc_wgrad.json 2> gpurun_out/r02_bench_b.err; echo "bench (tcgen05 wgrad) rc=$?"
+FFWM_CONV_NT128=1 timeout 600 python bench.py --no-cpu-baseline --no-warp > gpurun_out/r02_bench_nt128.json 2> gpurun_out/r02_bench_c.err; echo "bench (nt128) rc=$?"
 python - <<'PY'
 import json
-for f in ("r02_bench_cudnn_wgrad", "r02_bench_tc_wgrad"):
+for f in ("r02_bench_cudnn_wgrad", "r02_bench_tc_wgrad", "r02_bench_nt128"):
     try:
         d = json.loads(open("gpurun_out/%s.json" % f).read().strip().splitlines()[-1])
         print(f, d["value"], d["unit"], d["ms_per_step"], "ms/step")
