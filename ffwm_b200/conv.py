@@ -70,10 +70,12 @@ class Conv3x3TCFunction(Function):
             nt = _nt(grad_out.size(3), weight.size(1))
             ops.conv3x3_forward(grad_out, ops.conv3x3_pack_weights(weight, dgrad=True, nt=nt), None, gx, nt=nt)
         if WGRAD_TC and weight.size(0) >= WGRAD_MIN_COUT and weight.size(1) >= WGRAD_MIN_CIN:
+            want_b = ctx.has_bias and ctx.needs_input_grad[2]
             if ctx.needs_input_grad[1]:
                 gw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
-                ops.conv3x3_wgrad(x, grad_out, gw)
-            if ctx.has_bias and ctx.needs_input_grad[2]:
+                gb = grad_out.new_zeros(weight.size(0)) if want_b else None    # falls out of staging grad_out
+                ops.conv3x3_wgrad(x, grad_out, gw, gb)
+            elif want_b:
                 gb = grad_out.sum((0, 2, 3))
         elif ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             _, gw, gb = torch.ops.aten.convolution_backward(

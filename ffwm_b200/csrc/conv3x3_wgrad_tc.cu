@@ -63,6 +63,7 @@ constexpr int WG_ITEMS_PER_WARP = (WG_ITEMS + WG_PRODUCERS / 32 - 1) / (WG_PRODU
 static_assert(WG_A_LBO % 128 == 0 && WG_B_LBO % 128 == 0 && WG_STAGE % 128 == 0, "operand tiles stay 128-byte aligned");
 static_assert(3 * WG_N <= WG_TMEM_COLS && WG_N % 16 == 0 && WG_N <= 256, "three accumulators of N columns");
 static_assert(WG_SMEM <= 227 * 1024, "shared memory");
+static_assert(WG_A_ITEMS == 2 * (WG_PRODUCERS / 32), "the bias-gradient partial sums assume two A items per producer warp");
 static_assert(64 * WG_EPI_PITCH * 4 <= 2 * WG_STAGE, "the epilogue tile reuses the stage buffers");
 
 struct WgGeo {
@@ -77,7 +78,7 @@ struct WgGeo {
 
 __global__ void __launch_bounds__(WG_PRODUCERS + 32, 1)
 conv3x3_wgrad_tc_kernel(View<const float> x, View<const float> go, float* __restrict__ dw, int64_t s_co, int64_t s_ci,
-                        int64_t s_ky, int64_t s_kx, WgGeo g) {
+                        int64_t s_ky, int64_t s_kx, float* __restrict__ dbias, WgGeo g) {
     extern __shared__ __align__(128) unsigned char wg_smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(wg_smem + 2 * WG_STAGE);    // full[0,1] empty[2,3]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wg_smem + 2 * WG_STAGE + 32);
@@ -110,6 +111,11 @@ conv3x3_wgrad_tc_kernel(View<const float> x, View<const float> go, float* __rest
         // instruction covers 8 rows x 4 consecutive pixels.  Every slot is rewritten every stage (zeros where
         // the channel, the image row or the pixel does not exist), so nothing relies on an initial fill.
         const int r8 = lane & 7, jq = lane >> 3;
+        // bias gradient = sum of grad_out over (b, y, x): the CTAs of input-channel tile 0 see every grad_out
+        // element of their 128 output channels exactly once while staging A, so they add them up on the way
+        // (items 0..15 are the A rows; a warp owns items warp and warp + 8, i.e. i = 0, 1)
+        const bool do_bias = dbias != nullptr && cit == 0;
+        float bsum[2] = {0.f, 0.f};
         for (int k = 0; k < nst; ++k) {
             const int buf = k & 1;
             if (k >= 2) mbar_wait(&bars[2 + buf], ((k >> 1) - 1) & 1);      // MMAs of stage k-2 done
@@ -146,6 +152,8 @@ conv3x3_wgrad_tc_kernel(View<const float> x, View<const float> go, float* __rest
                         v[i][q][m] = ok ? __ldg(rowp + (int64_t)p * sw) : 0.f;
                     }
                 }
+                if (i < 2 && do_bias)                                        // A item (zeros where the row does not exist)
+                    bsum[i] += (v[i][0][0] + v[i][0][1]) + (v[i][0][2] + v[i][0][3]) + (v[i][1][0] + v[i][1][1]) + (v[i][1][2] + v[i][1][3]);
             }
 #pragma unroll
             for (int i = 0; i < WG_ITEMS_PER_WARP; ++i) {
@@ -163,6 +171,16 @@ conv3x3_wgrad_tc_kernel(View<const float> x, View<const float> go, float* __rest
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // my stores -> visible to the tensor core
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[buf])) : "memory");
+        }
+        if (do_bias) {                                                       // warp-uniform
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                float t = bsum[i];
+                t += __shfl_xor_sync(0xffffffffu, t, 8);                     // the four chunk phases jq of a row
+                t += __shfl_xor_sync(0xffffffffu, t, 16);
+                const int co = cot * WG_MT + (warp + i * (WG_PRODUCERS / 32)) * 8 + r8;
+                if (jq == 0 && co < g.cout) red_add(dbias + co, t);
+            }
         }
     } else if (lane == 0) {
         // ================= issuer =================
@@ -259,7 +277,9 @@ conv3x3_wgrad_tc_kernel(View<const float> x, View<const float> go, float* __rest
 
 // grad_weight (Cout,Cin,3,3) += d/dw of conv2d(x, w, stride 1, padding 1) for grad_out; the caller zero-fills
 // grad_weight (partial sums of the K splits arrive as REDs).  x (B,Cin,H,W), grad_out (B,Cout,H,W), W % 32 == 0.
-extern "C" int ffwm_conv3x3_wgrad(const ffwm_tensor4* x, const ffwm_tensor4* grad_out, const ffwm_tensor4* grad_weight, void* stream) {
+// grad_bias (Cout floats, zero-filled by the caller, may be NULL) += sum of grad_out over (b, y, x).
+extern "C" int ffwm_conv3x3_wgrad(const ffwm_tensor4* x, const ffwm_tensor4* grad_out, const ffwm_tensor4* grad_weight,
+                                  float* grad_bias, void* stream) {
     using namespace ffwm;
     View<const float> xv, gv;
     View<float> wv;
@@ -293,6 +313,6 @@ extern "C" int ffwm_conv3x3_wgrad(const ffwm_tensor4* x, const ffwm_tensor4* gra
     if (e != cudaSuccess) { set_error("conv3x3_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
     dim3 grid((unsigned)tiles, (unsigned)splits);
     conv3x3_wgrad_tc_kernel<<<grid, WG_PRODUCERS + 32, WG_SMEM, static_cast<cudaStream_t>(stream)>>>(
-        xv, gv, wv.p, wv.sb, wv.sc, (int64_t)wv.sh, (int64_t)wv.sw, g);
+        xv, gv, wv.p, wv.sb, wv.sc, (int64_t)wv.sh, (int64_t)wv.sw, grad_bias, g);
     return check_launch("conv3x3_wgrad");
 }

@@ -76,8 +76,14 @@ def conv3x3_forward(x, packed, bias, out, nt=64):
            ctypes.c_void_p(bias.data_ptr() if bias is not None else None), L.t4(out), int(nt))
 
 
-def conv3x3_wgrad(x, grad_out, grad_weight):
-    """grad_weight (Cout,Cin,3,3, zero-filled by the caller) += weight gradient of the 3x3/s1/p1 convolution.
+def conv3x3_wgrad(x, grad_out, grad_weight, grad_bias=None):
+    """grad_weight (Cout,Cin,3,3, zero-filled by the caller) += weight gradient of the 3x3/s1/p1 convolution;
+    grad_bias (Cout, contiguous fp32, zero-filled) += grad_out.sum((0,2,3)) if given.
     EXPERIMENTAL (not yet run on a B200): see csrc/conv3x3_wgrad_tc.cu."""
-    dev = L.require_cuda(x, grad_out, grad_weight)
-    L.call("ffwm_conv3x3_wgrad", dev, L.t4(x), L.t4(grad_out), L.t4(grad_weight))
+    import ctypes
+    dev = L.require_cuda(x, grad_out, grad_weight, grad_bias)
+    if grad_bias is not None and not (grad_bias.is_contiguous() and grad_bias.numel() == grad_out.size(1)
+                                      and grad_bias.dtype == grad_out.dtype):
+        raise ValueError("conv3x3_wgrad: grad_bias must be a contiguous fp32 tensor of Cout elements")
+    L.call("ffwm_conv3x3_wgrad", dev, L.t4(x), L.t4(grad_out), L.t4(grad_weight),
+           ctypes.c_void_p(grad_bias.data_ptr() if grad_bias is not None else None))

@@ -148,9 +148,11 @@ int ffwm_conv3x3_forward_nt(const ffwm_tensor4* x, const float* packed, const fl
  * nn.Conv2d(Cin, Cout, 3, 1, 1), models/base_networks.py:218-222,235-246), tcgen05, 3xTF32:
  *   grad_weight (Cout,Cin,3,3) += sum_{b,y,x} grad_out[b,co,y,x] * x[b,ci,y+ky-1,x+kx-1]   (zero padding)
  * grad_weight accumulates (zero-fill it: the K splits arrive as fp32 REDs); x (B,Cin,H,W), grad_out (B,Cout,H,W),
- * W % 32 == 0, any strides.  EXPERIMENTAL: compiled and checked by a CPU emulation of its indexing, not yet run on
+ * W % 32 == 0, any strides.  grad_bias (Cout floats, zero-filled, or NULL) += sum_{b,y,x} grad_out[b,co,y,x] — the
+ * bias gradient falls out of staging grad_out and replaces a separate reduction.  EXPERIMENTAL: compiled and checked by a CPU emulation of its indexing, not yet run on
  * a B200 (written after the round-1 GPU budget was spent) — callers opt in with FFWM_WGRAD_TC=1. */
-int ffwm_conv3x3_wgrad(const ffwm_tensor4* x, const ffwm_tensor4* grad_out, const ffwm_tensor4* grad_weight, void* stream);
+int ffwm_conv3x3_wgrad(const ffwm_tensor4* x, const ffwm_tensor4* grad_out, const ffwm_tensor4* grad_weight,
+                       float* grad_bias, void* stream);
 
 #ifdef __cplusplus
 }

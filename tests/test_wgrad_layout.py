@@ -63,6 +63,7 @@ def emulate(x, go, splits_hint):
     per = min(-(-stages_total // splits), c["WG_MAX_STAGES"])
     splits = -(-stages_total // per)
     dw = np.zeros((cout, cin, 3, 3), np.float64)
+    dbias = np.zeros(cout, np.float64)
     for tile in range(tiles):
         cot, cit = divmod(tile, n_ci_tiles)
         for sp in range(splits):
@@ -102,6 +103,8 @@ def emulate(x, go, splits_hint):
                                     p = jbase + cc + m * S
                                     if rok and 0 <= p < W:
                                         v[m] = src[p]
+                                if is_a and cit == 0 and rok:                  # fused bias gradient: A items of ci tile 0
+                                    dbias[co] += float(v.astype(np.float64).sum())
                                 hi, lo = split(v)
                                 d = (base + row * 16 + cc * lbo) // 4
                                 smem[d:d + 4] = hi
@@ -142,7 +145,7 @@ def emulate(x, go, splits_hint):
                         ky, kx = divmod(t9, 3)
                         assert not np.isnan(tile[r * pitch + e])
                         dw[co, cit * NCI + ci_l, ky, kx] += tile[r * pitch + e]
-    return dw
+    return dw, dbias
 
 
 @pytest.mark.parametrize("b,cin,cout,h,w,splits_hint", [(2, 5, 3, 3, 32, 148), (1, 50, 130, 2, 64, 7), (1, 3, 8, 1, 32, 1),
@@ -153,10 +156,11 @@ def test_wgrad_plan_matches_torch(b, cin, cout, h, w, splits_hint):
     go = torch.randn(b, cout, h, w, generator=g)
     wt = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, requires_grad=True)
     F.conv2d(x.double(), wt, None, padding=1).backward(go.double())
-    got = emulate(x.numpy(), go.numpy(), splits_hint)
+    got, got_bias = emulate(x.numpy(), go.numpy(), splits_hint)
     want = wt.grad.numpy()
     err = np.abs(got - want).max() / np.abs(want).max()
     assert err <= 2e-6, err          # only the dropped lo*lo terms (2^-22 relative) separate the two
+    np.testing.assert_allclose(got_bias, go.double().sum((0, 2, 3)).numpy(), rtol=0, atol=1e-9)   # every element exactly once
 
 
 def test_wgrad_constants_fit_the_hardware():

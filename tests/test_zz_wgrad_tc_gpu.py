@@ -34,9 +34,11 @@ def test_conv3x3_wgrad_matches_fp64(b, cin, cout, h, w):
     wt = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, device=DEV, requires_grad=True)
     F.conv2d(xd.double(), wt, None, padding=1).backward(gd.double())
     gw = torch.zeros(cout, cin, 3, 3, device=DEV)
-    ops.conv3x3_wgrad(xd, gd, gw)
+    gbias = torch.zeros(cout, device=DEV)
+    ops.conv3x3_wgrad(xd, gd, gw, gbias)
     torch.cuda.synchronize()
     assert rel(gw, wt.grad) <= 4e-5
+    assert rel(gbias, gd.double().sum((0, 2, 3))) <= 1e-5          # fused bias gradient (plain fp32 adds)
     # accumulates into the caller's buffer
     ops.conv3x3_wgrad(xd, gd, gw)
     assert rel(gw, 2 * wt.grad) <= 4e-5
