@@ -46,6 +46,8 @@ SIGNATURES = {
     "ffwm_conv3x3_packed_floats_nt": [_I, _I, _I],
     "ffwm_conv3x3_pack_weights_nt": [_T4P, _I, _VP, ctypes.c_int64, _I, _VP],
     "ffwm_conv3x3_forward_nt": [_T4P, _VP, _VP, _T4P, _I, _VP],
+    "ffwm_mfm_forward": [_VP, _VP, ctypes.c_int64, ctypes.c_int64, _VP],
+    "ffwm_mfm_backward": [_VP, _VP, _VP, ctypes.c_int64, ctypes.c_int64, _VP],
 }
 
 _lib = None

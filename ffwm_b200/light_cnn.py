@@ -8,11 +8,36 @@ max-feature-map (MFM) activations, used frozen as the identity-preserving featur
     group / resblock   light_cnn.py:29-54
     network_29layers   light_cnn.py:82-129   returns (logits, fc256, pooled 128x8x8)
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
 from .conv import Conv2d
+
+# experimental, unmeasured (csrc/mfm.cu was written after the round-1 GPU budget was spent): off unless asked for
+FUSED_MFM = os.environ.get("FFWM_FUSED_MFM", "0") == "1"
+
+
+class MFMFunction(torch.autograd.Function):
+    """max over the two channel halves as one kernel per direction (PyTorch: 1 forward + 8 backward kernels)."""
+
+    @staticmethod
+    def forward(ctx, y):
+        y = y.contiguous()
+        out = y.new_empty((y.size(0), y.size(1) // 2) + tuple(y.shape[2:]))
+        ops.mfm_forward(y, out)
+        ctx.save_for_backward(y)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (y,) = ctx.saved_tensors
+        gy = torch.empty_like(y)
+        ops.mfm_backward(y, grad_out.contiguous(), gy)
+        return gy
 
 
 class mfm(nn.Module):
@@ -25,7 +50,10 @@ class mfm(nn.Module):
             self.filter = nn.Linear(in_channels, 2 * out_channels)
 
     def forward(self, x):
-        a, b = self.filter(x).split(self.out_channels, 1)
+        y = self.filter(x)
+        if FUSED_MFM and y.is_cuda and y.dtype == torch.float32:
+            return MFMFunction.apply(y)
+        a, b = y.split(self.out_channels, 1)
         return torch.max(a, b)
 
 

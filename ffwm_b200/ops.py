@@ -87,3 +87,28 @@ def conv3x3_wgrad(x, grad_out, grad_weight, grad_bias=None):
         raise ValueError("conv3x3_wgrad: grad_bias must be a contiguous fp32 tensor of Cout elements")
     L.call("ffwm_conv3x3_wgrad", dev, L.t4(x), L.t4(grad_out), L.t4(grad_weight),
            ctypes.c_void_p(grad_bias.data_ptr() if grad_bias is not None else None))
+
+
+def mfm_forward(x, out):
+    """out (N,C,...) = elementwise max of the two channel halves of x (N,2C,...); contiguous fp32 CUDA tensors.
+    EXPERIMENTAL (not yet run on a B200): see csrc/mfm.cu."""
+    import ctypes
+    dev = L.require_cuda(x, out)
+    n, chw = x.size(0), out.numel() // max(x.size(0), 1)
+    if not (x.is_contiguous() and out.is_contiguous() and x.dtype == out.dtype and L.dtype_code(x) == L.FFWM_F32
+            and x.numel() == 2 * out.numel()):
+        raise ValueError("mfm_forward: contiguous fp32 x (N,2C,...) and out (N,C,...) expected")
+    L.call("ffwm_mfm_forward", dev, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+           ctypes.c_int64(n), ctypes.c_int64(chw))
+
+
+def mfm_backward(x, grad_out, grad_x):
+    import ctypes
+    dev = L.require_cuda(x, grad_out, grad_x)
+    n, chw = x.size(0), grad_out.numel() // max(x.size(0), 1)
+    if not (x.is_contiguous() and grad_out.is_contiguous() and grad_x.is_contiguous() and L.dtype_code(x) == L.FFWM_F32
+            and grad_out.dtype == x.dtype and grad_x.dtype == x.dtype and x.numel() == 2 * grad_out.numel()
+            and grad_x.numel() == x.numel()):
+        raise ValueError("mfm_backward: contiguous fp32 x / grad_x (N,2C,...) and grad_out (N,C,...) expected")
+    L.call("ffwm_mfm_backward", dev, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(grad_out.data_ptr()),
+           ctypes.c_void_p(grad_x.data_ptr()), ctypes.c_int64(n), ctypes.c_int64(chw))

@@ -154,6 +154,13 @@ int ffwm_conv3x3_forward_nt(const ffwm_tensor4* x, const float* packed, const fl
 int ffwm_conv3x3_wgrad(const ffwm_tensor4* x, const ffwm_tensor4* grad_out, const ffwm_tensor4* grad_weight,
                        float* grad_bias, void* stream);
 
+/* ---- LightCNN max-feature-map activation (lightcnn/light_cnn.py:13-26: `torch.max(out[0], out[1])` over the two
+ * channel halves of the preceding conv / linear output) and its gradient, one streaming kernel each; ATen's
+ * semantics incl. NaN propagation and tie splitting.  x (n, 2*chw) and out (n, chw) contiguous fp32; chw = C*H*W.
+ * EXPERIMENTAL: not yet run on a B200 (written after the round-1 GPU budget was spent); opt-in FFWM_FUSED_MFM=1. */
+int ffwm_mfm_forward(const float* x, float* out, int64_t n, int64_t chw, void* stream);
+int ffwm_mfm_backward(const float* x, const float* grad_out, float* grad_x, int64_t n, int64_t chw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
