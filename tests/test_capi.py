@@ -64,6 +64,42 @@ def test_argument_validation_without_gpu():
     assert rc == 0
 
 
+def test_conv_entry_points_validate_without_gpu():
+    """The tensor-core convolution entry points reject bad tiles / shapes before any launch."""
+    from ffwm_b200 import _lib
+    lib = _lib.lib()
+    null = ctypes.c_void_p(0)
+    assert lib.ffwm_conv3x3_packed_floats_nt(195, 195, 64) == lib.ffwm_conv3x3_packed_floats(195, 195) == 4 * 25 * 9216
+    assert lib.ffwm_conv3x3_packed_floats_nt(195, 195, 128) == 2 * 25 * 18432
+    assert lib.ffwm_conv3x3_packed_floats_nt(195, 195, 96) == 0 and lib.ffwm_conv3x3_packed_floats_nt(0, 8, 64) == 0
+    x64, o64 = torch.zeros(1, 8, 4, 64), torch.zeros(1, 128, 4, 64)
+    fake = ctypes.c_void_p(16)                                      # non-null "packed" pointer, never dereferenced
+    rc = lib.ffwm_conv3x3_forward_nt(_lib.t4(x64), fake, null, _lib.t4(o64), 128, null)
+    assert rc == -3 and b"nt must be 64" in lib.ffwm_last_error()  # the 128-channel tile exists for W = 128 only
+    rc = lib.ffwm_conv3x3_forward_nt(_lib.t4(x64), fake, null, _lib.t4(o64), 32, null)
+    assert rc == -3
+    rc = lib.ffwm_conv3x3_forward_nt(_lib.t4(torch.zeros(1, 8, 4, 48)), fake, null, _lib.t4(torch.zeros(1, 8, 4, 48)), 64, null)
+    assert rc == -2                                                 # width not in {128, 64, 32, 16}
+    w = torch.zeros(16, 8, 3, 3)
+    rc = lib.ffwm_conv3x3_pack_weights_nt(_lib.t4(w), 0, fake, ctypes.c_int64(10), 64, null)
+    assert rc == -2 and b"too small" in lib.ffwm_last_error()
+    rc = lib.ffwm_conv3x3_pack_weights_nt(_lib.t4(w), 0, fake, ctypes.c_int64(1 << 20), 100, null)
+    assert rc == -3
+    # weight gradient: W % 32, matching shapes, (Cout,Cin,3,3) target
+    x, go = torch.zeros(1, 8, 4, 48), torch.zeros(1, 16, 4, 48)
+    rc = lib.ffwm_conv3x3_wgrad(_lib.t4(x), _lib.t4(go), _lib.t4(w), null, null)
+    assert rc == -2 and b"W % 32" in lib.ffwm_last_error()
+    x, go = torch.zeros(1, 8, 4, 64), torch.zeros(1, 16, 4, 64)
+    rc = lib.ffwm_conv3x3_wgrad(_lib.t4(x), _lib.t4(go), _lib.t4(torch.zeros(16, 9, 3, 3)), null, null)
+    assert rc == -2
+    e = torch.zeros(0, 8, 4, 64)
+    assert lib.ffwm_conv3x3_wgrad(_lib.t4(e), _lib.t4(torch.zeros(0, 16, 4, 64)), _lib.t4(w), null, null) == 0
+    # max-feature-map: sizes and pointers
+    assert lib.ffwm_mfm_forward(null, null, ctypes.c_int64(0), ctypes.c_int64(5), null) == 0
+    assert lib.ffwm_mfm_forward(null, null, ctypes.c_int64(2), ctypes.c_int64(5), null) == -1
+    assert lib.ffwm_mfm_backward(null, null, null, ctypes.c_int64(-1), ctypes.c_int64(5), null) == -2
+
+
 def test_python_surface_mirrors_reference_errors():
     from ffwm_b200 import external_function as E
     with pytest.raises(NotImplementedError):                       # external_function.py:37-38
