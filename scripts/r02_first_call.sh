@@ -36,6 +36,8 @@ for f in ("r02_bench_cudnn_wgrad", "r02_bench_tc_wgrad", "r02_bench_nt128", "r02
     except Exception as e:
         print(f, "unreadable:", e)
 PY
+# BASELINE config 2 (FlowNetF forward+backward, batch 6) was never recorded in round 1
+timeout 600 python bench.py --workload flownet --no-cpu-baseline > gpurun_out/r02_bench_flownet.json 2> gpurun_out/r02_bench_f.err; echo "bench (flownet, cfg2) rc=$?"; cat gpurun_out/r02_bench_flownet.json
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv3x3_wgrad -s 2 -c 3 -f -o gpurun_out/prof_r02_wgrad \
     python -m benchmarks.conv --wgrad --out gpurun_out/conv_ncu_tmp.json > gpurun_out/r02_ncu_wgrad.log 2>&1; echo "ncu wgrad rc=$?"
 python scripts/ncu_summary.py gpurun_out/prof_r02_wgrad.ncu-rep r02_wgrad gpurun_out > /dev/null 2>&1
