@@ -108,8 +108,47 @@ class TrainStepWorkload:
                 "note": "algorithmic 447.0 GFLOP/image (conv+matmul fwd+bwd; the reference's unused LightCNN weight gradients skipped) / measured step time; "
                         "peak is the measured sustained bf16 tensor rate, the math here is %s" % ("tf32" if self.tf32 else "fp32")}
 
+    # the step's dominant hand-written kernel (conv3x3_tc: 55 % of the step's convolution FLOPs), on its three
+    # heaviest layer shapes, batch = the step's batch
+    KERNEL_SHAPES = (("conv3x3_tc fwd 195->195 @128x128 (netG dres2)", 195, 195, 128),
+                     ("conv3x3_tc fwd 128->128 @128x128 (netG att2)", 128, 128, 128),
+                     ("conv3x3_tc fwd 384->384 @32x32 (netG dres0)", 384, 384, 32))
+
     def kernel_table(self, pk):
-        return None
+        """Those kernels timed alone, live, with CUDA events on the launching stream (operands 100+ MB at 128x128:
+        larger than L2 together with the output).  `TFLOP/s` counts the algorithmic 2*B*H*W*Cin*Cout*9 once;
+        the kernel issues three TF32 MMAs per product (3xTF32 split), `tensor_issued_TFLOP/s`.  Never fatal:
+        a failure here is reported in the table instead of losing the bench line."""
+        try:
+            from ffwm_b200 import ops
+            rows = {}
+            for name, cin, cout, r in self.KERNEL_SHAPES:
+                x = torch.randn(BATCH, cin, r, r, device=self.dev)
+                w = torch.randn(cout, cin, 3, 3, device=self.dev) / (cin * 9) ** 0.5
+                out = torch.empty(BATCH, cout, r, r, device=self.dev)
+                packed = ops.conv3x3_pack_weights(w)
+                for _ in range(3):
+                    ops.conv3x3_forward(x, packed, None, out)
+                iters = 10
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(iters):
+                    ops.conv3x3_forward(x, packed, None, out)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / iters
+                flop = 2.0 * BATCH * r * r * cin * cout * 9
+                tf = flop / (ms * 1e-3) / 1e12
+                rows[name] = {"ms": round(ms, 4), "GFLOP": round(flop / 1e9, 2), "TFLOP/s": round(tf, 1),
+                              "tensor_issued_TFLOP/s": round(3 * tf, 1),
+                              "frac_bf16_peak_issued": round(3 * tf / pk["bf16_tflops"], 4) if pk.get("bf16_tflops") else None}
+                del x, w, out, packed
+            rows["note"] = ("timed alone after the step (burst clocks); peak = measured dense bf16 burst rate, the kernel's math "
+                            "is TF32 (half the bf16 rate on paper) issued three times per product for fp32-level accuracy")
+            return rows
+        except Exception as e:          # noqa: BLE001 - the bench line must survive
+            return {"error": repr(e)}
 
     # ------------------------------------------------------------------ CPU arm
     CPU_BATCH = 2
