@@ -72,3 +72,55 @@ def test_single_process_is_a_noop():
     p.grad = torch.full((3,), 2.0)
     GradAverager([p], One()).average()
     assert torch.equal(p.grad, torch.full((3,), 2.0))
+
+
+def _trainer_worker(rank, world, port, q):
+    """One data-parallel FFWM train step per rank on the CPU (the warps served by torch ops through the oracle's
+    cpu_ops shim — test infrastructure), different data and different initial weights per rank."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(max(1, (os.cpu_count() or 2) // world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import train_cpu
+        from ffwm_b200.parallel import Distributed
+        from ffwm_b200.train_step import FFWMTrainer
+        torch.manual_seed(100 + rank)                     # replicas start different: the broadcast must fix that
+        with train_cpu.cpu_ops():
+            tr = FFWMTrainer("cpu", distributed=Distributed())
+            g = torch.Generator().manual_seed(7 + rank)   # per-rank data
+            batch = {'img_S': torch.rand(1, 3, 128, 128, generator=g), 'img_F': torch.rand(1, 3, 128, 128, generator=g),
+                     'mask_F': (torch.rand(1, 1, 128, 128, generator=g) > 0.3).float(),
+                     'mask_S': (torch.rand(1, 1, 128, 128, generator=g) > 0.3).float(),
+                     'lm_F': torch.randint(20, 108, (1, 1000, 2), generator=g), 'titers': 30000, 'epoch': 0}
+            tr.set_input(batch)
+            tr.optimize_parameters()
+        sums = {}
+        for name in ("netG", "netD", "flowNetF", "flowNetB"):
+            net = getattr(tr, name)
+            sums[name] = float(sum(p.detach().double().sum() for p in net.parameters()))
+            sums[name + "_abs"] = float(sum(p.detach().double().abs().sum() for p in net.parameters()))
+            sums[name + "_grad"] = float(sum(p.grad.double().abs().sum() for p in net.parameters() if p.grad is not None))
+        unused = [n for n, p in tr.flowNetF.named_parameters() if p.grad is None]
+        q.put((rank, sums, float(tr.loss_G), float(tr.loss_D), unused))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_train_step_world2_keeps_replicas_identical():
+    """SURVEY 8e on the CPU: after one step on different per-rank batches the two replicas hold bit-identical
+    weights and gradients (broadcast at start, averaged gradients, same Adam update), although their losses differ."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_trainer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=600) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    (_, s0, lg0, ld0, un0), (_, s1, lg1, ld1, un1) = out
+    assert s0 == s1, "replicas diverged: %r vs %r" % (s0, s1)
+    assert lg0 != lg1 and ld0 != ld1                      # the ranks really saw different data
+    assert all(v > 0 for k, v in s0.items() if k.endswith("_grad"))
+    assert un0 == un1 and any("inter_conv_occ" in n for n in un0)    # never-used parameters are skipped on both ranks
