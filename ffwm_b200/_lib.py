@@ -48,6 +48,8 @@ SIGNATURES = {
     "ffwm_conv3x3_forward_nt": [_T4P, _VP, _VP, _T4P, _I, _VP],
     "ffwm_mfm_forward": [_VP, _VP, ctypes.c_int64, ctypes.c_int64, _VP],
     "ffwm_mfm_backward": [_VP, _VP, _VP, ctypes.c_int64, ctypes.c_int64, _VP],
+    "ffwm_guided_filter_forward": [_VP, _VP, _VP, _VP, _VP, ctypes.c_int64, _I, _I, _I, ctypes.c_float, _VP],
+    "ffwm_guided_filter_backward": [_VP, _VP, _VP, _VP, _VP, _VP, ctypes.c_int64, _I, _I, _I, _VP],
 }
 
 _lib = None

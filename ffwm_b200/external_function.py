@@ -16,12 +16,17 @@ Differences that are deliberate and visible:
   * `Resample2d` builds its sigma plane on the input's device (the reference
     keeps it on the CPU and would fail on GPU input).
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 from torch.autograd import Function
 
 from . import ops
+
+# experimental, unmeasured (csrc/guided_filter.cu was written after the round-1 GPU budget was spent): off unless asked for
+FUSED_GF = os.environ.get("FFWM_FUSED_GF", "0") == "1"
 
 
 def _cuda_only(t):
@@ -210,6 +215,29 @@ class BoxFilter(nn.Module):
         return _window_sum(_window_sum(x, self.r, 2), self.r, 3)
 
 
+class GuidedFilterFunction(Function):
+    """GuidedFilter.forward (models/external_function.py:239-277) as four kernels per direction
+    (csrc/guided_filter.cu); gradient with respect to x only (y is data for every caller in the reference)."""
+
+    @staticmethod
+    def forward(ctx, x, y, r, eps):
+        _cuda_only(x)
+        x, y = x.contiguous(), y.contiguous()
+        q = torch.empty_like(x)
+        save = x.new_empty((5,) + tuple(x.shape))
+        ops.guided_filter_forward(x, y, q, save, x.new_empty((5,) + tuple(x.shape)), r, eps)
+        ctx.save_for_backward(x, y, save)
+        ctx.r = r
+        return q
+
+    @staticmethod
+    def backward(ctx, grad_q):
+        x, y, save = ctx.saved_tensors
+        grad_x = torch.empty_like(x)
+        ops.guided_filter_backward(x, y, grad_q.contiguous(), save, grad_x, x.new_empty((6,) + tuple(x.shape)), ctx.r)
+        return grad_x, None, None, None
+
+
 class GuidedFilter(nn.Module):
     """models/external_function.py:239-277: q = mean(A) * x + mean(b)."""
 
@@ -227,6 +255,9 @@ class GuidedFilter(nn.Module):
         assert h_x == h_y and w_x == w_y
         assert h_x > 2 * self.r + 1 and w_x > 2 * self.r + 1
 
+        if (FUSED_GF and x.is_cuda and x.dtype == torch.float32 and y.dtype == torch.float32 and c_x == c_y
+                and not y.requires_grad):
+            return GuidedFilterFunction.apply(x, y, self.r, self.eps)
         count = self.boxfilter(x.new_ones((1, 1, h_x, w_x)))
         mean_x = self.boxfilter(x) / count
         mean_y = self.boxfilter(y) / count

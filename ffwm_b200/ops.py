@@ -112,3 +112,34 @@ def mfm_backward(x, grad_out, grad_x):
         raise ValueError("mfm_backward: contiguous fp32 x / grad_x (N,2C,...) and grad_out (N,C,...) expected")
     L.call("ffwm_mfm_backward", dev, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(grad_out.data_ptr()),
            ctypes.c_void_p(grad_x.data_ptr()), ctypes.c_int64(n), ctypes.c_int64(chw))
+
+
+def _gf_ptrs(*tensors):
+    import ctypes
+    for t in tensors:
+        if not (t.is_contiguous() and L.dtype_code(t) == L.FFWM_F32):
+            raise ValueError("guided_filter: contiguous fp32 CUDA tensors expected")
+    return [ctypes.c_void_p(t.data_ptr()) for t in tensors]
+
+
+def guided_filter_forward(x, y, q, save, scratch, r, eps):
+    """q = GuidedFilter(r, eps)(x, y) for (B,C,H,W) x, y; save (5,B,C,H,W), scratch (5,B,C,H,W).
+    EXPERIMENTAL (not yet run on a B200): see csrc/guided_filter.cu."""
+    import ctypes
+    dev = L.require_cuda(x, y, q, save, scratch)
+    b, c, h, w = x.shape
+    if y.shape != x.shape or q.shape != x.shape or save.numel() < 5 * x.numel() or scratch.numel() < 5 * x.numel():
+        raise ValueError("guided_filter_forward: shape mismatch")
+    L.call("ffwm_guided_filter_forward", dev, *_gf_ptrs(x, y, q, save, scratch), ctypes.c_int64(b * c), int(h), int(w),
+           int(r), ctypes.c_float(eps))
+
+
+def guided_filter_backward(x, y, grad_q, save, grad_x, scratch, r):
+    import ctypes
+    dev = L.require_cuda(x, y, grad_q, save, grad_x, scratch)
+    b, c, h, w = x.shape
+    if (y.shape != x.shape or grad_q.shape != x.shape or grad_x.shape != x.shape or save.numel() < 5 * x.numel()
+            or scratch.numel() < 6 * x.numel()):
+        raise ValueError("guided_filter_backward: shape mismatch")
+    L.call("ffwm_guided_filter_backward", dev, *_gf_ptrs(x, y, grad_q, save, grad_x, scratch), ctypes.c_int64(b * c),
+           int(h), int(w), int(r))

@@ -161,6 +161,17 @@ int ffwm_conv3x3_wgrad(const ffwm_tensor4* x, const ffwm_tensor4* grad_out, cons
 int ffwm_mfm_forward(const float* x, float* out, int64_t n, int64_t chw, void* stream);
 int ffwm_mfm_backward(const float* x, const float* grad_out, float* grad_x, int64_t n, int64_t chw, void* stream);
 
+/* ---- Guided filter (models/external_function.py:164-195 BoxFilter, :239-277 GuidedFilter.forward) and its gradient
+ * with respect to x, four kernels per direction; box sums are truncated window sums taken directly (separable).
+ * x, y, q, grad_q, grad_x: (planes = B*C, H, W) contiguous fp32, H and W > 2r+1 (the reference's assert).
+ * save: 5*planes*H*W floats written by forward, read by backward; scratch: 5 (forward) / 6 (backward) * planes*H*W.
+ * EXPERIMENTAL: arithmetic checked on the CPU (float64, against autograd of the reference formula), kernels not yet
+ * run on a B200 (written after the round-1 GPU budget was spent); opt-in FFWM_FUSED_GF=1. */
+int ffwm_guided_filter_forward(const float* x, const float* y, float* q, float* save, float* scratch,
+                               int64_t planes, int h, int w, int r, float eps, void* stream);
+int ffwm_guided_filter_backward(const float* x, const float* y, const float* grad_q, const float* save,
+                                float* grad_x, float* scratch, int64_t planes, int h, int w, int r, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

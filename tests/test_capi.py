@@ -98,6 +98,12 @@ def test_conv_entry_points_validate_without_gpu():
     assert lib.ffwm_mfm_forward(null, null, ctypes.c_int64(0), ctypes.c_int64(5), null) == 0
     assert lib.ffwm_mfm_forward(null, null, ctypes.c_int64(2), ctypes.c_int64(5), null) == -1
     assert lib.ffwm_mfm_backward(null, null, null, ctypes.c_int64(-1), ctypes.c_int64(5), null) == -2
+    # guided filter: the reference's H, W > 2r+1 assert, null pointers, empty input
+    f = ctypes.c_float(1e-8)
+    assert lib.ffwm_guided_filter_forward(fake, fake, fake, fake, fake, ctypes.c_int64(3), 16, 16, 8, f, null) == -3
+    assert lib.ffwm_guided_filter_forward(null, fake, fake, fake, fake, ctypes.c_int64(3), 32, 32, 8, f, null) == -1
+    assert lib.ffwm_guided_filter_forward(null, null, null, null, null, ctypes.c_int64(0), 32, 32, 8, f, null) == 0
+    assert lib.ffwm_guided_filter_backward(fake, fake, fake, fake, fake, null, ctypes.c_int64(3), 32, 32, 8, null) == -1
 
 
 def test_python_surface_mirrors_reference_errors():
