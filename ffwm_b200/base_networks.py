@@ -19,6 +19,7 @@ Dense convolutions go through `ffwm_b200.conv` (see DESIGN.md for which shapes
 run on the hand-written tensor-core path and which stay on cuDNN).
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -27,8 +28,12 @@ from torch.nn.utils import spectral_norm
 
 from . import external_function as EF
 from .conv import Conv2d
+from .spectral import batch_spectral_norm
 
 LRELU_SLOPE = 0.2
+# spectral norm of a whole network in one batched update per weight shape (ffwm_b200/spectral.py) instead of one
+# power iteration per layer; CPU-verified, not yet measured on a B200: off unless asked for
+BATCHED_SN = os.environ.get("FFWM_BATCHED_SN", "0") == "1"
 
 
 def initialize_msra(modules):
@@ -238,6 +243,8 @@ class FFWM(nn.Module):
             setattr(self, "att%d" % i, nn.Sequential(ConvBlock(w, w, 3, 1, 1, sn=sn),
                                                      ResidualBlock(w, w, activ='sigmoid', sn=sn)))
         self.warpNet = WarpNet()
+        if sn and BATCHED_SN:
+            batch_spectral_norm(self)
 
     def forward(self, x, flow=None, return_att=False):
         fencs = [self.e0(x)]
@@ -275,6 +282,8 @@ class MSDiscriminator(nn.Module):
         self.max_n_scales = min(int(math.ceil(math.log(smallest * 1.0 / self.min_size) / math.log(scale_factor))),
                                 max_n_scales)
         self.nets = nn.ModuleList([self.make_net() for _ in range(self.max_n_scales)])
+        if BATCHED_SN:
+            batch_spectral_norm(self)
 
     def make_net(self):
         c = self.base_channels
