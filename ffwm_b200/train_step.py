@@ -15,6 +15,7 @@ the optimiser step — discriminator gradients after `backward_D`, generator + b
 `backward_G`.  The reference has no multi-GPU path at all.
 """
 import itertools
+import os
 
 import torch
 import torch.nn.functional as F
@@ -22,6 +23,12 @@ import torch.nn.functional as F
 from . import base_networks, external_function, losses
 from .light_cnn import LightCNN_29Layers
 from .parallel import GradAverager
+
+
+# The perceptual losses of one step through 6 VGG19 passes instead of 14 and the identity losses through 2 LightCNN
+# passes instead of 4 (losses.PerceptualLoss.many / IdentityLoss.many: same samples, bigger batches): CPU-verified
+# against the reference goldens, not yet measured on a B200 (written after the round-1 GPU budget was spent).
+BATCHED_VGG = os.environ.get("FFWM_BATCHED_VGG", "0") == "1"
 
 
 def set_requires_grad(nets, flag):
@@ -131,14 +138,21 @@ class FFWMTrainer:
             gf64 = self.gf64(self.fake_F64, img_F64)
             gf32 = self.gf32(self.fake_F32, img_F32)
         scales = ((gf128, img_F, mask_F, 1), (gf64, img_F64, mask_F64, 1), (gf32, img_F32, mask_F32, 1.5))
-        self.loss_prc = sum(w * self.criterionPerceptual(g * m, t * m) for g, t, m, w in scales)
+        if BATCHED_VGG:      # one VGG pass per resolution over the generated and one over the target images
+            prc = self.criterionPerceptual.many([(g * m, t * m) for g, t, m, _ in scales] + list(self.parts))
+            self.loss_prc = sum(w * l for (_, _, _, w), l in zip(scales, prc))
+        else:
+            self.loss_prc = sum(w * self.criterionPerceptual(g * m, t * m) for g, t, m, w in scales)
         self.loss_l1 = sum(w * self.criterionL1(g * m, t * m) for g, t, m, w in scales)
         self.loss_illu = self.criterionIllu([self.flow_B128, self.flow_B64, self.flow_B32],
                                             [self.fake_F128, self.fake_F64, self.fake_F32], self.img_S, self.mask_S)
-        self.loss_iden = self.criterionIden(self.fake_F128, img_F)
-        self.loss_iden_gf = self.criterionIden(gf128, img_F)
+        if BATCHED_VGG:      # likewise the two LightCNN identity losses: 2 passes instead of 4
+            self.loss_iden, self.loss_iden_gf = self.criterionIden.many([(self.fake_F128, img_F), (gf128, img_F)])
+        else:
+            self.loss_iden = self.criterionIden(self.fake_F128, img_F)
+            self.loss_iden_gf = self.criterionIden(gf128, img_F)
         self.loss_adv = self.criterionGAN(self.netD(self.img_GF128 * mask_F), True, for_dis=False)
-        (eyel, eyer, nose, mouth) = [self.criterionPerceptual(g, t) for g, t in self.parts]
+        (eyel, eyer, nose, mouth) = prc[3:] if BATCHED_VGG else [self.criterionPerceptual(g, t) for g, t in self.parts]
         self.loss_fc = 2 * (eyel + eyer) + mouth + nose
 
         self.loss_l1 = self.loss_l1 * 5

@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of round 2: validate and measure what was written blind at the end of round 1
 # (the tcgen05 weight-gradient kernel, the 128-channel CTA tile of the forward kernel, the fused MFM and guided-filter kernels), without touching the established suite's context.
-#   /usr/local/graft/bin/gpurun --timeout 1800 -- 'bash scripts/r02_first_call.sh'     (about 18 minutes of box time)
+#   /usr/local/graft/bin/gpurun --timeout 1800 -- 'bash scripts/r02_first_call.sh'     (about 22 minutes of box time)
 # Each step runs in its own process under its own timeout: a trap in the unproven kernel ends that step only.
 mkdir -p gpurun_out
 FFWM_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_zz_wgrad_tc_gpu.py -x -q > gpurun_out/r02_wgrad_pytest.log 2>&1; echo "wgrad pytest rc=$?"
@@ -33,10 +33,14 @@ FFWM_FUSED_GF=1 timeout 600 python bench.py --no-cpu-baseline --no-warp > gpurun
 # batched spectral norm is plain torch ops, CPU-verified against the reference goldens: parity on the GPU, then the A/B
 FFWM_BATCHED_SN=1 timeout 600 python -m pytest tests/test_networks.py tests/test_train_step.py -m gpu -x -q > gpurun_out/r02_sn_pytest.log 2>&1; echo "batched SN gpu goldens rc=$?"; tail -3 gpurun_out/r02_sn_pytest.log
 FFWM_BATCHED_SN=1 timeout 600 python bench.py --no-cpu-baseline --no-warp > gpurun_out/r02_bench_sn.json 2> gpurun_out/r02_bench_h.err; echo "bench (batched SN) rc=$?"
-FFWM_WGRAD_TC=1 FFWM_CONV_NT128=1 FFWM_FUSED_MFM=1 FFWM_FUSED_GF=1 FFWM_BATCHED_SN=1 timeout 600 python bench.py --no-cpu-baseline --no-warp > gpurun_out/r02_bench_all.json 2> gpurun_out/r02_bench_e.err; echo "bench (all five) rc=$?"
+# batched VGG19 / LightCNN loss passes (6 + 2 passes instead of 14 + 4): also plain torch, CPU-verified
+FFWM_BATCHED_VGG=1 timeout 600 python -m pytest tests/test_train_step.py -m gpu -x -q > gpurun_out/r02_vgg_pytest.log 2>&1; echo "batched VGG gpu goldens rc=$?"; tail -3 gpurun_out/r02_vgg_pytest.log
+FFWM_BATCHED_VGG=1 timeout 600 python bench.py --no-cpu-baseline --no-warp > gpurun_out/r02_bench_vgg.json 2> gpurun_out/r02_bench_i.err; echo "bench (batched VGG/LightCNN) rc=$?"
+FFWM_BATCHED_SN=1 FFWM_BATCHED_VGG=1 timeout 600 python bench.py --no-cpu-baseline --no-warp > gpurun_out/r02_bench_host.json 2> gpurun_out/r02_bench_j.err; echo "bench (both host-side restructurings) rc=$?"
+FFWM_WGRAD_TC=1 FFWM_CONV_NT128=1 FFWM_FUSED_MFM=1 FFWM_FUSED_GF=1 FFWM_BATCHED_SN=1 FFWM_BATCHED_VGG=1 timeout 600 python bench.py --no-cpu-baseline --no-warp > gpurun_out/r02_bench_all.json 2> gpurun_out/r02_bench_e.err; echo "bench (all six) rc=$?"
 python - <<'PY'
 import json
-for f in ("r02_bench_cudnn_wgrad", "r02_bench_tc_wgrad", "r02_bench_nt128", "r02_bench_mfm", "r02_bench_gf", "r02_bench_sn", "r02_bench_all"):
+for f in ("r02_bench_cudnn_wgrad", "r02_bench_tc_wgrad", "r02_bench_nt128", "r02_bench_mfm", "r02_bench_gf", "r02_bench_sn", "r02_bench_vgg", "r02_bench_host", "r02_bench_all"):
     try:
         d = json.loads(open("gpurun_out/%s.json" % f).read().strip().splitlines()[-1])
         print(f, d["value"], d["unit"], d["ms_per_step"], "ms/step")
