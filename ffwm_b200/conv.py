@@ -43,6 +43,26 @@ def _nt(width, n_out):
     return 128 if (NT128 and width == 128 and n_out > 64) else 64
 
 
+# experimental, unmeasured: keep the packed image of FROZEN weights (VGG19, LightCNN: ~280 of the step's 380 packing
+# launches) instead of re-packing on every call.  A weight qualifies while it is a leaf that does not require grad;
+# the image is tagged with the tensor's version counter and data pointer, so any in-place update (optimizer step,
+# load_state_dict, .data swap) re-packs.  Spectral-normed weights are new tensors on every call and never qualify.
+CACHE_PACKED = os.environ.get("FFWM_CACHE_PACKED", "0") == "1"
+
+
+def _packed(weight, dgrad, nt):
+    if not (CACHE_PACKED and weight.is_leaf and not weight.requires_grad):
+        return ops.conv3x3_pack_weights(weight, dgrad=dgrad, nt=nt)
+    cache = getattr(weight, "_ffwm_packed", None)
+    if cache is None:
+        cache = weight._ffwm_packed = {}
+    tag = (weight._version, weight.data_ptr())
+    hit = cache.get((dgrad, nt))
+    if hit is None or hit[0] != tag:
+        hit = cache[(dgrad, nt)] = (tag, ops.conv3x3_pack_weights(weight, dgrad=dgrad, nt=nt))
+    return hit[1]
+
+
 def eligible(x, weight, stride, padding, dilation, groups, padding_mode="zeros"):
     return (ENABLED and x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.dim() == 4
             and x.size(3) in WIDTHS and tuple(weight.shape[2:]) == (3, 3) and tuple(stride) == (1, 1)
@@ -57,7 +77,7 @@ class Conv3x3TCFunction(Function):
         ctx.has_bias = bias is not None
         out = x.new_empty((x.size(0), weight.size(0), x.size(2), x.size(3)))
         nt = _nt(x.size(3), weight.size(0))
-        ops.conv3x3_forward(x, ops.conv3x3_pack_weights(weight, nt=nt), bias, out, nt=nt)
+        ops.conv3x3_forward(x, _packed(weight, False, nt), bias, out, nt=nt)
         return out
 
     @staticmethod
@@ -68,7 +88,7 @@ class Conv3x3TCFunction(Function):
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
             nt = _nt(grad_out.size(3), weight.size(1))
-            ops.conv3x3_forward(grad_out, ops.conv3x3_pack_weights(weight, dgrad=True, nt=nt), None, gx, nt=nt)
+            ops.conv3x3_forward(grad_out, _packed(weight, True, nt), None, gx, nt=nt)
         if WGRAD_TC and weight.size(0) >= WGRAD_MIN_COUT and weight.size(1) >= WGRAD_MIN_CIN:
             want_b = ctx.has_bias and ctx.needs_input_grad[2]
             if ctx.needs_input_grad[1]:

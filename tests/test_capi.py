@@ -140,3 +140,29 @@ def test_guided_filter_box_sums():
     r = 5
     ref = torch.nn.functional.avg_pool2d(torch.nn.functional.pad(x, (r, r, r, r)), 2 * r + 1, 1, divisor_override=1)
     assert torch.allclose(BoxFilter(r)(x), ref, atol=1e-9)
+
+
+def test_packed_weight_cache_invalidation(monkeypatch):
+    """conv._packed (opt-in FFWM_CACHE_PACKED): frozen leaves are packed once per (direction, tile) and re-packed
+    after any in-place update; trainable or derived weights are never cached.  (Packing itself is CUDA-only: mocked.)"""
+    from ffwm_b200 import conv
+    calls = []
+    monkeypatch.setattr(conv.ops, "conv3x3_pack_weights", lambda w, dgrad=False, nt=64: calls.append((dgrad, nt)) or object())
+    monkeypatch.setattr(conv, "CACHE_PACKED", True)
+    w = torch.nn.Parameter(torch.zeros(8, 4, 3, 3), requires_grad=False)
+    a = conv._packed(w, False, 64)
+    assert conv._packed(w, False, 64) is a and len(calls) == 1
+    assert conv._packed(w, True, 64) is not a and conv._packed(w, False, 128) is not a and len(calls) == 3
+    with torch.no_grad():
+        w.add_(1.0)                                       # optimizer step / load_state_dict: version counter moves
+    assert conv._packed(w, False, 64) is not a and len(calls) == 4
+    w.data = torch.ones(8, 4, 3, 3)                       # storage swapped
+    conv._packed(w, False, 64)
+    assert len(calls) == 5
+    t = torch.nn.Parameter(torch.zeros(8, 4, 3, 3))       # trainable: never cached
+    conv._packed(t, False, 64), conv._packed(t, False, 64)
+    conv._packed(w * 2, False, 64), conv._packed(w * 2, False, 64)   # derived (spectral norm): a new tensor per call
+    assert len(calls) == 9
+    monkeypatch.setattr(conv, "CACHE_PACKED", False)
+    conv._packed(w, False, 64), conv._packed(w, False, 64)
+    assert len(calls) == 11
