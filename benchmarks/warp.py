@@ -25,6 +25,8 @@ import torch
 C, R = 128, 128
 K_BLOCK = 3
 KS, DIL = 4, 1
+# "iid" (default: SURVEY cfg5's independent per-pixel displacement) or "smooth" (see make_inputs.field)
+FLOW_MODE = os.environ.get("FFWM_BENCH_FLOW", "iid")
 
 
 def _mib(n):
@@ -71,14 +73,25 @@ def make_inputs(shapes, device, seed, pin=False):
         t = fn(*s, generator=g)
         return t.pin_memory() if pin else t
 
+    smooth = FLOW_MODE == "smooth"
+
+    def field(b, fn=torch.randn):
+        """(b, 2, r, r) displacement noise: independent per pixel (SURVEY cfg5), or — FFWM_BENCH_FLOW=smooth — noise
+        drawn on an r/16 lattice and upsampled bilinearly: neighbouring pixels then move together, as the flow a
+        network predicts does (same distribution at the lattice points, hence somewhat smaller between them)."""
+        if not smooth:
+            return rnd(b, 2, r, r, fn=fn)
+        lo = fn(b, 2, max(r // 16, 2), max(r // 16, 2), generator=g)
+        return torch.nn.functional.interpolate(lo, size=(r, r), mode="bilinear", align_corners=True)
+
     t = {
         "feat": rnd(B, c, r, r) * 2 - 1,
-        "disp": torch.cat([rnd(B, 2, r, r, fn=torch.randn) * 2, torch.full((B, 1, r, r), 2.0)], 1),
+        "disp": torch.cat([field(B) * 2, torch.full((B, 1, r, r), 2.0)], 1),
         "gout": rnd(B, c, r, r, fn=torch.randn),
         # WarpNet's absolute sampling grid (SURVEY D2): identity + the same 2 px noise as resample2d
-        "grid": _identity_grid(B, r) + rnd(B, 2, r, r, fn=torch.randn) * (2 * 2.0 / r),
+        "grid": _identity_grid(B, r) + field(B) * (2 * 2.0 / r),
         "be_src": rnd(Bb, c, r, r),
-        "be_flow": rnd(Bb, 2, r, r) * 1.8,
+        "be_flow": field(Bb, fn=torch.rand) * 1.8,
         "be_gout": rnd(Bb, c, K_BLOCK * r, K_BLOCK * r, fn=torch.randn),
         "lar_in": rnd(B2, K_BLOCK * K_BLOCK, r, r),
         "lar_gout": rnd(B2, 1, K_BLOCK * r, K_BLOCK * r, fn=torch.randn),
@@ -222,6 +235,8 @@ class WarpWorkload:
         return {"workload": "warp (BASELINE cfg5 primary point)", "C": s["C"], "R": s["R"], "B": s["B"],
                 "B_block_extractor": s["Bb"], "B_local_attn_reshape": s["B2"], "resample2d_ks": KS,
                 "block_extractor_k": K_BLOCK, "l2": "inputs_exceed_l2 (every large operand >= 256 MiB)",
+                "flow": ("independent per pixel: N(0, 2 px) / U(0, 1.8) px (SURVEY cfg5)" if FLOW_MODE != "smooth" else
+                         "smooth: the same noise on an r/16 lattice, bilinearly upsampled (FFWM_BENCH_FLOW=smooth)"),
                 "per_rank": "independent replicas, no collective"}
 
     # ------------------------------------------------------------------ end-to-end leg

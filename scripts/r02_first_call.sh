@@ -49,6 +49,18 @@ for f in ("r02_bench_cudnn_wgrad", "r02_bench_tc_wgrad", "r02_bench_nt128", "r02
     except Exception as e:
         print(f, "unreadable:", e)
 PY
+# the warp microbench with a smooth (network-like) displacement field next to cfg5's independent per-pixel noise
+timeout 600 python bench.py --workload warp --no-cpu-baseline > gpurun_out/r02_bench_warp_iid.json 2> gpurun_out/r02_bench_l.err; echo "bench warp (iid flow) rc=$?"
+FFWM_BENCH_FLOW=smooth timeout 600 python bench.py --workload warp --no-cpu-baseline > gpurun_out/r02_bench_warp_smooth.json 2>> gpurun_out/r02_bench_l.err; echo "bench warp (smooth flow) rc=$?"
+python - <<'PY'
+import json
+for f in ("r02_bench_warp_iid", "r02_bench_warp_smooth"):
+    try:
+        d = json.loads(open("gpurun_out/%s.json" % f).read().strip().splitlines()[-1])
+        print(f, "%.0f GB/s" % d["value"], {k: (v["ms"], v["frac_hbm"]) for k, v in d["kernels"].items()})
+    except Exception as e:
+        print(f, "unreadable:", e)
+PY
 # BASELINE config 2 (FlowNetF forward+backward, batch 6) was never recorded in round 1
 timeout 600 python bench.py --workload flownet --no-cpu-baseline > gpurun_out/r02_bench_flownet.json 2> gpurun_out/r02_bench_f.err; echo "bench (flownet, cfg2) rc=$?"; cat gpurun_out/r02_bench_flownet.json
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv3x3_wgrad -s 2 -c 3 -f -o gpurun_out/prof_r02_wgrad \
