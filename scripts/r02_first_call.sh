@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of round 2: validate and measure what was written blind at the end of round 1
 # (the tcgen05 weight-gradient kernel, the 128-channel CTA tile of the forward kernel, the fused MFM and guided-filter kernels), without touching the established suite's context.
-#   /usr/local/graft/bin/gpurun --timeout 1800 -- 'bash scripts/r02_first_call.sh'     (about 22 minutes of box time)
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash scripts/r02_first_call.sh'     (about 30 minutes of box time; comment out what is not needed)
 # Each step runs in its own process under its own timeout: a trap in the unproven kernel ends that step only.
 mkdir -p gpurun_out
 FFWM_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_zz_wgrad_tc_gpu.py -x -q > gpurun_out/r02_wgrad_pytest.log 2>&1; echo "wgrad pytest rc=$?"
