@@ -29,6 +29,7 @@ from .parallel import GradAverager
 # passes instead of 4 (losses.PerceptualLoss.many / IdentityLoss.many: same samples, bigger batches): CPU-verified
 # against the reference goldens, not yet measured on a B200 (written after the round-1 GPU budget was spent).
 BATCHED_VGG = os.environ.get("FFWM_BATCHED_VGG", "0") == "1"
+FLOW_STREAMS = os.environ.get("FFWM_FLOW_STREAMS", "0") == "1"      # see FFWMTrainer._flownets
 
 
 def set_requires_grad(nets, flag):
@@ -106,10 +107,32 @@ class FFWMTrainer:
         self.epoch = batch.get('epoch', 0)
 
     # ------------------------------------------------------------------ forward
+    def _flownets(self):
+        """flowNetF and flowNetB on the same input.  They are independent until the losses, and half of their 38
+        convolutions each work on maps of 8x8 and below (a few CTAs on 148 SMs), so FFWM_FLOW_STREAMS=1 runs
+        flowNetB on a second stream, forked from and joined back into the current one (legal inside CUDA-graph
+        capture; autograd runs each net's backward on the stream its forward used).  Same arithmetic, same order
+        within each net.  Not yet run on a GPU (written after the round-1 GPU budget was spent): off by default."""
+        if not (FLOW_STREAMS and self.device.type == "cuda"):
+            flows_F = self.flowNetF(self.img_S)
+            return flows_F, self.flowNetB(self.img_S)
+        cur = torch.cuda.current_stream(self.device)
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        side = self._side_stream
+        side.wait_stream(cur)                               # fork: img_S and the weights are ready on `cur`
+        with torch.cuda.stream(side):
+            flows_B = self.flowNetB(self.img_S)
+        flows_F = self.flowNetF(self.img_S)
+        cur.wait_stream(side)                               # join before anything consumes flows_B
+        if not torch.cuda.is_current_stream_capturing():
+            for t in flows_B:
+                t.record_stream(cur)                        # allocated on `side`, consumed on `cur`
+        return flows_F, flows_B
+
     def forward(self):
-        flow_F128, flow_F64, flow_F32 = self.flowNetF(self.img_S)
+        (flow_F128, flow_F64, flow_F32), (self.flow_B128, self.flow_B64, self.flow_B32) = self._flownets()
         self.img_S_warp = self.warpNet(self.img_S, flow_F128)
-        self.flow_B128, self.flow_B64, self.flow_B32 = self.flowNetB(self.img_S)
         self.img_S_rec = self.warpNet(self.img_F, self.flow_B128)
         self.fake_F32, self.fake_F64, self.fake_F128 = self.netG(self.img_S, flow=[flow_F32, flow_F64, flow_F128])
         self.img_GF128 = self.gf128(self.fake_F128, self.img_F)

@@ -36,13 +36,16 @@ FFWM_BATCHED_SN=1 timeout 600 python bench.py --no-cpu-baseline --no-warp > gpur
 # batched VGG19 / LightCNN loss passes (6 + 2 passes instead of 14 + 4): also plain torch, CPU-verified
 FFWM_BATCHED_VGG=1 timeout 600 python -m pytest tests/test_train_step.py -m gpu -x -q > gpurun_out/r02_vgg_pytest.log 2>&1; echo "batched VGG gpu goldens rc=$?"; tail -3 gpurun_out/r02_vgg_pytest.log
 FFWM_BATCHED_VGG=1 timeout 600 python bench.py --no-cpu-baseline --no-warp > gpurun_out/r02_bench_vgg.json 2> gpurun_out/r02_bench_i.err; echo "bench (batched VGG/LightCNN) rc=$?"
+# flowNetF / flowNetB on two streams (fork-join inside the captured graph): parity first, then the A/B
+FFWM_FLOW_STREAMS=1 timeout 600 python -m pytest tests/test_train_step.py -m gpu -x -q > gpurun_out/r02_streams_pytest.log 2>&1; echo "flow streams gpu goldens rc=$?"; tail -3 gpurun_out/r02_streams_pytest.log
+FFWM_FLOW_STREAMS=1 timeout 600 python bench.py --no-cpu-baseline --no-warp > gpurun_out/r02_bench_streams.json 2> gpurun_out/r02_bench_m.err; echo "bench (flow streams) rc=$?"
 FFWM_CACHE_PACKED=1 timeout 600 python bench.py --no-cpu-baseline --no-warp > gpurun_out/r02_bench_cache.json 2> gpurun_out/r02_bench_k.err; echo "bench (packed-weight cache) rc=$?"
 FFWM_BATCHED_SN=1 FFWM_BATCHED_VGG=1 timeout 600 python bench.py --no-cpu-baseline --no-warp > gpurun_out/r02_bench_host.json 2> gpurun_out/r02_bench_j.err; echo "bench (both host-side restructurings) rc=$?"
 FFWM_WGRAD_TC=1 FFWM_CONV_NT128=1 FFWM_FUSED_MFM=1 FFWM_FUSED_GF=1 FFWM_CACHE_PACKED=1 timeout 600 python bench.py --no-cpu-baseline --no-warp > gpurun_out/r02_bench_cache.json 2> gpurun_out/r02_bench_k.err; echo "bench (packed-weight cache) rc=$?"
 FFWM_BATCHED_SN=1 FFWM_BATCHED_VGG=1 FFWM_CACHE_PACKED=1 timeout 600 python bench.py --no-cpu-baseline --no-warp > gpurun_out/r02_bench_all.json 2> gpurun_out/r02_bench_e.err; echo "bench (all seven) rc=$?"
 python - <<'PY'
 import json
-for f in ("r02_bench_cudnn_wgrad", "r02_bench_tc_wgrad", "r02_bench_nt128", "r02_bench_mfm", "r02_bench_gf", "r02_bench_sn", "r02_bench_vgg", "r02_bench_cache", "r02_bench_host", "r02_bench_all"):
+for f in ("r02_bench_cudnn_wgrad", "r02_bench_tc_wgrad", "r02_bench_nt128", "r02_bench_mfm", "r02_bench_gf", "r02_bench_sn", "r02_bench_vgg", "r02_bench_streams", "r02_bench_cache", "r02_bench_host", "r02_bench_all"):
     try:
         d = json.loads(open("gpurun_out/%s.json" % f).read().strip().splitlines()[-1])
         print(f, d["value"], d["unit"], d["ms_per_step"], "ms/step")
