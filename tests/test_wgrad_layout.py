@@ -149,7 +149,7 @@ def emulate(x, go, splits_hint):
 
 
 @pytest.mark.parametrize("b,cin,cout,h,w,splits_hint", [(2, 5, 3, 3, 32, 148), (1, 50, 130, 2, 64, 7), (1, 3, 8, 1, 32, 1),
-                                                        (1, 2, 2, 70, 32, 1)])
+                                                        (1, 2, 2, 70, 32, 1), (1, 100, 140, 2, 96, 13)])
 def test_wgrad_plan_matches_torch(b, cin, cout, h, w, splits_hint):
     g = torch.Generator().manual_seed(cin * 100 + cout)
     x = torch.randn(b, cin, h, w, generator=g)
