@@ -99,6 +99,37 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def tensor_peaks(local_rank, n=8192, iters=10):
+    """cuBLAS GEMM rates measured in this run (burst, best of `iters`, CUDA events): the TF32 rate BASELINE.md 2 asks
+    for before any TF32 fraction is quoted, and the bf16 rate next to MEASURED_PEAKS.json's.  Never fatal."""
+    import torch
+    out = {}
+    try:
+        dev = torch.device("cuda", local_rank)
+        saved = torch.backends.cuda.matmul.allow_tf32
+        for name, dtype, tf32 in (("tf32_tflops", torch.float32, True), ("bf16_tflops", torch.bfloat16, False)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            a = torch.randn(n, n, device=dev, dtype=dtype)
+            b = torch.randn(n, n, device=dev, dtype=dtype)
+            for _ in range(3):
+                a @ b
+            best = 1e30
+            for _ in range(iters):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                a @ b
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            out[name] = round(2.0 * n ** 3 / (best * 1e-3) / 1e12, 1)
+            del a, b
+        torch.backends.cuda.matmul.allow_tf32 = saved
+        out["how"] = "torch.matmul %d^3 (cuBLAS), best of %d, CUDA events, this run" % (n, iters)
+    except Exception as e:  # noqa: BLE001
+        out["error"] = repr(e)
+    return out
+
+
 def warp_microbench(local_rank, pk, steps=10, warmup=3):
     """BASELINE's second metric (resample2d / block_extractor HBM GB/s): the `warp` workload's
     device leg, attached to the train-step line at N=1."""
@@ -146,6 +177,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--no-warp", action="store_true", help="train_step: skip the attached flow-warp microbench")
+    ap.add_argument("--no-library-baseline", action="store_true",
+                    help="train_step: skip the same-run cuDNN/ATen baseline (fp32 and TF32) of the same trainer")
     args = ap.parse_args()
 
     from benchmarks import get_workload
@@ -249,7 +282,12 @@ def main():
         }
         if args.workload in ("default", "train_step") and world == 1 and not args.no_warp:
             line["warp_microbench"] = warp_microbench(local_rank, pk)
+        if hasattr(wl, "gpu_library_baseline") and world == 1 and not args.no_library_baseline:
+            note("library baseline (same trainer on cuDNN / ATen)")
+            line["gpu_library_baseline"] = wl.gpu_library_baseline()
+            line["measured_tensor_peaks"] = tensor_peaks(local_rank)
         if not args.no_cpu_baseline and world == 1:
+            note("cpu baseline")
             line["cpu_baseline"] = wl_cls.cpu_baseline()
         print(json.dumps(line), flush=True)
     if world > 1:

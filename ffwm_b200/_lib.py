@@ -108,17 +108,22 @@ def t4(t):
 
 def require_cuda(*tensors):
     """The reference raises NotImplementedError for CPU tensors
-    (models/external_function.py:37-38,84-85); so does this path."""
-    dev = None
+    (models/external_function.py:37-38,84-85); so does this path.  Also checks that all tensors of the call live on
+    one device and share one dtype."""
+    dev = dtype = None
     for t in tensors:
         if t is None:
             continue
         if not t.is_cuda:
             raise NotImplementedError("ffwm_b200 ops are CUDA-only (no CPU path, as in the reference)")
         if dev is None:
-            dev = t.device
+            dev, dtype = t.device, t.dtype
         elif t.device != dev:
             raise RuntimeError("ffwm_b200: tensors live on different devices (%s vs %s)" % (dev, t.device))
+        elif t.dtype != dtype:
+            # the C ABI takes ONE dtype code per call and reinterprets every pointer with it; the reference's
+            # `.data<scalar_t>()` raises on a mismatch, so does this (a silent mismatch would read out of bounds)
+            raise TypeError("ffwm_b200: tensors of one call must share a dtype (%s vs %s)" % (dtype, t.dtype))
     return dev
 
 

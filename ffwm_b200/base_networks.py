@@ -32,8 +32,9 @@ from .spectral import batch_spectral_norm
 
 LRELU_SLOPE = 0.2
 # spectral norm of a whole network in one batched update per weight shape (ffwm_b200/spectral.py) instead of one
-# power iteration per layer; CPU-verified, not yet measured on a B200: off unless asked for
-BATCHED_SN = os.environ.get("FFWM_BATCHED_SN", "0") == "1"
+# power iteration per layer: reference goldens green on CPU and B200, train step 95.2 -> 90.1 ms
+# (profiles/r02a_switches.txt).  FFWM_BATCHED_SN=0 restores torch's per-layer hooks for A/B runs.
+BATCHED_SN = os.environ.get("FFWM_BATCHED_SN", "1") == "1"
 
 
 def initialize_msra(modules):

@@ -36,7 +36,7 @@ WGRAD_TC = os.environ.get("FFWM_WGRAD_TC", "0") == "1"     # experimental, unmea
 # the first convolutions on 3 channels: 0.7 % of the weight-gradient FLOPs of the step) stay on cuDNN
 WGRAD_MIN_COUT, WGRAD_MIN_CIN = 32, 16
 # experimental, unmeasured: 128 output channels per CTA for the W = 128 layers with more than 64 of them
-NT128 = os.environ.get("FFWM_CONV_NT128", "0") == "1"
+NT128 = os.environ.get("FFWM_CONV_NT128", "1") == "1"
 
 
 def _nt(width, n_out):
@@ -47,7 +47,7 @@ def _nt(width, n_out):
 # launches) instead of re-packing on every call.  A weight qualifies while it is a leaf that does not require grad;
 # the image is tagged with the tensor's version counter and data pointer, so any in-place update (optimizer step,
 # load_state_dict, .data swap) re-packs.  Spectral-normed weights are new tensors on every call and never qualify.
-CACHE_PACKED = os.environ.get("FFWM_CACHE_PACKED", "0") == "1"
+CACHE_PACKED = os.environ.get("FFWM_CACHE_PACKED", "1") == "1"
 
 
 def _packed(weight, dgrad, nt):

@@ -25,8 +25,9 @@ from torch.autograd import Function
 
 from . import ops
 
-# experimental, unmeasured (csrc/guided_filter.cu was written after the round-1 GPU budget was spent): off unless asked for
-FUSED_GF = os.environ.get("FFWM_FUSED_GF", "0") == "1"
+# the guided filter as four kernels per direction (csrc/guided_filter.cu): parity-green on a B200 (tests/test_guided_filter_gpu.py),
+# train step 95.2 -> 90.7 ms (profiles/r02a_switches.txt).  FFWM_FUSED_GF=0 restores the cumsum formulation for A/B runs.
+FUSED_GF = os.environ.get("FFWM_FUSED_GF", "1") == "1"
 
 
 def _cuda_only(t):

@@ -136,9 +136,8 @@ class network_29layers(nn.Module):
         x = self.pool3(self.group2(self.block2(x)))
         x = self.group3(self.block3(x))
         p = self.pool4(self.group4(self.block4(x)))
-        fc = self.fc(p.flatten(1))
-        out = self.fc2(F.dropout(fc, training=self.training))
-        return out, fc, p
+        fc = F.dropout(self.fc(p.flatten(1)), training=self.training)    # the POST-dropout features are returned (:124-127)
+        return self.fc2(fc), fc, p
 
 
 class network_29layers_v2(nn.Module):

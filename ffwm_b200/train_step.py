@@ -28,8 +28,8 @@ from .parallel import GradAverager
 # The perceptual losses of one step through 6 VGG19 passes instead of 14 and the identity losses through 2 LightCNN
 # passes instead of 4 (losses.PerceptualLoss.many / IdentityLoss.many: same samples, bigger batches): CPU-verified
 # against the reference goldens, not yet measured on a B200 (written after the round-1 GPU budget was spent).
-BATCHED_VGG = os.environ.get("FFWM_BATCHED_VGG", "0") == "1"
-FLOW_STREAMS = os.environ.get("FFWM_FLOW_STREAMS", "0") == "1"      # see FFWMTrainer._flownets
+BATCHED_VGG = os.environ.get("FFWM_BATCHED_VGG", "1") == "1"
+FLOW_STREAMS = os.environ.get("FFWM_FLOW_STREAMS", "1") == "1"      # see FFWMTrainer._flownets
 
 
 def set_requires_grad(nets, flag):
@@ -297,6 +297,10 @@ class FFWMTrainer:
         lm = self.lm_F
         el, er = lm[:, 63:64], lm[:, 515:516]
         mouth = torch.cat((lm[:, 64:128], lm[:, 516:580]), 1)
+        # LongTensor / 2: true division on torch >= 1.6 (x.5 centres), floor division on the torch 1.5 the reference was
+        # written for (models/ffwm_model.py:225).  Parity here is pinned to the UNMODIFIED reference as it executes on the
+        # installed torch (tests/golden/ref_train_step.json, ref_orchestrators.json), i.e. true division; unlike
+        # MultiScaleLDLoss (losses._int_div) nothing fails either way, the mouth crop just sits half a pixel apart.
         mc = (mouth.min(dim=1, keepdim=True)[0] + mouth.max(dim=1, keepdim=True)[0]) / 2
         nc = lm[:, 429:430]
         return [self.build_grid(c, 32) for c in (el, er, nc, mc)]

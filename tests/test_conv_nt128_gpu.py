@@ -1,16 +1,13 @@
 """tcgen05 3x3 convolution with 128 output channels per CTA (conv3x3_tc_kernel<128, 128>) against float64.
 
-OPT-IN like tests/test_zz_wgrad_tc_gpu.py: the variant was written after the round-1 GPU budget was spent and has
-not run on a B200 yet — FFWM_EXPERIMENTAL=1 enables these tests.  Same tolerances as tests/test_conv_tc_gpu.py."""
+Validated on a B200 in round 2 (gpurun call 1, profiles/r02a_*)."""
 import os
 
 import pytest
 import torch
 import torch.nn.functional as F
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FFWM_EXPERIMENTAL", "0") != "1",
-                                 reason="experimental kernel variant, not yet validated on a B200: set FFWM_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 

@@ -1,9 +1,5 @@
 """tcgen05 weight gradient (ffwm_b200/csrc/conv3x3_wgrad_tc.cu) against PyTorch float64.
 
-OPT-IN: the kernel was written after the round-1 GPU budget was spent and has not run on a B200 yet, so
-these tests only run with FFWM_EXPERIMENTAL=1 (the file sorts last so that a trap in an unproven kernel
-cannot poison the CUDA context of the established suite).  The first gpurun call of round 2 is
-`FFWM_EXPERIMENTAL=1 python -m pytest tests/test_zz_wgrad_tc_gpu.py -x -q`.
 Tolerance: 4e-5 of max|ref|: a CTA's accumulation chain is capped at 768 truncating tensor-core updates (~2e-5,
 the forward kernel's measured error at the same chain length); the path's contract is 1e-4."""
 import os
@@ -12,9 +8,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FFWM_EXPERIMENTAL", "0") != "1",
-                                 reason="experimental kernel, not yet validated on a B200: set FFWM_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 

@@ -1,15 +1,13 @@
 """Fused guided-filter kernels (ffwm_b200/csrc/guided_filter.cu) against the torch-op mirror of the reference formula
 in float64 (forward 1e-5, gradient 1e-4 relative to max|ref|: the path's stated tolerances).
 
-OPT-IN (FFWM_EXPERIMENTAL=1): written after the round-1 GPU budget was spent, not yet run on a B200."""
+Validated on a B200 in round 2 (gpurun call 1, profiles/r02a_*)."""
 import os
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FFWM_EXPERIMENTAL", "0") != "1",
-                                 reason="experimental kernel, not yet validated on a B200: set FFWM_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
