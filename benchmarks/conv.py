@@ -118,7 +118,7 @@ def main():
     if args.nt128:
         return nt128_bench(args.out or os.path.join(ROOT, "gpurun_out", "conv_nt128.json"))
     args.out = args.out or os.path.join(ROOT, "gpurun_out", "conv.json")
-    from ffwm_b200 import ops
+    from ffwm_b200 import _lib, ops
     dev = torch.device("cuda", 0)
     torch.backends.cudnn.benchmark = True
     rows = []
@@ -127,30 +127,35 @@ def main():
         w = torch.randn(cout, cin, 3, 3, device=dev) / (cin * 9) ** 0.5
         b = torch.randn(cout, device=dev)
         out = torch.empty(8, cout, r, r, device=dev)
-        packed = ops.conv3x3_pack_weights(w)
+        nt = 128 if (r == 128 and cout > 64) else 64            # what ffwm_b200/conv.py selects
         flop = 2.0 * 8 * r * r * cin * cout * 9
-        t_mine = timeit(lambda: ops.conv3x3_forward(x, packed, b, out))
-        t_pack = timeit(lambda: ops.conv3x3_pack_weights(w))
-        torch.backends.cudnn.allow_tf32 = False
-        t_fp32 = timeit(lambda: F.conv2d(x, w, b, padding=1))
         ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
-        err_mine = float((out.double() - ref).abs().max() / ref.abs().max())
-        err_fp32 = float((F.conv2d(x, w, b, padding=1).double() - ref).abs().max() / ref.abs().max())
+        row = dict(shape=name, cin=cin, cout=cout, gflop=flop / 1e9, nt=nt)
+        for math, tag in ((1, "bf16x3"), (0, "tf32x3")):
+            old = _lib.set_option("CONV_MATH", math)
+            packed = ops.conv3x3_pack_weights(w, nt=nt)
+            t = timeit(lambda: ops.conv3x3_forward(x, packed, b, out, nt=nt))
+            row["ms_" + tag] = t
+            row["tflops_" + tag] = flop / t / 1e9
+            row["err_" + tag] = float((out.double() - ref).abs().max() / ref.abs().max())
+            row["ms_pack_" + tag] = timeit(lambda: ops.conv3x3_pack_weights(w, nt=nt))
+            _lib.set_option("CONV_MATH", old)
+        torch.backends.cudnn.allow_tf32 = False
+        row["ms_cudnn_fp32"] = timeit(lambda: F.conv2d(x, w, b, padding=1))
+        row["err_cudnn_fp32"] = float((F.conv2d(x, w, b, padding=1).double() - ref).abs().max() / ref.abs().max())
         torch.backends.cudnn.allow_tf32 = True
-        t_tf32 = timeit(lambda: F.conv2d(x, w, b, padding=1))
-        err_tf32 = float((F.conv2d(x, w, b, padding=1).double() - ref).abs().max() / ref.abs().max())
-        rows.append(dict(shape=name, cin=cin, cout=cout, gflop=flop / 1e9, ms_tcgen05=t_mine, ms_pack=t_pack,
-                         ms_cudnn_fp32=t_fp32, ms_cudnn_tf32=t_tf32, tflops_tcgen05=flop / t_mine / 1e9,
-                         tflops_tensor_issued=3 * flop / t_mine / 1e9, err_tcgen05=err_mine, err_cudnn_fp32=err_fp32,
-                         err_cudnn_tf32=err_tf32))
+        row["ms_cudnn_tf32"] = timeit(lambda: F.conv2d(x, w, b, padding=1))
+        row["err_cudnn_tf32"] = float((F.conv2d(x, w, b, padding=1).double() - ref).abs().max() / ref.abs().max())
+        rows.append(row)
         del ref
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(rows, open(args.out, "w"), indent=1)
-    print("%-22s %8s %8s %8s %8s %8s %9s %9s %9s" % ("shape", "tc ms", "pack ms", "fp32 ms", "tf32 ms", "TF/s", "err tc", "err fp32", "err tf32"))
+    print("%-22s %3s | %8s %7s %8s | %8s %7s %8s | %8s %8s | %8s %8s" % (
+        "shape", "nt", "bf16x3", "TF/s", "err", "tf32x3", "TF/s", "err", "cudnn32", "err", "cudnnTF", "err"))
     for r in rows:
-        print("%-22s %8.3f %8.3f %8.3f %8.3f %8.1f %9.1e %9.1e %9.1e" % (
-            r["shape"], r["ms_tcgen05"], r["ms_pack"], r["ms_cudnn_fp32"], r["ms_cudnn_tf32"], r["tflops_tcgen05"],
-            r["err_tcgen05"], r["err_cudnn_fp32"], r["err_cudnn_tf32"]))
+        print("%-22s %3d | %8.3f %7.1f %8.1e | %8.3f %7.1f %8.1e | %8.3f %8.1e | %8.3f %8.1e" % (
+            r["shape"], r["nt"], r["ms_bf16x3"], r["tflops_bf16x3"], r["err_bf16x3"], r["ms_tf32x3"], r["tflops_tf32x3"],
+            r["err_tf32x3"], r["ms_cudnn_fp32"], r["err_cudnn_fp32"], r["ms_cudnn_tf32"], r["err_cudnn_tf32"]))
 
 
 if __name__ == "__main__":

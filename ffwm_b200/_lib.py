@@ -31,6 +31,8 @@ SIGNATURES = {
     "ffwm_abi_version": [],
     "ffwm_last_error": [],
     "ffwm_kernel_launches": [],
+    "ffwm_set_option": [ctypes.c_char_p, _I],
+    "ffwm_get_option": [ctypes.c_char_p],
     "ffwm_resample2d_forward": [_T4P, _T4P, _T4P, _I, _I, _I, _VP],
     "ffwm_resample2d_backward": [_T4P, _T4P, _T4P, _T4P, _T4P, _I, _I, _I, _VP],
     "ffwm_block_extractor_forward": [_T4P, _T4P, _T4P, _I, _I, _VP],
@@ -81,6 +83,19 @@ def lib():
                               % (l.ffwm_abi_version(), ABI_VERSION))
         _lib = l
     return _lib
+
+
+def set_option(name, value):
+    """Process-wide runtime option of the library (include/ffwm_b200.h: ffwm_set_option); returns the old value."""
+    l = lib()
+    old = l.ffwm_get_option(name.encode())
+    if l.ffwm_set_option(name.encode(), int(value)) != 0:
+        raise ValueError(l.ffwm_last_error().decode())
+    return old
+
+
+def get_option(name):
+    return int(lib().ffwm_get_option(name.encode()))
 
 
 def dtype_code(t):

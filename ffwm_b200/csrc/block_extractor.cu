@@ -478,7 +478,7 @@ static int block_extractor_backward_t(const ffwm_tensor4* a, const ffwm_tensor4*
     if (gout.n > 65535) { set_error("block_extractor: batch %d > 65535", gout.n); return FFWM_ERR_TOO_LARGE; }
     if (src.h == 0 || src.w == 0) { set_error("block_extractor: empty source plane"); return FFWM_ERR_SHAPE; }
     if constexpr (sizeof(T) == 4) {
-        if ((k == 2 || k == 3) && gout.c >= 8 && !getenv("FFWM_DISABLE_TILED")) {
+        if ((k == 2 || k == 3) && gout.c >= 8 && !opt(OPT_DISABLE_TILED)) {
             constexpr int SL = 8, PX = 256 / SL;
             dim3 grid(ceil_div(flow.h * flow.w, PX), 1, gout.n), block(PX, SL);
             if (k == 2) block_extractor_bwd_window_kernel<2, SL><<<grid, block, 0, st>>>(src, flow, gout, gs, gf);

@@ -1,5 +1,6 @@
 // C-ABI plumbing shared by every entry point: argument validation, error text.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -65,9 +66,11 @@ static unsigned long long g_launches = 0;   // kernels enqueued by this process 
 
 int check_launch(const char* what) {
     __atomic_add_fetch(&g_launches, 1ULL, __ATOMIC_RELAXED);
-    cudaError_t e = cudaGetLastError();
+    // Peek, do not consume: a sticky/asynchronous error raised earlier by someone else's kernel on this context stays
+    // visible to its owner (PyTorch) instead of being swallowed and mis-attributed here.
+    cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) {
-        set_error("%s: %s", what, cudaGetErrorString(e));
+        set_error("%s: launch failed or the context already carried an error: %s", what, cudaGetErrorString(e));
         return int(e);
     }
     return FFWM_OK;
@@ -86,7 +89,51 @@ int sm_count() {
     return cached;
 }
 
+static const char* const g_opt_names[OPT_COUNT] = {
+    "DISABLE_TILED", "FORCE_TILED", "DISABLE_ROLL", "FORCE_ROLL", "SCATTER_TILED", "DISABLE_TILED_GFLOW",
+    "DISABLE_QUAD", "GQ_SCALAR_FILL", "SCATTER_SCALAR_FLUSH", "WGRAD_DIRECT_EPILOGUE", "CONV_MATH"};
+static int g_opts[OPT_COUNT];
+static int g_opts_ready = 0;
+
+static void init_opts() {
+    if (__atomic_load_n(&g_opts_ready, __ATOMIC_ACQUIRE)) return;
+    for (int i = 0; i < OPT_COUNT; ++i) {
+        char env[64];
+        snprintf(env, sizeof(env), "FFWM_%s", g_opt_names[i]);
+        const char* v = getenv(env);
+        int val = i == OPT_CONV_MATH ? 1 : 0;                          // defaults: everything off, 3xBF16 convolution math
+        if (v && *v) val = (v[0] >= '0' && v[0] <= '9') ? atoi(v) : 1; // FFWM_X=1, FFWM_X=anything -> 1, FFWM_X=0 -> 0
+        g_opts[i] = val;
+    }
+    __atomic_store_n(&g_opts_ready, 1, __ATOMIC_RELEASE);
+}
+
+int opt(int id) {
+    init_opts();
+    return g_opts[id];
+}
+
+static int opt_index(const char* name) {
+    if (!name) return -1;
+    if (!strncmp(name, "FFWM_", 5)) name += 5;
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (!strcmp(name, g_opt_names[i])) return i;
+    return -1;
+}
+
 }  // namespace ffwm
+
+extern "C" int ffwm_set_option(const char* name, int value) {
+    const int i = ffwm::opt_index(name);
+    if (i < 0) { ffwm::set_error("ffwm_set_option: unknown option '%s'", name ? name : "(null)"); return FFWM_ERR_ARG; }
+    ffwm::init_opts();
+    ffwm::g_opts[i] = value;
+    return FFWM_OK;
+}
+extern "C" int ffwm_get_option(const char* name) {
+    const int i = ffwm::opt_index(name);
+    return i < 0 ? -1 : ffwm::opt(i);
+}
 
 extern "C" int ffwm_abi_version(void) { return FFWM_ABI_VERSION; }
 extern "C" const char* ffwm_last_error(void) { return ffwm::g_err; }

@@ -63,4 +63,23 @@ inline int ceil_div(int64_t a, int64_t b) { return int((a + b - 1) / b); }
 // Number of SMs of the current device (cached); grids are sized against it.
 int sm_count();
 
+// Runtime options (diagnostics / A-B switches).  Each is read ONCE from the environment variable FFWM_<NAME> when
+// the library is first used and can be changed afterwards through ffwm_set_option() (tests do that); launch paths
+// only read a cached int.
+enum Opt {
+    OPT_DISABLE_TILED = 0,       // every warp op through the direct kernels
+    OPT_FORCE_TILED,             // small / ragged shapes through the tiled kernels (tests)
+    OPT_DISABLE_ROLL,
+    OPT_FORCE_ROLL,
+    OPT_SCATTER_TILED,           // previous-generation destination-sorted scatter
+    OPT_DISABLE_TILED_GFLOW,
+    OPT_DISABLE_QUAD,
+    OPT_GQ_SCALAR_FILL,
+    OPT_SCATTER_SCALAR_FLUSH,
+    OPT_WGRAD_DIRECT_EPILOGUE,
+    OPT_CONV_MATH,               // 0 = 3xTF32 operand split, 1 = 3xBF16 operand split (conv3x3_tc.cu)
+    OPT_COUNT
+};
+int opt(int id);
+
 }  // namespace ffwm

@@ -33,6 +33,8 @@
 
 #include <algorithm>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -43,7 +45,16 @@ namespace ffwm {
 // l1tex 72 % / tensor pipe 48 %); N = 128 reads 4 + 4 KB for 66 clk of math.  The N = 128 variant is EXPERIMENTAL
 // (written after the round-1 GPU budget was spent, not yet run): callers opt in per call (nt argument of the
 // *_nt entry points; ffwm_b200/conv.py: FFWM_CONV_NT128=1).
-constexpr int CV_KB = 8;               // input channels per K block = one tf32 MMA K
+// Operand math (template parameter BF of everything below; runtime choice: option CONV_MATH, common.cuh):
+//   BF = false  3xTF32: a = hi + lo, hi = a & 0xffffe000 (exact in tf32); hi*hi + hi*lo + lo*hi; K block = 8 channels
+//   BF = true   3xBF16: a = b1 + b2 + (dropped), b1 = bf16_rn(a), b2 = bf16_rn(a - b1); b1*b1 + b1*b2 + b2*b1;
+//               K block = 16 channels.  A 16-byte slot holds 8 bf16 channels instead of 4 fp32, so every
+//               shared-memory tile has the SAME size and layout, each MMA contracts twice as many channels at the
+//               same cost (kind::f16 runs at twice the kind::tf32 rate), and the kernel — shared-memory bound, see
+//               NT below — does half the MMAs.  Dropped terms: b1*b3, b2*b2, b3*b1 <= 3 * 2^-17 per product, random
+//               sign: 4-6e-6 of max|out| over the step's K range (CPU simulation, profiles/README.md), the same order
+//               as the tensor core's truncating fp32 accumulation (1-2e-5 measured) and inside the path's 1e-4.
+template <bool BF> struct CvMath { static constexpr int KB = BF ? 16 : 8, CPS = BF ? 8 : 4; };   // channels per K block / per slot
 constexpr int CV_PRODUCERS = 256;
 
 // Geometry per image width WI (= 128, 64, 32 or 16).  The MMA M dimension is always 128 pixels:
@@ -82,7 +93,7 @@ template <int nt>
 __global__ void conv3x3_pack_kernel(const float* __restrict__ w, float* __restrict__ packed, int cout, int cin, int dgrad,
                                     int64_t s_co, int64_t s_ci, int64_t s_ky, int64_t s_kx) {
     const int n_out = dgrad ? cin : cout, n_in = dgrad ? cout : cin;     // of the convolution being packed
-    const int ncob = (n_out + nt - 1) / nt, nkb = (n_in + CV_KB - 1) / CV_KB;
+    const int ncob = (n_out + nt - 1) / nt, nkb = (n_in + 7) / 8;
     const int64_t total = (int64_t)ncob * nkb * 9 * 2 * nt * 4;       // (hi,lo) pairs are written together
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = i;
@@ -92,7 +103,7 @@ __global__ void conv3x3_pack_kernel(const float* __restrict__ w, float* __restri
         const int tap = r % 9; r /= 9;
         const int kb = r % nkb; r /= nkb;
         const int cob = (int)r;
-        const int o = cob * nt + col, c = kb * CV_KB + kc * 4 + j;
+        const int o = cob * nt + col, c = kb * 8 + kc * 4 + j;
         float v = 0.f;
         if (o < n_out && c < n_in) {
             const int ky = tap / 3, kx = tap % 3;
@@ -108,16 +119,48 @@ __global__ void conv3x3_pack_kernel(const float* __restrict__ w, float* __restri
     }
 }
 
+// The 3xBF16 image: packed[cob][kb][tap][part][kchunk][co_local NT][8 ci] of bf16 (part: 0 = b1, 1 = b2), K block = 16.
+template <int nt>
+__global__ void conv3x3_pack_bf_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed, int cout, int cin, int dgrad,
+                                       int64_t s_co, int64_t s_ci, int64_t s_ky, int64_t s_kx) {
+    const int n_out = dgrad ? cin : cout, n_in = dgrad ? cout : cin;
+    const int ncob = (n_out + nt - 1) / nt, nkb = (n_in + 15) / 16;
+    const int64_t total = (int64_t)ncob * nkb * 9 * 2 * nt * 8;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i;
+        const int j = r % 8; r /= 8;
+        const int col = r % nt; r /= nt;
+        const int kc = r % 2; r /= 2;
+        const int tap = r % 9; r /= 9;
+        const int kb = r % nkb; r /= nkb;
+        const int cob = (int)r;
+        const int o = cob * nt + col, c = kb * 16 + kc * 8 + j;
+        float v = 0.f;
+        if (o < n_out && c < n_in) {
+            const int ky = tap / 3, kx = tap % 3;
+            v = dgrad ? w[c * s_co + o * s_ci + (2 - ky) * s_ky + (2 - kx) * s_kx]
+                      : w[o * s_co + c * s_ci + ky * s_ky + kx * s_kx];
+        }
+        const __nv_bfloat16 b1 = __float2bfloat16_rn(v);
+        const __nv_bfloat16 b2 = __float2bfloat16_rn(v - __bfloat162float(b1));
+        const int64_t base = ((((int64_t)cob * nkb + kb) * 9 + tap) * 2) * (2 * nt * 8);
+        const int64_t within = ((int64_t)kc * nt + col) * 8 + j;
+        packed[base + within] = b1;
+        packed[base + 2 * nt * 8 + within] = b2;
+    }
+}
+
 // ---------------------------------------------------------------- the convolution
 // Warp roles (288 threads): warps 0-7 stage activations (producers) and run the epilogue; warp 8
 // lane 0 copies the packed weights with one bulk async copy per K block and issues the MMAs.
 // Pipeline state lives in mbarriers: fullA[2] (256 producer arrivals), fullB[2] (bulk-copy
 // transaction bytes), empty[2] (tcgen05.commit of the MMAs that read the buffer).
-template <int WI, int NT>
+template <int WI, int NT, bool BF>
 __global__ void __launch_bounds__(CV_PRODUCERS + 32, 1)
 conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const float* __restrict__ bias,
                   View<float> out, int nkb) {
     using G = CvGeo<WI, NT>;
+    constexpr int KB = CvMath<BF>::KB, CPS = CvMath<BF>::CPS;
     extern __shared__ __align__(128) unsigned char cv_smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(cv_smem + 2 * G::STAGE);    // fullA[0,1] fullB[2,3] empty[4,5]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cv_smem + 2 * G::STAGE + 48);
@@ -158,14 +201,14 @@ conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const f
         for (int kb = 0; kb < nkb; ++kb) {
             const int buf = kb & 1;
             if (kb >= 2) mbar_wait(&bars[4 + buf], ((kb >> 1) - 1) & 1);          // MMAs of K block kb-2 done
-            const int c0 = kb * CV_KB + kc * 4;
-            float v[NR][4];
+            const int c0 = kb * KB + kc * CPS;
+            float v[NR][CPS];
 #pragma unroll
             for (int i = 0; i < NR; ++i) {
                 const int rr = ph + i * PH;
                 const bool ok = rr < G::IN_ROWS && (unsigned)(y0 - 1 + rr) < (unsigned)x.h;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < CPS; ++j)
                     v[i][j] = (ok && c0 + j < x.c) ? __ldg(gp0 + (int64_t)(c0 + j) * x.sc + rr * x.sh) : 0.f;
             }
             unsigned char* sA = cv_smem + buf * G::STAGE + kc * G::A_CHUNK;
@@ -174,12 +217,12 @@ conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const f
                 const int rr = ph + i * PH;
                 if (rr >= G::IN_ROWS || (unsigned)(y0 - 1 + rr) >= (unsigned)x.h) continue;   // stays zero
                 if (WI == 128) {
-                    split_store(sA + (rr * G::ROW_SLOTS + px + 1) * 16, G::A_PART, v[i]);
+                    split_store_m<BF>(sA + (rr * G::ROW_SLOTS + px + 1) * 16, G::A_PART, v[i]);
                 } else {
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) {
                         const int xd = px - kx + 1;                              // copy kx holds in[x + kx - 1] at slot x
-                        if ((unsigned)xd < (unsigned)WI) split_store(sA + kx * G::A_COPY + (rr * WI + xd) * 16, G::A_PART, v[i]);
+                        if ((unsigned)xd < (unsigned)WI) split_store_m<BF>(sA + kx * G::A_COPY + (rr * WI + xd) * 16, G::A_PART, v[i]);
                     }
                 }
             }
@@ -188,7 +231,7 @@ conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const f
         }
     } else if (lane == 0) {
         // ================= issuer: weight copies + MMAs =================
-        constexpr uint32_t IDESC = umma_idesc_tf32(128, NT);
+        constexpr uint32_t IDESC = BF ? umma_idesc_bf16(128, NT) : umma_idesc_tf32(128, NT);
         auto copy_b = [&](int kb) {
             const int buf = kb & 1;
             const uint32_t bar = smem_u32(&bars[2 + buf]);
@@ -216,10 +259,9 @@ conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const f
                     const uint64_t dA_hi = dA0 + (uint64_t)(a_off >> 4), dA_lo = dA_hi + (G::A_PART >> 4);
                     const uint64_t dB_hi = dB0 + (uint64_t)((tap * 2 * G::B_TAP) >> 4), dB_lo = dB_hi + (G::B_TAP >> 4);
                     const uint32_t d = tmem + t * NT;
-                    if (tap == 0) umma_tf32(d, dA_hi, dB_hi, IDESC, kb > 0);
-                    else umma_tf32_acc(d, dA_hi, dB_hi, IDESC);
-                    umma_tf32_acc(d, dA_hi, dB_lo, IDESC);
-                    umma_tf32_acc(d, dA_lo, dB_hi, IDESC);
+                    umma_ss<BF>(d, dA_hi, dB_hi, IDESC, tap > 0 || kb > 0);
+                    umma_ss<BF>(d, dA_hi, dB_lo, IDESC, true);
+                    umma_ss<BF>(d, dA_lo, dB_hi, IDESC, true);
                 }
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[4 + buf])) : "memory");
@@ -270,15 +312,20 @@ conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const f
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(G::TMEM_COLS) : "memory");
 }
 
-template <int WI, int NT = 64>
-static int launch_conv3x3(const View<const float>& xv, const float* packed, const float* bias, const View<float>& ov, cudaStream_t st) {
+template <int WI, int NT, bool BF>
+static int launch_conv3x3_m(const View<const float>& xv, const float* packed, const float* bias, const View<float>& ov, cudaStream_t st) {
     using G = CvGeo<WI, NT>;
-    const int ncob = ceil_div(ov.c, NT), nkb = ceil_div(xv.c, CV_KB);
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<WI, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+    const int ncob = ceil_div(ov.c, NT), nkb = ceil_div(xv.c, CvMath<BF>::KB);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<WI, NT, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
     if (e != cudaSuccess) { set_error("conv3x3_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
     dim3 grid(ceil_div(ov.h, G::ROWS), ncob, ov.n);
-    conv3x3_tc_kernel<WI, NT><<<grid, CV_PRODUCERS + 32, G::SMEM, st>>>(xv, packed, bias, ov, nkb);
+    conv3x3_tc_kernel<WI, NT, BF><<<grid, CV_PRODUCERS + 32, G::SMEM, st>>>(xv, packed, bias, ov, nkb);
     return FFWM_OK;
+}
+template <int WI, int NT = 64>
+static int launch_conv3x3(const View<const float>& xv, const float* packed, const float* bias, const View<float>& ov, cudaStream_t st) {
+    return opt(OPT_CONV_MATH) ? launch_conv3x3_m<WI, NT, true>(xv, packed, bias, ov, st)
+                              : launch_conv3x3_m<WI, NT, false>(xv, packed, bias, ov, st);
 }
 
 }  // namespace ffwm
@@ -287,7 +334,8 @@ static bool cv_nt_ok(int nt) { return nt == 64 || nt == 128; }
 
 extern "C" int64_t ffwm_conv3x3_packed_floats_nt(int cout, int cin, int nt) {
     if (cout <= 0 || cin <= 0 || !cv_nt_ok(nt)) return 0;
-    const int64_t ncob = (cout + nt - 1) / nt, nkb = (cin + ffwm::CV_KB - 1) / ffwm::CV_KB;
+    const int kbs = ffwm::opt(ffwm::OPT_CONV_MATH) ? 16 : 8;                  // channels per K block of the selected operand math
+    const int64_t ncob = (cout + nt - 1) / nt, nkb = (cin + kbs - 1) / kbs;
     return ncob * nkb * (2 * 9 * 2 * nt * 4);                                 // CvGeo::B_STAGE / 4 floats per (cob, kb)
 }
 extern "C" int64_t ffwm_conv3x3_packed_floats(int cout, int cin) { return ffwm_conv3x3_packed_floats_nt(cout, cin, 64); }
@@ -304,10 +352,15 @@ extern "C" int ffwm_conv3x3_pack_weights_nt(const ffwm_tensor4* weight, int dgra
     const int blocks = (int)std::min<int64_t>((pairs + 255) / 256, 4096);
     const float* wp = static_cast<const float*>(weight->data);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (nt == 64)
-        conv3x3_pack_kernel<64><<<blocks, 256, 0, st>>>(wp, packed, cout, cin, dgrad, weight->stride[0], weight->stride[1], weight->stride[2], weight->stride[3]);
-    else
-        conv3x3_pack_kernel<128><<<blocks, 256, 0, st>>>(wp, packed, cout, cin, dgrad, weight->stride[0], weight->stride[1], weight->stride[2], weight->stride[3]);
+    const int64_t s0 = weight->stride[0], s1 = weight->stride[1], s2 = weight->stride[2], s3 = weight->stride[3];
+    if (opt(OPT_CONV_MATH)) {
+        __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(packed);
+        if (nt == 64) conv3x3_pack_bf_kernel<64><<<blocks, 256, 0, st>>>(wp, pb, cout, cin, dgrad, s0, s1, s2, s3);
+        else conv3x3_pack_bf_kernel<128><<<blocks, 256, 0, st>>>(wp, pb, cout, cin, dgrad, s0, s1, s2, s3);
+    } else {
+        if (nt == 64) conv3x3_pack_kernel<64><<<blocks, 256, 0, st>>>(wp, packed, cout, cin, dgrad, s0, s1, s2, s3);
+        else conv3x3_pack_kernel<128><<<blocks, 256, 0, st>>>(wp, packed, cout, cin, dgrad, s0, s1, s2, s3);
+    }
     return check_launch("conv3x3_pack_weights");
 }
 extern "C" int ffwm_conv3x3_pack_weights(const ffwm_tensor4* weight, int dgrad, float* packed, int64_t packed_floats, void* stream) {

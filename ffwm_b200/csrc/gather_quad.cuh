@@ -273,7 +273,7 @@ static int launch_gather_quad(const P& pol, int n, int h, int w, cudaStream_t st
     if (e != cudaSuccess) { set_error("gather_quad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
     const View<const float>& src = pol.src();
     const int vec = src.sw == 1 && (src.w & 3) == 0 && (src.sh & 3) == 0 && (src.sc & 3) == 0 && (src.sb & 3) == 0 &&
-                    (reinterpret_cast<uintptr_t>(src.p) & 15) == 0 && !getenv("FFWM_GQ_SCALAR_FILL");
+                    (reinterpret_cast<uintptr_t>(src.p) & 15) == 0 && !opt(OPT_GQ_SCALAR_FILL);
     dim3 grid(ceil_div(w, GQ_TW), ceil_div(h, GQ_TH), n);
     gather_quad_kernel<P><<<grid, GQ_THREADS, smem, st>>>(pol, vec);
     return FFWM_OK;
@@ -286,11 +286,11 @@ static int launch_gather_quad(const P& pol, int n, int h, int w, cudaStream_t st
 // memory is round-2 work.)
 
 inline bool gather_quad_applicable(int n, int c, int h, int w, const View<const float>& src) {
-    if (getenv("FFWM_DISABLE_TILED") || getenv("FFWM_DISABLE_QUAD")) return false;
+    if (opt(OPT_DISABLE_TILED) || opt(OPT_DISABLE_QUAD)) return false;
     if (src.sh < 0 || src.sw < 0 || c < 16 || n > 65535) return false;
     if ((int64_t)(src.h - 1) * src.sh + (int64_t)(src.w - 1) * src.sw >= (1 << 30)) return false;
     if (ceil_div(h, GQ_TH) > 65535) return false;
-    if (getenv("FFWM_FORCE_TILED")) return true;          // tests: small ragged shapes through the tiled kernels
+    if (opt(OPT_FORCE_TILED)) return true;          // tests: small ragged shapes through the tiled kernels
     const int64_t tiles = (int64_t)ceil_div(w, GQ_TW) * ceil_div(h, GQ_TH) * n;
     return tiles >= sm_count() / 2;
 }

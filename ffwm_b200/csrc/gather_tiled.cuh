@@ -113,7 +113,7 @@ __device__ __forceinline__ float gt_packed_reduce(float (&v)[N], int lane) {
 }
 
 inline bool gather_tiled_applicable(int n, int c, int h, int w, const View<const float>& src) {
-    if (getenv("FFWM_DISABLE_TILED")) return false;
+    if (opt(OPT_DISABLE_TILED)) return false;
     if (src.sh < 0 || src.sw < 0 || c < 16 || n > 65535) return false;
     const int64_t tiles = (int64_t)ceil_div(w, GT_TW) * ceil_div(h, GT_TH) * n;
     return tiles >= sm_count() / 2 && ceil_div(h, GT_TH) <= 65535;

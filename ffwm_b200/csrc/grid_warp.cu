@@ -314,14 +314,14 @@ static int grid_warp_backward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, co
         // grad_images through the tiled scatter when the maps are large and of equal size (a flow
         // that is a perturbed identity then lands inside the tile's halo)
         if (gi.p && img.h == gout.h && img.w == gout.w && scatter_tiled_applicable(gout, gi)) {
-            int rc2 = getenv("FFWM_SCATTER_TILED") ? launch_scatter_tiled(GridWarpScatterGeo{flow, img.h, img.w}, gout, gi, 7, st)
+            int rc2 = opt(OPT_SCATTER_TILED) ? launch_scatter_tiled(GridWarpScatterGeo{flow, img.h, img.w}, gout, gi, 7, st)
                                                    : launch_scatter_rows(GridWarpScatterGeo{flow, img.h, img.w}, gout, gi, st);
             if (rc2) return rc2;
             if ((rc2 = check_launch("grid_warp_backward(tiled scatter)"))) return rc2;
             if (!gf.p) return FFWM_OK;
             gi.p = nullptr;
         }
-        if (!gi.p && gf.p && img.h == gout.h && img.w == gout.w && !getenv("FFWM_DISABLE_TILED_GFLOW") &&
+        if (!gi.p && gf.p && img.h == gout.h && img.w == gout.w && !opt(OPT_DISABLE_TILED_GFLOW) &&
             gather_quad_applicable(gout.n, gout.c, gout.h, gout.w, img)) {
             const int rc2 = launch_gather_quad(GwQuadPolicy{img, flow, gout, gf}, gout.n, gout.h, gout.w, st);
             if (rc2) return rc2;

@@ -956,7 +956,7 @@ static int resample2d_forward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, co
         // rolling-strip gather (roll_gather.cuh): kernel_size 2 and 4, dilation 1
         // measured at the cfg5 point (scripts/roll_ab.py): kernel_size 4 0.89 ms (tiled gather 1.05, direct 1.41);
         // kernel_size 2 0.67 ms against 0.53 ms for the direct kernel, so 4-tap calls stay direct unless forced
-        if ((half == 2 || (half == 1 && getenv("FFWM_FORCE_ROLL"))) && dil == 1 && in1.n >= out.n &&
+        if ((half == 2 || (half == 1 && opt(OPT_FORCE_ROLL))) && dil == 1 && in1.n >= out.n &&
             roll_applicable(out.n, out.c, out.h, out.w, in1, ceil_div(out.c, 32))) {
             const int rc2 = half == 1 ? launch_fwd_roll<1>(in1, in2, out, st) : launch_fwd_roll<2>(in1, in2, out, st);
             if (rc2) return rc2;
@@ -1022,7 +1022,7 @@ static int resample2d_backward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, c
         if (g1.p && (half == 1 || half == 2) && dil >= 1 && hmax >= 2 && scatter_tiled_applicable(gout, g1)) {
             const int ml = hmax + (half - 1) * dil;
             int rc2;
-            if (dil == 1 && !getenv("FFWM_SCATTER_TILED")) {      // row-owner scatter (scatter_rows.cuh)
+            if (dil == 1 && !opt(OPT_SCATTER_TILED)) {      // row-owner scatter (scatter_rows.cuh)
                 if (half == 1) rc2 = launch_scatter_rows(Resample2dScatterGeo<1>{in2, dil, in1.h, in1.w}, gout, g1, st);
                 else rc2 = launch_scatter_rows(Resample2dScatterGeo<2>{in2, dil, in1.h, in1.w}, gout, g1, st);
             } else if (half == 1) rc2 = launch_scatter_tiled(Resample2dScatterGeo<1>{in2, dil, in1.h, in1.w}, gout, g1, ml, st);
@@ -1033,7 +1033,7 @@ static int resample2d_backward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, c
             g1.p = nullptr;
         }
         // flow gradient: accumulate-then-weigh gather (gather_quad.cuh)
-        if (!g1.p && g2.p && (half == 1 || half == 2) && dil == 1 && !getenv("FFWM_DISABLE_TILED_GFLOW") &&
+        if (!g1.p && g2.p && (half == 1 || half == 2) && dil == 1 && !opt(OPT_DISABLE_TILED_GFLOW) &&
             gather_quad_applicable(gout.n, gout.c, gout.h, gout.w, in1)) {
             const int rc2 = half == 1 ? launch_gather_quad(RsQuadPolicy<1>{in1, in2, gout, g2}, gout.n, gout.h, gout.w, st)
                                       : launch_gather_quad(RsQuadPolicy<2>{in1, in2, gout, g2}, gout.n, gout.h, gout.w, st);
@@ -1043,7 +1043,7 @@ static int resample2d_backward_t(const ffwm_tensor4* a, const ffwm_tensor4* b, c
         // dilation > 1: the tiled gather
         if (!g1.p && g2.p && (half == 1 || half == 2) && dil >= 1 && hmax >= 2 &&
             (int64_t)(in1.h - 1) * in1.sh + (int64_t)(in1.w - 1) * in1.sw < (1 << 30) &&
-            gather_tiled_applicable(gout.n, gout.c, gout.h, gout.w, in1) && !getenv("FFWM_DISABLE_TILED_GFLOW")) {
+            gather_tiled_applicable(gout.n, gout.c, gout.h, gout.w, in1) && !opt(OPT_DISABLE_TILED_GFLOW)) {
             const int ml = hmax + (half - 1) * dil;
             const int rc2 = half == 1 ? launch_gflow_tiled<1>(in1, in2, gout, g2, dil, ml, st)
                                       : launch_gflow_tiled<2>(in1, in2, gout, g2, dil, ml, st);

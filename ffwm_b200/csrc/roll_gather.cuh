@@ -88,10 +88,10 @@ __device__ __forceinline__ void rg_store_row(const float* stage, const View<floa
 
 // Applicability of the rolling kernels: fp32, non-negative strides, enough strips to fill the GPU.
 inline bool roll_applicable(int n, int c, int h, int w, const View<const float>& src, int ctas_per_strip) {
-    if (getenv("FFWM_DISABLE_ROLL") || getenv("FFWM_DISABLE_TILED")) return false;
+    if (opt(OPT_DISABLE_ROLL) || opt(OPT_DISABLE_TILED)) return false;
     if (src.sh < 0 || src.sw < 0 || c < 16 || n > 65535 || h < 32) return false;
     if ((int64_t)(src.h - 1) * src.sh + (int64_t)(src.w - 1) * src.sw >= (1 << 30)) return false;
-    if (getenv("FFWM_FORCE_ROLL") || getenv("FFWM_FORCE_TILED")) return true;   // tests: small shapes through the rolling kernels
+    if (opt(OPT_FORCE_ROLL) || opt(OPT_FORCE_TILED)) return true;   // tests: small shapes through the rolling kernels
     const int64_t ctas = (int64_t)ceil_div(w, RG_SW) * n * ctas_per_strip;
     return ctas >= sm_count() / 2;
 }

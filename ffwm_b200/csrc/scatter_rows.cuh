@@ -351,7 +351,7 @@ static int launch_scatter_rows(const Geo& geo, const View<const float>& gout, co
     cudaError_t e = cudaFuncSetAttribute(scatter_rows_kernel<Geo>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("scatter_rows: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
     const int vec_ok = gsrc.sw == 1 && (gsrc.w & 3) == 0 && (gsrc.sh & 3) == 0 && (gsrc.sc & 3) == 0 && (gsrc.sb & 3) == 0 &&
-                       (reinterpret_cast<uintptr_t>(gsrc.p) & 15) == 0 && !getenv("FFWM_SCATTER_SCALAR_FLUSH");
+                       (reinterpret_cast<uintptr_t>(gsrc.p) & 15) == 0 && !opt(OPT_SCATTER_SCALAR_FLUSH);
     dim3 grid(ceil_div(gout.w, ST_TW), ceil_div(gout.h, ST_TH), gout.n);
     scatter_rows_kernel<Geo><<<grid, SR_THREADS, smem, st>>>(geo, gout, gsrc, vec_ok);
     return FFWM_OK;

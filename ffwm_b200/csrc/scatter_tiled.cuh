@@ -258,12 +258,12 @@ scatter_tiled_kernel(Geo geo, View<const float> gout, View<float> gsrc, int ml) 
 
 // The far encoding keeps the in-plane element offset in 23 bits.
 inline bool scatter_tiled_applicable(const View<const float>& gout, const View<float>& gsrc) {
-    if (getenv("FFWM_DISABLE_TILED")) return false;
+    if (opt(OPT_DISABLE_TILED)) return false;
     const int64_t span = (int64_t)(gsrc.h - 1) * (gsrc.sh < 0 ? -gsrc.sh : gsrc.sh) + (int64_t)(gsrc.w - 1) * (gsrc.sw < 0 ? -gsrc.sw : gsrc.sw);
     if (gsrc.sh < 0 || gsrc.sw < 0 || span >= (1 << 23)) return false;
     if (gout.c < 16 || gout.n > 65535) return false;
     if (ceil_div(gout.h, ST_TH) > 65535) return false;
-    if (getenv("FFWM_FORCE_TILED")) return true;          // tests: small ragged shapes through the tiled kernels
+    if (opt(OPT_FORCE_TILED)) return true;          // tests: small ragged shapes through the tiled kernels
     const int64_t tiles = (int64_t)ceil_div(gout.w, ST_TW) * ceil_div(gout.h, ST_TH) * gout.n;
     return tiles >= sm_count() / 2;
 }

@@ -2,6 +2,7 @@
 // (conv3x3_tc.cu: forward + data gradient, conv3x3_wgrad_tc.cu: weight gradient).
 // Every encoding here was validated on a B200 through conv3x3_tc.cu's parity tests.
 #pragma once
+#include <cuda_bf16.h>
 #include <stdint.h>
 
 #include "common.cuh"
@@ -21,6 +22,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major.
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// D = f32, A = B = bf16 (kind::f16: format code 1), both K-major.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
@@ -65,6 +71,41 @@ __device__ __forceinline__ void split_store(unsigned char* d, int part_bytes, co
     hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u); lo.w = v[3] - hi.w;
     *reinterpret_cast<float4*>(d) = hi;
     *reinterpret_cast<float4*>(d + part_bytes) = lo;
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+
+// one MMA, both operands from shared memory, of the kind the operand math uses
+template <bool BF>
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    if (BF) umma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
+    else umma_tf32(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+
+// 8 fp32 -> one 16-byte slot of b1 = bf16_rn(v) and one of b2 = bf16_rn(v - b1); element j at byte 2j.
+__device__ __forceinline__ void split_store_bf(unsigned char* d, int part_bytes, const float* v) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 hb = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);       // .x (low half) = v[2i]
+        const __nv_bfloat162 lb = __floats2bfloat162_rn(v[2 * i] - __low2float(hb), v[2 * i + 1] - __high2float(hb));
+        h[i] = *reinterpret_cast<const uint32_t*>(&hb);
+        l[i] = *reinterpret_cast<const uint32_t*>(&lb);
+    }
+    *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(d + part_bytes) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <bool BF>
+__device__ __forceinline__ void split_store_m(unsigned char* d, int part_bytes, const float* v) {
+    if (BF) split_store_bf(d, part_bytes, v);
+    else split_store(d, part_bytes, v);
 }
 
 }  // namespace ffwm

@@ -17,8 +17,9 @@ import torch.nn.functional as F
 from . import ops
 from .conv import Conv2d
 
-# experimental, unmeasured (csrc/mfm.cu was written after the round-1 GPU budget was spent): off unless asked for
-FUSED_MFM = os.environ.get("FFWM_FUSED_MFM", "0") == "1"
+# max-feature-map as one kernel per direction (csrc/mfm.cu): bit-exact vs torch.max on a B200 (tests/test_mfm_gpu.py), train step
+# 73.4 -> 72.0 ms (profiles/r02b_switches.txt).  FFWM_FUSED_MFM=0 restores the torch ops for A/B runs.
+FUSED_MFM = os.environ.get("FFWM_FUSED_MFM", "1") == "1"
 
 
 class MFMFunction(torch.autograd.Function):

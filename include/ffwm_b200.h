@@ -121,6 +121,13 @@ int ffwm_grid_warp_backward(const ffwm_tensor4* images, const ffwm_tensor4* flow
                             const ffwm_tensor4* grad_images, const ffwm_tensor4* grad_flow,
                             int dtype, void* stream);
 
+/* ---- runtime options (A/B switches and test hooks; no reference counterpart) -------------------------------
+ * Each option NAME ("DISABLE_TILED", "FORCE_TILED", "CONV_MATH", ...: the list is in csrc/common.cuh) is read once
+ * from the environment variable FFWM_<NAME> when the library is first used; launch paths read a cached int.
+ * ffwm_set_option changes it afterwards (process-wide), ffwm_get_option returns it (-1: unknown name). */
+int ffwm_set_option(const char* name, int value);
+int ffwm_get_option(const char* name);
+
 /* ---- 3x3 / stride 1 / pad 1 convolution on the tcgen05 tensor cores (fp32 in/out, 3xTF32) --------
  * Replaces the cuDNN call behind nn.Conv2d(Cin, Cout, 3, 1, 1).forward (models/base_networks.py:218-222,
  * 235-246: the generator's ResidualBlock / ConvBlock convolutions) for maps of width 128, 64, 32 or 16, and — with

@@ -69,8 +69,15 @@ def test_conv_entry_points_validate_without_gpu():
     from ffwm_b200 import _lib
     lib = _lib.lib()
     null = ctypes.c_void_p(0)
+    assert _lib.get_option("CONV_MATH") == 1 and _lib.get_option("DISABLE_TILED") == 0 and _lib.get_option("NO_SUCH") == -1
+    old = _lib.set_option("CONV_MATH", 0)                           # 3xTF32: K blocks of 8 channels
     assert lib.ffwm_conv3x3_packed_floats_nt(195, 195, 64) == lib.ffwm_conv3x3_packed_floats(195, 195) == 4 * 25 * 9216
     assert lib.ffwm_conv3x3_packed_floats_nt(195, 195, 128) == 2 * 25 * 18432
+    _lib.set_option("CONV_MATH", 1)                                 # 3xBF16: K blocks of 16 channels, same bytes each
+    assert lib.ffwm_conv3x3_packed_floats_nt(195, 195, 64) == 4 * 13 * 9216
+    _lib.set_option("CONV_MATH", old)
+    with pytest.raises(ValueError):
+        _lib.set_option("NO_SUCH", 1)
     assert lib.ffwm_conv3x3_packed_floats_nt(195, 195, 96) == 0 and lib.ffwm_conv3x3_packed_floats_nt(0, 8, 64) == 0
     x64, o64 = torch.zeros(1, 8, 4, 64), torch.zeros(1, 128, 4, 64)
     fake = ctypes.c_void_p(16)                                      # non-null "packed" pointer, never dereferenced

@@ -28,7 +28,7 @@ def test_conv3x3_forward_nt128_matches_fp64(b, cin, cout, h):
     out = torch.full((b, cout, h, 128), float("nan"), device=DEV)
     ops.conv3x3_forward(xd, ops.conv3x3_pack_weights(wd, nt=128), bd, out, nt=128)
     torch.cuda.synchronize()
-    assert rel(out.cpu(), want) <= (2e-5 if cin * 9 < 2048 else 5e-5)
+    assert rel(out.cpu(), want) <= (3e-5 if cin * 9 < 2048 else 5e-5)      # default operand math (3xBF16)
     out64 = torch.empty_like(out)
     ops.conv3x3_forward(xd, ops.conv3x3_pack_weights(wd), bd, out64)
     assert rel(out, out64) <= 1e-6      # same MMAs in the same order per output element: expected to agree bit for bit
@@ -44,7 +44,7 @@ def test_conv3x3_dgrad_nt128():
     F.conv2d(x, w, None, padding=1).backward(go)
     gx = torch.empty(b, cin, h, 128, device=DEV)
     ops.conv3x3_forward(go.float().to(DEV), ops.conv3x3_pack_weights(w.float().to(DEV), dgrad=True, nt=128), None, gx, nt=128)
-    assert rel(gx.cpu(), x.grad) <= 2e-5
+    assert rel(gx.cpu(), x.grad) <= 3e-5
 
 
 def test_nt128_rejected_for_other_widths():

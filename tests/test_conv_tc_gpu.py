@@ -1,6 +1,8 @@
-"""tcgen05 3x3 convolution (ffwm_b200/csrc/conv3x3_tc.cu) against PyTorch float64 on the same inputs.
-Tolerance: 2e-5 relative to max|ref| (5e-5 for K = 9*Cin > 2048): the 3xTF32 split gives fp32-level accuracy
-(cuDNN strict fp32 measures 1e-5 on the same inputs, cuDNN TF32 2e-4); SURVEY 7 "hard parts"."""
+"""tcgen05 3x3 convolution (ffwm_b200/csrc/conv3x3_tc.cu) against PyTorch float64 on the same inputs, in both
+operand maths (option CONV_MATH: 0 = 3xTF32 split, 1 = 3xBF16 split, the default).
+Tolerance, relative to max|ref|: 2e-5 (5e-5 for K = 9*Cin > 2048) for 3xTF32, 3e-5 (5e-5) for 3xBF16 — both splits
+give fp32-level accuracy (cuDNN strict fp32 measures 1e-5..5e-5 on the same inputs, cuDNN TF32 2e-4..3e-4); the path's
+contract is 1e-4 (BASELINE north star).  SURVEY 7 "hard parts"."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -13,10 +15,13 @@ def rel(a, b):
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 
 
-@pytest.fixture(scope="module")
-def ops():
-    from ffwm_b200 import ops as o
-    return o
+@pytest.fixture(scope="module", params=[1, 0], ids=["bf16x3", "tf32x3"])
+def ops(request):
+    from ffwm_b200 import _lib, ops as o
+    old = _lib.set_option("CONV_MATH", request.param)
+    o.math_tol = 3e-5 if request.param else 2e-5
+    yield o
+    _lib.set_option("CONV_MATH", old)
 
 
 @pytest.mark.parametrize("b,cin,cout,h,width", [(1, 8, 64, 4, 128), (2, 16, 64, 8, 128), (1, 3, 64, 128, 128), (2, 195, 195, 10, 128),
@@ -35,7 +40,7 @@ def test_conv3x3_forward_matches_fp64(ops, b, cin, cout, h, width):
     out = torch.full((b, cout, h, width), float("nan"), device=DEV)
     ops.conv3x3_forward(xd, packed, bd, out)
     torch.cuda.synchronize()
-    tol = 2e-5 if cin * 9 < 2048 else 5e-5           # fp32 accumulation over K = 9*Cin terms (cuDNN fp32: 1.2e-5 at K=3456)
+    tol = ops.math_tol if cin * 9 < 2048 else 5e-5           # fp32 accumulation over K = 9*Cin terms (cuDNN fp32: 1.2e-5 at K=3456)
     assert rel(out.cpu(), want) <= tol
     out2 = torch.empty_like(out)
     ops.conv3x3_forward(xd, packed, None, out2)
@@ -53,7 +58,7 @@ def test_conv3x3_dgrad_packing(ops, wd):
     packed = ops.conv3x3_pack_weights(w.float().to(DEV), dgrad=True)
     gx = torch.empty(b, cin, h, wd, device=DEV)
     ops.conv3x3_forward(go.float().to(DEV), packed, None, gx)
-    assert rel(gx.cpu(), x.grad) <= 2e-5
+    assert rel(gx.cpu(), x.grad) <= ops.math_tol
 
 
 def test_conv3x3_rejects_other_widths(ops):
@@ -79,8 +84,8 @@ def test_conv_module_autograd_matches_cudnn_fp64():
     wr = m.weight.detach().double().requires_grad_(True)
     br = m.bias.detach().double().requires_grad_(True)
     F.conv2d(xr, wr, br, padding=1).backward(go.double())
-    assert rel(out, F.conv2d(xr, wr, br, padding=1)) <= 2e-5
-    assert rel(x.grad, xr.grad) <= 2e-5
+    assert rel(out, F.conv2d(xr, wr, br, padding=1)) <= 3e-5
+    assert rel(x.grad, xr.grad) <= 3e-5
     assert rel(m.weight.grad, wr.grad) <= 1e-4 and rel(m.bias.grad, br.grad) <= 1e-4
     # not eligible (width 48): falls back to the library convolution, same module
     y = m(torch.randn(1, 20, 8, 48, device=DEV))

@@ -385,21 +385,15 @@ def test_resample2d_tiled_scatter_matches_direct_and_oracle(ops, oracle_warp, ks
     d = [t.to(DEV) for t in (in1, in2, go)]
     g1_t, g2_t = torch.zeros_like(d[0]), torch.empty_like(d[1])
     ops.resample2d_backward(d[0], d[1], d[2], g1_t, g2_t, ks, 1)
-    os.environ["FFWM_DISABLE_TILED"] = "1"
-    try:
+    with _env(FFWM_DISABLE_TILED="1"):
         g1_d, g2_d = torch.zeros_like(d[0]), torch.empty_like(d[1])
         ops.resample2d_backward(d[0], d[1], d[2], g1_d, g2_d, ks, 1)
-    finally:
-        del os.environ["FFWM_DISABLE_TILED"]
     assert rel_err(g1_t, g1_d) <= 2e-5
     assert rel_err(g2_t, g2_d) <= 5e-5                   # tiled gather vs direct kernel: summation order only
     out_t, out_d = torch.empty_like(d[0]), torch.empty_like(d[0])
     ops.resample2d_forward(d[0], d[1], out_t, ks, 1)
-    os.environ["FFWM_DISABLE_TILED"] = "1"
-    try:
+    with _env(FFWM_DISABLE_TILED="1"):
         ops.resample2d_forward(d[0], d[1], out_d, ks, 1)
-    finally:
-        del os.environ["FFWM_DISABLE_TILED"]
     assert rel_err(out_t, out_d) <= 1e-6
     assert rel_err(out_t.cpu(), oracle_warp.resample2d_forward(in1, in2, ks, 1)) <= 1e-5
     w1, w2 = oracle_warp.resample2d_backward(in1, in2, go, ks, 1)
@@ -422,21 +416,14 @@ def test_grid_warp_tiled_scatter_matches_direct_and_torch(ops, noise):
     d = [t.to(DEV) for t in (img, grid, go)]
     gi_t, gf_t = torch.zeros_like(d[0]), torch.empty_like(d[1])
     ops.grid_warp_backward(d[0], d[1], d[2], gi_t, gf_t)
-    os.environ["FFWM_DISABLE_TILED"] = "1"
-    try:
+    with _env(FFWM_DISABLE_TILED="1"):
         gi_d, gf_d = torch.zeros_like(d[0]), torch.empty_like(d[1])
         ops.grid_warp_backward(d[0], d[1], d[2], gi_d, gf_d)
-    finally:
-        del os.environ["FFWM_DISABLE_TILED"]
     assert rel_err(gi_t, gi_d) <= 2e-5 and rel_err(gf_t, gf_d) <= 5e-5
     out_t, out_d = torch.empty_like(d[0]), torch.empty_like(d[0])
-    os.environ["FFWM_GRID_WARP_TILED_FWD"] = "1"          # the tiled forward is opt-in
-    try:
-        ops.grid_warp_forward(d[0], d[1], out_t)
-    finally:
-        del os.environ["FFWM_GRID_WARP_TILED_FWD"]
+    ops.grid_warp_forward(d[0], d[1], out_t)
     ops.grid_warp_forward(d[0], d[1], out_d)
-    assert torch.equal(out_t, out_d)                      # same arithmetic, term by term
+    assert torch.equal(out_t, out_d)                      # deterministic
     x = img.double().requires_grad_(True)
     gr = grid.double().requires_grad_(True)
     torch.nn.functional.grid_sample(x, gr.permute(0, 2, 3, 1), align_corners=False).backward(go.double())
@@ -459,12 +446,9 @@ def test_block_extractor_tiled_paths_match_direct_and_oracle(ops, oracle_warp, k
     assert rel_err(out.cpu(), oracle_warp.block_extractor_forward(src, flow, k)) <= 1e-6
     gs_t, gf_t = torch.zeros_like(d[0]), torch.empty_like(d[1])
     ops.block_extractor_backward(d[0], d[1], d[2], gs_t, gf_t, k)
-    os.environ["FFWM_DISABLE_TILED"] = "1"
-    try:
+    with _env(FFWM_DISABLE_TILED="1"):
         gs_d, gf_d = torch.zeros_like(d[0]), torch.empty_like(d[1])
         ops.block_extractor_backward(d[0], d[1], d[2], gs_d, gf_d, k)
-    finally:
-        del os.environ["FFWM_DISABLE_TILED"]
     assert rel_err(gs_t, gs_d) <= 2e-5 and rel_err(gf_t, gf_d) <= 5e-5
     ws, wf = oracle_warp.block_extractor_backward(src, flow, go, k)
     assert rel_err(gs_t.cpu(), ws) <= 1e-4 and rel_err(gf_t.cpu(), wf) <= 1e-4
@@ -472,23 +456,20 @@ def test_block_extractor_tiled_paths_match_direct_and_oracle(ops, oracle_warp, k
 
 # --------------------------------- tiled kernel generations on small ragged shapes (forced) vs direct kernels / oracle
 class _env:
+    """Runtime options of the library for the duration of a block (ffwm_set_option; the library reads the FFWM_*
+    environment only once, at load).  _env(FFWM_FORCE_TILED="1") -> option FORCE_TILED = 1, restored on exit."""
+
     def __init__(self, **kv):
         self.kv = kv
 
     def __enter__(self):
-        self.old = {k: os.environ.get(k) for k in self.kv}
-        for k, v in self.kv.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
+        from ffwm_b200 import _lib
+        self.old = {k: _lib.set_option(k, 0 if v is None else int(v)) for k, v in self.kv.items()}
 
     def __exit__(self, *a):
+        from ffwm_b200 import _lib
         for k, v in self.old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
+            _lib.set_option(k, v)
 
 
 @pytest.mark.gpu
