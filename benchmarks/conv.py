@@ -59,27 +59,31 @@ def wgrad_bench(out_path):
             ops.conv3x3_wgrad(x, go, gw)
 
         t_mine = timeit(mine)
+        gw2 = torch.empty_like(w)
+        t_gen = timeit(lambda: ops.conv_wgrad(go, x, gw2, 1, 1))
         w64 = w.double().requires_grad_()
         F.conv2d(x.double(), w64, None, padding=1).backward(go.double())
         ref = w64.grad
         err_mine = float((gw.double() - ref).abs().max() / ref.abs().max())
+        err_gen = float((gw2.double() - ref).abs().max() / ref.abs().max())
         torch.backends.cudnn.allow_tf32 = False
         t_fp32 = timeit(lambda: cudnn_wgrad(go, x, w))
         err_fp32 = float((cudnn_wgrad(go, x, w).double() - ref).abs().max() / ref.abs().max())
         torch.backends.cudnn.allow_tf32 = True
         t_tf32 = timeit(lambda: cudnn_wgrad(go, x, w))
         err_tf32 = float((cudnn_wgrad(go, x, w).double() - ref).abs().max() / ref.abs().max())
-        rows.append(dict(shape=name, cin=cin, cout=cout, gflop=flop / 1e9, ms_tcgen05=t_mine, ms_cudnn_fp32=t_fp32,
+        rows.append(dict(shape=name, cin=cin, cout=cout, gflop=flop / 1e9, ms_tcgen05=t_mine, ms_cudnn_fp32=t_fp32, ms_general=t_gen,
+                         tflops_general=flop / t_gen / 1e9, err_general=err_gen,
                          ms_cudnn_tf32=t_tf32, tflops_tcgen05=flop / t_mine / 1e9, err_tcgen05=err_mine,
                          err_cudnn_fp32=err_fp32, err_cudnn_tf32=err_tf32))
         del ref, w64
     os.makedirs(os.path.dirname(out_path), exist_ok=True)
     json.dump(rows, open(out_path, "w"), indent=1)
-    print("%-22s %8s %8s %8s %8s %9s %9s %9s" % ("wgrad shape", "tc ms", "fp32 ms", "tf32 ms", "TF/s", "err tc", "err fp32", "err tf32"))
+    print("%-22s %8s %8s %8s %8s %8s %9s %9s %9s %9s" % ("wgrad shape", "3x3 ms", "gen ms", "fp32 ms", "tf32 ms", "gen TF/s", "err 3x3", "err gen", "err fp32", "err tf32"))
     for r in rows:
-        print("%-22s %8.3f %8.3f %8.3f %8.1f %9.1e %9.1e %9.1e" % (
-            r["shape"], r["ms_tcgen05"], r["ms_cudnn_fp32"], r["ms_cudnn_tf32"], r["tflops_tcgen05"],
-            r["err_tcgen05"], r["err_cudnn_fp32"], r["err_cudnn_tf32"]))
+        print("%-22s %8.3f %8.3f %8.3f %8.3f %8.1f %9.1e %9.1e %9.1e %9.1e" % (
+            r["shape"], r["ms_tcgen05"], r["ms_general"], r["ms_cudnn_fp32"], r["ms_cudnn_tf32"], r["tflops_general"],
+            r["err_tcgen05"], r["err_general"], r["err_cudnn_fp32"], r["err_cudnn_tf32"]))
 
 
 def nt128_bench(out_path):
@@ -107,12 +111,66 @@ def nt128_bench(out_path):
             r["shape"], r["ms_nt64"], r["tflops_nt64"], r["ms_nt128"], r["tflops_nt128"], r["max_abs_diff"]))
 
 
+GEN_SHAPES = (  # name, b, cin, cout, h, k, stride, pad, transposed
+    ("G stem 7x7 3->64 @128", 8, 3, 64, 128, 7, 1, 3, 0), ("G e1 4x4s2 64->128 @128", 8, 64, 128, 128, 4, 2, 1, 0),
+    ("G e2 4x4s2 128->256 @64", 8, 128, 256, 64, 4, 2, 1, 0), ("G 1x1 195->195 @128", 8, 195, 195, 128, 1, 1, 0, 0),
+    ("3x3 384->384 @16", 8, 384, 384, 16, 3, 1, 1, 0), ("F 3x3s2 64->128 @64", 8, 64, 128, 64, 3, 2, 1, 0),
+    ("F 3x3s2 256->512 @16", 8, 256, 512, 16, 3, 2, 1, 0), ("F 3x3 512->512 @8", 8, 512, 512, 8, 3, 1, 1, 0),
+    ("F 3x3 1024->1024 @2", 8, 1024, 1024, 2, 3, 1, 1, 0), ("F deconv 1024->512 @2", 8, 1024, 512, 2, 4, 2, 1, 1),
+    ("F deconv 770->128 @8", 8, 770, 128, 8, 4, 2, 1, 1), ("F deconv 194->32 @32", 8, 194, 32, 32, 4, 2, 1, 1),
+    ("L 5x5 1->96 @128", 8, 1, 96, 128, 5, 1, 2, 0), ("L 3x3 192->384 @16", 8, 192, 384, 16, 3, 1, 1, 0),
+    ("VGG 3x3 512->512 @16", 8, 512, 512, 16, 3, 1, 1, 0), ("VGG 3x3 512->512 @8", 8, 512, 512, 8, 3, 1, 1, 0),
+    ("D 3x3s2 3->64 @128", 8, 3, 64, 128, 3, 2, 1, 0))
+
+
+def gen_bench(out_path):
+    """csrc/conv_gen_tc.cu (incl. its weight packing) vs cuDNN strict fp32 and TF32 on the non-3x3-stride-1 shapes."""
+    from ffwm_b200 import ops
+    dev = torch.device("cuda", 0)
+    torch.backends.cudnn.benchmark = True
+    rows = []
+    for name, b, cin, cout, r, k, s, p, tr in GEN_SHAPES:
+        x = torch.randn(b, cin, r, r, device=dev)
+        if tr:
+            w = torch.randn(cin, cout, k, k, device=dev) / (cin * k * k / s / s) ** 0.5
+            lib = lambda: F.conv_transpose2d(x, w, None, stride=s, padding=p)
+            ref = F.conv_transpose2d(x.double(), w.double(), None, stride=s, padding=p)
+        else:
+            w = torch.randn(cout, cin, k, k, device=dev) / (cin * k * k) ** 0.5
+            lib = lambda: F.conv2d(x, w, None, stride=s, padding=p)
+            ref = F.conv2d(x.double(), w.double(), None, stride=s, padding=p)
+        out = torch.empty(ref.shape, device=dev)
+        packed = ops.conv_pack_weights(w, bool(tr), s, p, bool(tr))
+        flop = 2.0 * ref.numel() / cout * cout * cin * k * k / (s * s if tr else 1)
+        t = timeit(lambda: ops.conv_forward(x, packed, None, out, k, k, s, p, bool(tr)))
+        t_pack = timeit(lambda: ops.conv_pack_weights(w, bool(tr), s, p, bool(tr)))
+        err = float((out.double() - ref).abs().max() / ref.abs().max())
+        torch.backends.cudnn.allow_tf32 = False
+        t32 = timeit(lib)
+        e32 = float((lib().double() - ref).abs().max() / ref.abs().max())
+        torch.backends.cudnn.allow_tf32 = True
+        ttf = timeit(lib)
+        rows.append(dict(shape=name, gflop=flop / 1e9, ms_tcgen05=t, ms_pack=t_pack, tflops=flop / t / 1e9, err=err,
+                         ms_cudnn_fp32=t32, err_cudnn_fp32=e32, ms_cudnn_tf32=ttf))
+        del ref
+    os.makedirs(os.path.dirname(out_path), exist_ok=True)
+    json.dump(rows, open(out_path, "w"), indent=1)
+    print("%-26s %7s | %8s %8s %7s %8s | %8s %8s | %8s" % ("shape", "GFLOP", "tc ms", "pack ms", "TF/s", "err", "cudnn32", "err", "cudnnTF"))
+    for r in rows:
+        print("%-26s %7.2f | %8.4f %8.4f %7.1f %8.1e | %8.4f %8.1e | %8.4f" % (
+            r["shape"], r["gflop"], r["ms_tcgen05"], r["ms_pack"], r["tflops"], r["err"], r["ms_cudnn_fp32"], r["err_cudnn_fp32"],
+            r["ms_cudnn_tf32"]))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--wgrad", action="store_true", help="measure the experimental tcgen05 weight gradient instead")
     ap.add_argument("--nt128", action="store_true", help="A/B the experimental 128-channel CTA tile on the W = 128 shapes")
+    ap.add_argument("--gen", action="store_true", help="the general kernel (conv_gen_tc.cu) on the other shapes of the path")
     args = ap.parse_args()
+    if args.gen:
+        return gen_bench(args.out or os.path.join(ROOT, "gpurun_out", "conv_gen.json"))
     if args.wgrad:
         return wgrad_bench(args.out or os.path.join(ROOT, "gpurun_out", "conv_wgrad.json"))
     if args.nt128:
@@ -132,14 +190,12 @@ def main():
         ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
         row = dict(shape=name, cin=cin, cout=cout, gflop=flop / 1e9, nt=nt)
         for math, tag in ((1, "bf16x3"), (0, "tf32x3")):
-            old = _lib.set_option("CONV_MATH", math)
-            packed = ops.conv3x3_pack_weights(w, nt=nt)
-            t = timeit(lambda: ops.conv3x3_forward(x, packed, b, out, nt=nt))
+            packed = ops.conv3x3_pack_weights(w, nt=nt, math=math)
+            t = timeit(lambda: ops.conv3x3_forward(x, packed, b, out, nt=nt, math=math))
             row["ms_" + tag] = t
             row["tflops_" + tag] = flop / t / 1e9
             row["err_" + tag] = float((out.double() - ref).abs().max() / ref.abs().max())
-            row["ms_pack_" + tag] = timeit(lambda: ops.conv3x3_pack_weights(w, nt=nt))
-            _lib.set_option("CONV_MATH", old)
+            row["ms_pack_" + tag] = timeit(lambda: ops.conv3x3_pack_weights(w, nt=nt, math=math))
         torch.backends.cudnn.allow_tf32 = False
         row["ms_cudnn_fp32"] = timeit(lambda: F.conv2d(x, w, b, padding=1))
         row["err_cudnn_fp32"] = float((F.conv2d(x, w, b, padding=1).double() - ref).abs().max() / ref.abs().max())

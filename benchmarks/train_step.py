@@ -116,36 +116,43 @@ class TrainStepWorkload:
 
     def kernel_table(self, pk):
         """Those kernels timed alone, live, with CUDA events on the launching stream (operands 100+ MB at 128x128:
-        larger than L2 together with the output).  `TFLOP/s` counts the algorithmic 2*B*H*W*Cin*Cout*9 once;
-        the kernel issues three TF32 MMAs per product (3xTF32 split), `tensor_issued_TFLOP/s`.  Never fatal:
-        a failure here is reported in the table instead of losing the bench line."""
+        larger than L2 together with the output), in both operand maths: 3xTF32 (what the step's forward passes run)
+        and 3xBF16 (its data gradients).  `TFLOP/s` counts the algorithmic 2*B*H*W*Cin*Cout*9 once; the kernel issues
+        three MMAs per product, `tensor_issued_TFLOP/s`, compared with the measured dense rate of that MMA kind.
+        Never fatal: a failure here is reported in the table instead of losing the bench line."""
         try:
-            from ffwm_b200 import ops
+            from ffwm_b200 import _lib, ops
             rows = {}
+            tf32_peak = None
             for name, cin, cout, r in self.KERNEL_SHAPES:
                 x = torch.randn(BATCH, cin, r, r, device=self.dev)
                 w = torch.randn(cout, cin, 3, 3, device=self.dev) / (cin * 9) ** 0.5
                 out = torch.empty(BATCH, cout, r, r, device=self.dev)
-                packed = ops.conv3x3_pack_weights(w)
-                for _ in range(3):
-                    ops.conv3x3_forward(x, packed, None, out)
-                iters = 10
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                torch.cuda.synchronize()
-                e0.record()
-                for _ in range(iters):
-                    ops.conv3x3_forward(x, packed, None, out)
-                e1.record()
-                torch.cuda.synchronize()
-                ms = e0.elapsed_time(e1) / iters
-                flop = 2.0 * BATCH * r * r * cin * cout * 9
-                tf = flop / (ms * 1e-3) / 1e12
-                rows[name] = {"ms": round(ms, 4), "GFLOP": round(flop / 1e9, 2), "TFLOP/s": round(tf, 1),
-                              "tensor_issued_TFLOP/s": round(3 * tf, 1),
-                              "frac_bf16_peak_issued": round(3 * tf / pk["bf16_tflops"], 4) if pk.get("bf16_tflops") else None}
-                del x, w, out, packed
-            rows["note"] = ("timed alone after the step (burst clocks); peak = measured dense bf16 burst rate, the kernel's math "
-                            "is TF32 (half the bf16 rate on paper) issued three times per product for fp32-level accuracy")
+                nt = 128 if (r == 128 and cout > 64) else 64
+                row = {"GFLOP": round(2.0 * BATCH * r * r * cin * cout * 9 / 1e9, 2), "nt": nt}
+                for math, tag in ((_lib.MATH_BF16X3, "bf16x3"), (_lib.MATH_TF32X3, "tf32x3")):
+                    packed = ops.conv3x3_pack_weights(w, nt=nt, math=math)
+                    for _ in range(3):
+                        ops.conv3x3_forward(x, packed, None, out, nt=nt, math=math)
+                    iters = 10
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize()
+                    e0.record()
+                    for _ in range(iters):
+                        ops.conv3x3_forward(x, packed, None, out, nt=nt, math=math)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms = e0.elapsed_time(e1) / iters
+                    tf = row["GFLOP"] / ms
+                    row[tag] = {"ms": round(ms, 4), "TFLOP/s": round(tf, 1), "tensor_issued_TFLOP/s": round(3 * tf, 1)}
+                    if math == _lib.MATH_BF16X3 and pk.get("bf16_tflops"):
+                        row[tag]["frac_bf16_peak_issued"] = round(3 * tf / pk["bf16_tflops"], 4)
+                    del packed
+                rows[name] = row
+                del x, w, out
+            rows["note"] = ("timed alone after the step (burst clocks); three MMAs are issued per product for fp32-level accuracy; "
+                            "bf16x3 fractions are against the measured dense bf16 burst rate (MEASURED_PEAKS.json), the TF32 rate "
+                            "measured in this run is in measured_tensor_peaks")
             return rows
         except Exception as e:          # noqa: BLE001 - the bench line must survive
             return {"error": repr(e)}

@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libffwm_b200.so")
 
 FFWM_F32, FFWM_F64 = 0, 1
-ABI_VERSION = 1
+MATH_TF32X3, MATH_BF16X3 = 0, 1          # enum FFWM_MATH_* (operand split of the tcgen05 convolutions)
+ABI_VERSION = 2
 
 
 class Tensor4(ctypes.Structure):
@@ -41,13 +42,15 @@ SIGNATURES = {
     "ffwm_local_attn_reshape_backward": [_T4P, _T4P, _I, _I, _VP],
     "ffwm_grid_warp_forward": [_T4P, _T4P, _T4P, _I, _VP],
     "ffwm_grid_warp_backward": [_T4P, _T4P, _T4P, _T4P, _T4P, _I, _VP],
-    "ffwm_conv3x3_packed_floats": [_I, _I],
-    "ffwm_conv3x3_pack_weights": [_T4P, _I, _VP, ctypes.c_int64, _VP],
-    "ffwm_conv3x3_forward": [_T4P, _VP, _VP, _T4P, _VP],
-    "ffwm_conv3x3_wgrad": [_T4P, _T4P, _T4P, _VP, _VP],
-    "ffwm_conv3x3_packed_floats_nt": [_I, _I, _I],
-    "ffwm_conv3x3_pack_weights_nt": [_T4P, _I, _VP, ctypes.c_int64, _I, _VP],
-    "ffwm_conv3x3_forward_nt": [_T4P, _VP, _VP, _T4P, _I, _VP],
+    "ffwm_conv3x3_packed_floats": [_I, _I, _I, _I],
+    "ffwm_conv3x3_pack_weights": [_T4P, _I, _VP, ctypes.c_int64, _I, _I, _VP],
+    "ffwm_conv3x3_forward": [_T4P, _VP, _VP, _T4P, _I, _I, _VP],
+    "ffwm_conv3x3_wgrad": [_T4P, _T4P, _T4P, _VP, _I, _VP],
+    "ffwm_conv_packed_bytes": [_I, _I, _I, _I, _I],
+    "ffwm_conv_pack_weights": [_T4P, _I, _I, _I, _I, _I, _VP, ctypes.c_int64, _VP],
+    "ffwm_conv_forward": [_T4P, _VP, _VP, _T4P, _I, _I, _I, _I, _I, _I, _VP],
+    "ffwm_conv_wgrad_workspace_bytes": [_I] * 11,
+    "ffwm_conv_wgrad": [_T4P, _T4P, _T4P, _I, _I, _VP, ctypes.c_int64, _VP],
     "ffwm_mfm_forward": [_VP, _VP, ctypes.c_int64, ctypes.c_int64, _VP],
     "ffwm_mfm_backward": [_VP, _VP, _VP, ctypes.c_int64, ctypes.c_int64, _VP],
     "ffwm_guided_filter_forward": [_VP, _VP, _VP, _VP, _VP, ctypes.c_int64, _I, _I, _I, ctypes.c_float, _VP],
@@ -77,7 +80,8 @@ def lib():
             fn.argtypes = argtypes
             fn.restype = {"ffwm_last_error": ctypes.c_char_p, "ffwm_kernel_launches": ctypes.c_ulonglong,
                           "ffwm_conv3x3_packed_floats": ctypes.c_int64,
-                          "ffwm_conv3x3_packed_floats_nt": ctypes.c_int64}.get(name, ctypes.c_int)
+                          "ffwm_conv_packed_bytes": ctypes.c_int64,
+                          "ffwm_conv_wgrad_workspace_bytes": ctypes.c_int64}.get(name, ctypes.c_int)
         if l.ffwm_abi_version() != ABI_VERSION:
             raise ImportError("ffwm_b200: ABI version mismatch (library %d, binding %d)"
                               % (l.ffwm_abi_version(), ABI_VERSION))

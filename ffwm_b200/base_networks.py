@@ -27,7 +27,7 @@ import torch.nn.functional as F
 from torch.nn.utils import spectral_norm
 
 from . import external_function as EF
-from .conv import Conv2d
+from .conv import Conv2d, ConvTranspose2d
 from .spectral import batch_spectral_norm
 
 LRELU_SLOPE = 0.2
@@ -52,7 +52,7 @@ def initialize_msra(modules):
 # ---------------------------------------------------------------------------------------------
 def _unit(cin, cout, norm, k=3, stride=1, transposed=False, bias=True):
     if transposed:
-        op = nn.ConvTranspose2d(cin, cout, kernel_size=4, stride=2, padding=1, bias=True)
+        op = ConvTranspose2d(cin, cout, kernel_size=4, stride=2, padding=1, bias=True)
     else:
         op = Conv2d(cin, cout, kernel_size=k, stride=stride, padding=(k - 1) // 2, bias=bias)
     return nn.Sequential(op, norm(cout), nn.LeakyReLU(LRELU_SLOPE, inplace=True))
@@ -107,7 +107,7 @@ class FlowNet(nn.Module):
         for lvl in (6, 5, 4, 3, 2, 1, 0):
             setattr(self, "predict_flow%d" % lvl, predict_flow(head_in[lvl]))
         for lvl in (6, 5, 4, 3, 2, 1):
-            setattr(self, "upsampled_flow%d_to_%d" % (lvl, lvl - 1), nn.ConvTranspose2d(2, 2, 4, 2, 1))
+            setattr(self, "upsampled_flow%d_to_%d" % (lvl, lvl - 1), ConvTranspose2d(2, 2, 4, 2, 1))
         initialize_msra(self.modules())
 
     def forward(self, x):
@@ -205,7 +205,7 @@ def ConvBlock(inc, outc, ks=3, s=1, p=0, activ='lrelu', norm='bn', res=0, resk=3
 
 
 def DeConvBlock(inc, outc, ks=3, s=1, p=0, op=0, activ='relu', norm='bn', res=0, resk=3, bn=True, sn=False):
-    return _block([_maybe_sn(nn.ConvTranspose2d(inc, outc, ks, s, p, op), sn)], outc, activ, norm, res, resk, bn, sn)
+    return _block([_maybe_sn(ConvTranspose2d(inc, outc, ks, s, p, op), sn)], outc, activ, norm, res, resk, bn, sn)
 
 
 def PixelSuffleBlock(inc, outc, ks=3, s=1, p=0, activ='lrelu', norm='bn', res=0, bn=True, sn=False):

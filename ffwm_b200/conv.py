@@ -1,5 +1,6 @@
-"""Convolution layer of the mirrored networks: `nn.Conv2d` whose eligible calls run on the
-hand-written tcgen05 kernel (ffwm_b200/csrc/conv3x3_tc.cu) instead of cuDNN.
+"""Convolution layers of the mirrored networks: `nn.Conv2d` / `nn.ConvTranspose2d` whose eligible calls run on the
+hand-written tcgen05 kernels (ffwm_b200/csrc/conv3x3_tc.cu for the dominant 3x3 / stride-1 layers described first,
+csrc/conv_gen_tc.cu for every other kernel size / stride / map size: see GENERAL below) instead of cuDNN.
 
 Eligible: CUDA fp32, 3x3, stride 1, padding 1, dilation 1, groups 1, zero padding, map width 128, 64
 or 32 — the generator's residual / attention / reconstruction / pixel-shuffle convolutions at all
@@ -27,7 +28,14 @@ from torch.autograd import Function
 
 from . import ops
 
-ENABLED = True          # set False to force cuDNN everywhere (A/B measurements)
+ENABLED = os.environ.get("FFWM_CONV_TC", "1") == "1"     # False / FFWM_CONV_TC=0: cuDNN everywhere (A/B measurements)
+# Operand split per direction (include/ffwm_b200.h FFWM_MATH_*).  Forward passes run 3xTF32: their rounding errors decide
+# which side of zero a pre-activation lands on, and with 3xBF16 forwards the GRADIENTS of the deep BatchNorm / LeakyReLU
+# stacks come out 1000x less accurate than cuDNN's strict fp32 (FlowNet: 5e-3 vs 8e-6 of max|grad| against float64;
+# with 3xTF32 forwards 1e-5; torch's default TF32: 8e-2 — profiles/r02h_network_accuracy.txt).  Gradients are linear in
+# their operands' errors, so the data and weight gradients run 3xBF16 (twice the tensor rate) at no measurable loss.
+MATH_FWD = int(os.environ.get("FFWM_CONV_MATH_FWD", ops.L.MATH_TF32X3))
+MATH_BWD = int(os.environ.get("FFWM_CONV_MATH_BWD", ops.L.MATH_BF16X3))
 # The kernel also handles width 16, but there a map is one or two CTAs per (image, channel tile) with a
 # long serial K loop: measured slower than cuDNN inside the train step (98.4 -> 101.8 ms), so it is off.
 WIDTHS = (128, 64, 32)
@@ -35,6 +43,7 @@ WGRAD_TC = os.environ.get("FFWM_WGRAD_TC", "0") == "1"     # experimental, unmea
 # its CTA tile is 128 output x 48 input channels: layers far below that (flow heads, RGB reconstructions,
 # the first convolutions on 3 channels: 0.7 % of the weight-gradient FLOPs of the step) stay on cuDNN
 WGRAD_MIN_COUT, WGRAD_MIN_CIN = 32, 16
+WGRAD_GEN_3X3 = os.environ.get("FFWM_WGRAD_GEN_3X3", "0") == "1"     # A/B: the general weight-gradient kernel for these layers too
 # experimental, unmeasured: 128 output channels per CTA for the W = 128 layers with more than 64 of them
 NT128 = os.environ.get("FFWM_CONV_NT128", "1") == "1"
 
@@ -50,17 +59,26 @@ def _nt(width, n_out):
 CACHE_PACKED = os.environ.get("FFWM_CACHE_PACKED", "1") == "1"
 
 
-def _packed(weight, dgrad, nt):
+def _cached(weight, key, pack):
     if not (CACHE_PACKED and weight.is_leaf and not weight.requires_grad):
-        return ops.conv3x3_pack_weights(weight, dgrad=dgrad, nt=nt)
+        return pack()
     cache = getattr(weight, "_ffwm_packed", None)
     if cache is None:
         cache = weight._ffwm_packed = {}
     tag = (weight._version, weight.data_ptr())
-    hit = cache.get((dgrad, nt))
+    hit = cache.get(key)
     if hit is None or hit[0] != tag:
-        hit = cache[(dgrad, nt)] = (tag, ops.conv3x3_pack_weights(weight, dgrad=dgrad, nt=nt))
+        hit = cache[key] = (tag, pack())
     return hit[1]
+
+
+def _packed(weight, dgrad, nt, math):
+    return _cached(weight, (dgrad, nt, math), lambda: ops.conv3x3_pack_weights(weight, dgrad=dgrad, nt=nt, math=math))
+
+
+def _packed_gen(weight, in_major, stride, pad, transposed, math):
+    return _cached(weight, ("gen", in_major, stride, pad, transposed, math),
+                   lambda: ops.conv_pack_weights(weight, in_major, stride, pad, transposed, math))
 
 
 def eligible(x, weight, stride, padding, dilation, groups, padding_mode="zeros"):
@@ -69,15 +87,20 @@ def eligible(x, weight, stride, padding, dilation, groups, padding_mode="zeros")
             and tuple(padding) == (1, 1) and tuple(dilation) == (1, 1) and groups == 1 and padding_mode == "zeros")
 
 
+_DIAG_FWD_LIB = _DIAG_DGRAD_LIB = False      # scripts/diag_nets.py only: one direction on the library
+
+
 class Conv3x3TCFunction(Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         x = x.contiguous()
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        if _DIAG_FWD_LIB:
+            return torch.nn.functional.conv2d(x, weight, bias, padding=1)
         out = x.new_empty((x.size(0), weight.size(0), x.size(2), x.size(3)))
         nt = _nt(x.size(3), weight.size(0))
-        ops.conv3x3_forward(x, _packed(weight, False, nt), bias, out, nt=nt)
+        ops.conv3x3_forward(x, _packed(weight, False, nt, MATH_FWD), bias, out, nt=nt, math=MATH_FWD)
         return out
 
     @staticmethod
@@ -85,16 +108,20 @@ class Conv3x3TCFunction(Function):
         x, weight = ctx.saved_tensors
         grad_out = grad_out.contiguous()
         gx = gw = gb = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and _DIAG_DGRAD_LIB:
+            gx = torch.ops.aten.convolution_backward(grad_out, x, weight, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, False, False])[0]
+        elif ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
             nt = _nt(grad_out.size(3), weight.size(1))
-            ops.conv3x3_forward(grad_out, _packed(weight, True, nt), None, gx, nt=nt)
-        if WGRAD_TC and weight.size(0) >= WGRAD_MIN_COUT and weight.size(1) >= WGRAD_MIN_CIN:
+            ops.conv3x3_forward(grad_out, _packed(weight, True, nt, MATH_BWD), None, gx, nt=nt, math=MATH_BWD)
+        if WGRAD_GEN and WGRAD_GEN_3X3 and (ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])):
+            gw, gb = _wgrad(grad_out, x, weight, ctx.has_bias, 1, 1, False, 0, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
+        elif WGRAD_TC and weight.size(0) >= WGRAD_MIN_COUT and weight.size(1) >= WGRAD_MIN_CIN:
             want_b = ctx.has_bias and ctx.needs_input_grad[2]
             if ctx.needs_input_grad[1]:
                 gw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
                 gb = grad_out.new_zeros(weight.size(0)) if want_b else None    # falls out of staging grad_out
-                ops.conv3x3_wgrad(x, grad_out, gw, gb)
+                ops.conv3x3_wgrad(x, grad_out, gw, gb, math=MATH_BWD)
             elif want_b:
                 gb = grad_out.sum((0, 2, 3))
         elif ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
@@ -104,16 +131,134 @@ class Conv3x3TCFunction(Function):
         return gx, gw, gb
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# Every other dense convolution (csrc/conv_gen_tc.cu): kernels up to 7x7, stride 1 or 2, any padding / map size,
+# nn.Conv2d and nn.ConvTranspose2d, forward and data gradient on tcgen05 (3xBF16).  Weight gradients: cuDNN.
+GENERAL = os.environ.get("FFWM_CONV_GENERAL", "1") == "1"
+
+
+def _sym(v):
+    v = tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+    return v[0] if len(v) == 2 and v[0] == v[1] else None
+
+
+def eligible_general(x, weight, stride, padding, dilation, groups, padding_mode="zeros", output_padding=(0, 0), transposed=False):
+    if not (ENABLED and GENERAL and x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.dim() == 4
+            and groups == 1 and padding_mode == "zeros" and isinstance(padding, (tuple, list, int))):
+        return False
+    s, p, d, op = _sym(stride), _sym(padding), _sym(dilation), _sym(output_padding)
+    kh, kw = weight.shape[2:]
+    return (s in (1, 2) and p is not None and 0 <= p <= 7 and d == 1 and op is not None and op < s and kh <= 7 and kw <= 7
+            and min(kh, kw) >= (s if transposed else 1) and x.size(1) == weight.size(0 if transposed else 1)
+            and x.size(0) > 0 and x.size(2) + 2 * p >= kh and x.size(3) + 2 * p >= kw)
+
+
+# weight gradient of the general layers on tcgen05 (csrc/conv_gen_wgrad_tc.cu); FFWM_WGRAD_GEN=0: cuDNN through aten
+WGRAD_GEN = os.environ.get("FFWM_WGRAD_GEN", "1") == "1"
+
+
+def _wgrad(grad_out, x, weight, has_bias, stride, pad, transposed, out_pad, need_w, need_b):
+    if not WGRAD_GEN:
+        return _wgrad_library(grad_out, x, weight, has_bias, stride, pad, transposed, out_pad, need_w, need_b)
+    gw = gb = None
+    if need_w:
+        gw = torch.empty_like(weight, memory_format=torch.contiguous_format)
+        small, large = (x, grad_out) if transposed else (grad_out, x)
+        ops.conv_wgrad(small, large, gw, stride, pad)
+    if has_bias and need_b:
+        gb = grad_out.sum((0, 2, 3))
+    return gw, gb
+
+
+def _wgrad_library(grad_out, x, weight, has_bias, stride, pad, transposed, out_pad, need_w, need_b):
+    """Weight / bias gradient of the general layers: cuDNN through aten (grad_input is NOT requested)."""
+    _, gw, gb = torch.ops.aten.convolution_backward(
+        grad_out, x, weight, [weight.size(1 if transposed else 0)] if has_bias else None, [stride, stride], [pad, pad], [1, 1],
+        transposed, [out_pad, out_pad], 1, [False, bool(need_w), bool(has_bias and need_b)])
+    return gw, gb
+
+
+class ConvGenFunction(Function):
+    """conv2d(x, W, b, stride, pad) — forward: conv_forward; grad_input: the transposed mode on the same weights."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad):
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (bias is not None, stride, pad)
+        kh, kw = weight.shape[2:]
+        out = x.new_empty((x.size(0), weight.size(0), (x.size(2) + 2 * pad - kh) // stride + 1, (x.size(3) + 2 * pad - kw) // stride + 1))
+        ops.conv_forward(x, _packed_gen(weight, False, stride, pad, False, MATH_FWD), bias, out, kh, kw, stride, pad, False, MATH_FWD)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        x, weight = ctx.saved_tensors
+        has_bias, stride, pad = ctx.cfg
+        kh, kw = weight.shape[2:]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x, memory_format=torch.contiguous_format)
+            ops.conv_forward(grad_out, _packed_gen(weight, True, stride, pad, True, MATH_BWD), None, gx, kh, kw, stride, pad, True, MATH_BWD)
+        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+            gw, gb = _wgrad(grad_out, x, weight, has_bias, stride, pad, False, 0, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
+        return gx, gw, gb, None, None
+
+
+class ConvTGenFunction(Function):
+    """conv_transpose2d(x, W, b, stride, pad, output_padding) — forward: the transposed mode; grad_input: a convolution."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad, out_pad):
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (bias is not None, stride, pad, out_pad)
+        kh, kw = weight.shape[2:]
+        out = x.new_empty((x.size(0), weight.size(1), (x.size(2) - 1) * stride - 2 * pad + kh + out_pad,
+                           (x.size(3) - 1) * stride - 2 * pad + kw + out_pad))
+        ops.conv_forward(x, _packed_gen(weight, True, stride, pad, True, MATH_FWD), bias, out, kh, kw, stride, pad, True, MATH_FWD)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        x, weight = ctx.saved_tensors
+        has_bias, stride, pad, out_pad = ctx.cfg
+        kh, kw = weight.shape[2:]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x, memory_format=torch.contiguous_format)
+            # a convolution over grad_out; with output_padding < stride its floor division still yields x's size
+            ops.conv_forward(grad_out, _packed_gen(weight, False, stride, pad, False, MATH_BWD), None, gx, kh, kw, stride, pad, False, MATH_BWD)
+        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+            gw, gb = _wgrad(grad_out, x, weight, has_bias, stride, pad, True, out_pad, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
+        return gx, gw, gb, None, None, None
+
+
 def conv2d(x, weight, bias, stride=(1, 1), padding=(0, 0), dilation=(1, 1), groups=1):
-    """F.conv2d with the tcgen05 path for eligible calls."""
+    """F.conv2d with the tcgen05 paths for eligible calls."""
     if eligible(x, weight, stride, padding, dilation, groups):
         return Conv3x3TCFunction.apply(x, weight, bias)
+    if eligible_general(x, weight, stride, padding, dilation, groups):
+        return ConvGenFunction.apply(x, weight, bias, _sym(stride), _sym(padding))
     return torch.nn.functional.conv2d(x, weight, bias, stride, padding, dilation, groups)
 
 
 class Conv2d(nn.Conv2d):
     def _conv_forward(self, input, weight, bias):
-        if isinstance(self.padding, tuple) and eligible(input, weight, self.stride, self.padding, self.dilation,
-                                                        self.groups, self.padding_mode):
-            return Conv3x3TCFunction.apply(input, weight, bias)
+        if isinstance(self.padding, tuple):
+            if eligible(input, weight, self.stride, self.padding, self.dilation, self.groups, self.padding_mode):
+                return Conv3x3TCFunction.apply(input, weight, bias)
+            if eligible_general(input, weight, self.stride, self.padding, self.dilation, self.groups, self.padding_mode):
+                return ConvGenFunction.apply(input, weight, bias, _sym(self.stride), _sym(self.padding))
         return super()._conv_forward(input, weight, bias)
+
+
+class ConvTranspose2d(nn.ConvTranspose2d):
+    """Drop-in nn.ConvTranspose2d (same parameters / state_dict keys) on the tcgen05 kernel for eligible calls."""
+
+    def forward(self, input, output_size=None):
+        if (output_size is None and isinstance(self.padding, tuple)
+                and eligible_general(input, self.weight, self.stride, self.padding, self.dilation, self.groups, self.padding_mode,
+                                     self.output_padding, transposed=True)):
+            return ConvTGenFunction.apply(input, self.weight, self.bias, _sym(self.stride), _sym(self.padding), _sym(self.output_padding))
+        return super().forward(input, output_size)

@@ -91,7 +91,7 @@ int sm_count() {
 
 static const char* const g_opt_names[OPT_COUNT] = {
     "DISABLE_TILED", "FORCE_TILED", "DISABLE_ROLL", "FORCE_ROLL", "SCATTER_TILED", "DISABLE_TILED_GFLOW",
-    "DISABLE_QUAD", "GQ_SCALAR_FILL", "SCATTER_SCALAR_FLUSH", "WGRAD_DIRECT_EPILOGUE", "CONV_MATH"};
+    "DISABLE_QUAD", "GQ_SCALAR_FILL", "SCATTER_SCALAR_FLUSH", "WGRAD_DIRECT_EPILOGUE"};
 static int g_opts[OPT_COUNT];
 static int g_opts_ready = 0;
 
@@ -101,7 +101,7 @@ static void init_opts() {
         char env[64];
         snprintf(env, sizeof(env), "FFWM_%s", g_opt_names[i]);
         const char* v = getenv(env);
-        int val = i == OPT_CONV_MATH ? 1 : 0;                          // defaults: everything off, 3xBF16 convolution math
+        int val = 0;                                                   // defaults: everything off
         if (v && *v) val = (v[0] >= '0' && v[0] <= '9') ? atoi(v) : 1; // FFWM_X=1, FFWM_X=anything -> 1, FFWM_X=0 -> 0
         g_opts[i] = val;
     }

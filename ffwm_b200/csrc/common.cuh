@@ -77,7 +77,6 @@ enum Opt {
     OPT_GQ_SCALAR_FILL,
     OPT_SCATTER_SCALAR_FLUSH,
     OPT_WGRAD_DIRECT_EPILOGUE,
-    OPT_CONV_MATH,               // 0 = 3xTF32 operand split, 1 = 3xBF16 operand split (conv3x3_tc.cu)
     OPT_COUNT
 };
 int opt(int id);

@@ -45,7 +45,7 @@ namespace ffwm {
 // l1tex 72 % / tensor pipe 48 %); N = 128 reads 4 + 4 KB for 66 clk of math.  The N = 128 variant is EXPERIMENTAL
 // (written after the round-1 GPU budget was spent, not yet run): callers opt in per call (nt argument of the
 // *_nt entry points; ffwm_b200/conv.py: FFWM_CONV_NT128=1).
-// Operand math (template parameter BF of everything below; runtime choice: option CONV_MATH, common.cuh):
+// Operand math (template parameter BF of everything below; chosen per call: the `math` argument of the entry points):
 //   BF = false  3xTF32: a = hi + lo, hi = a & 0xffffe000 (exact in tf32); hi*hi + hi*lo + lo*hi; K block = 8 channels
 //   BF = true   3xBF16: a = b1 + b2 + (dropped), b1 = bf16_rn(a), b2 = bf16_rn(a - b1); b1*b1 + b1*b2 + b2*b1;
 //               K block = 16 channels.  A 16-byte slot holds 8 bf16 channels instead of 4 fp32, so every
@@ -323,37 +323,37 @@ static int launch_conv3x3_m(const View<const float>& xv, const float* packed, co
     return FFWM_OK;
 }
 template <int WI, int NT = 64>
-static int launch_conv3x3(const View<const float>& xv, const float* packed, const float* bias, const View<float>& ov, cudaStream_t st) {
-    return opt(OPT_CONV_MATH) ? launch_conv3x3_m<WI, NT, true>(xv, packed, bias, ov, st)
-                              : launch_conv3x3_m<WI, NT, false>(xv, packed, bias, ov, st);
+static int launch_conv3x3(const View<const float>& xv, const float* packed, const float* bias, const View<float>& ov, int math, cudaStream_t st) {
+    return math ? launch_conv3x3_m<WI, NT, true>(xv, packed, bias, ov, st) : launch_conv3x3_m<WI, NT, false>(xv, packed, bias, ov, st);
 }
 
 }  // namespace ffwm
 
 static bool cv_nt_ok(int nt) { return nt == 64 || nt == 128; }
+static bool cv_math_ok(int math) { return math == FFWM_MATH_TF32X3 || math == FFWM_MATH_BF16X3; }
 
-extern "C" int64_t ffwm_conv3x3_packed_floats_nt(int cout, int cin, int nt) {
-    if (cout <= 0 || cin <= 0 || !cv_nt_ok(nt)) return 0;
-    const int kbs = ffwm::opt(ffwm::OPT_CONV_MATH) ? 16 : 8;                  // channels per K block of the selected operand math
+extern "C" int64_t ffwm_conv3x3_packed_floats(int cout, int cin, int nt, int math) {
+    if (cout <= 0 || cin <= 0 || !cv_nt_ok(nt) || !cv_math_ok(math)) return 0;
+    const int kbs = math ? 16 : 8;                                            // channels per K block of the operand math
     const int64_t ncob = (cout + nt - 1) / nt, nkb = (cin + kbs - 1) / kbs;
     return ncob * nkb * (2 * 9 * 2 * nt * 4);                                 // CvGeo::B_STAGE / 4 floats per (cob, kb)
 }
-extern "C" int64_t ffwm_conv3x3_packed_floats(int cout, int cin) { return ffwm_conv3x3_packed_floats_nt(cout, cin, 64); }
 
-extern "C" int ffwm_conv3x3_pack_weights_nt(const ffwm_tensor4* weight, int dgrad, float* packed, int64_t packed_floats, int nt, void* stream) {
+extern "C" int ffwm_conv3x3_pack_weights(const ffwm_tensor4* weight, int dgrad, float* packed, int64_t packed_floats, int nt, int math, void* stream) {
     using namespace ffwm;
     if (!weight || !weight->data || !packed) { set_error("conv3x3_pack_weights: null pointer"); return FFWM_ERR_NULL; }
     if (weight->size[2] != 3 || weight->size[3] != 3) { set_error("conv3x3_pack_weights: kernel must be 3x3"); return FFWM_ERR_SHAPE; }
     if (!cv_nt_ok(nt)) { set_error("conv3x3_pack_weights: nt must be 64 or 128 (got %d)", nt); return FFWM_ERR_ARG; }
+    if (!cv_math_ok(math)) { set_error("conv3x3_pack_weights: math must be 0 (3xTF32) or 1 (3xBF16)"); return FFWM_ERR_ARG; }
     const int cout = (int)weight->size[0], cin = (int)weight->size[1];
-    const int64_t need = dgrad ? ffwm_conv3x3_packed_floats_nt(cin, cout, nt) : ffwm_conv3x3_packed_floats_nt(cout, cin, nt);
+    const int64_t need = dgrad ? ffwm_conv3x3_packed_floats(cin, cout, nt, math) : ffwm_conv3x3_packed_floats(cout, cin, nt, math);
     if (packed_floats < need) { set_error("conv3x3_pack_weights: packed buffer too small (%lld < %lld floats)", (long long)packed_floats, (long long)need); return FFWM_ERR_SHAPE; }
     const int64_t pairs = need / 2;
     const int blocks = (int)std::min<int64_t>((pairs + 255) / 256, 4096);
     const float* wp = static_cast<const float*>(weight->data);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t s0 = weight->stride[0], s1 = weight->stride[1], s2 = weight->stride[2], s3 = weight->stride[3];
-    if (opt(OPT_CONV_MATH)) {
+    if (math) {
         __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(packed);
         if (nt == 64) conv3x3_pack_bf_kernel<64><<<blocks, 256, 0, st>>>(wp, pb, cout, cin, dgrad, s0, s1, s2, s3);
         else conv3x3_pack_bf_kernel<128><<<blocks, 256, 0, st>>>(wp, pb, cout, cin, dgrad, s0, s1, s2, s3);
@@ -363,14 +363,10 @@ extern "C" int ffwm_conv3x3_pack_weights_nt(const ffwm_tensor4* weight, int dgra
     }
     return check_launch("conv3x3_pack_weights");
 }
-extern "C" int ffwm_conv3x3_pack_weights(const ffwm_tensor4* weight, int dgrad, float* packed, int64_t packed_floats, void* stream) {
-    return ffwm_conv3x3_pack_weights_nt(weight, dgrad, packed, packed_floats, 64, stream);
-}
 
 // conv2d(x, w, bias, stride 1, padding 1) for 3x3 kernels with `packed` = pack_weights(w): x (B,Cin,H,W) fp32,
 // out (B,Cout,H,W) fp32, W in {128, 64, 32, 16}.  Replaces the cuDNN call behind nn.Conv2d(…, 3, 1, 1) for those shapes.
-// nt = output channels per CTA the weights were packed for: 64, or 128 (W = 128 only, experimental).
-extern "C" int ffwm_conv3x3_forward_nt(const ffwm_tensor4* x, const float* packed, const float* bias, const ffwm_tensor4* out, int nt, void* stream) {
+extern "C" int ffwm_conv3x3_forward(const ffwm_tensor4* x, const float* packed, const float* bias, const ffwm_tensor4* out, int nt, int math, void* stream) {
     using namespace ffwm;
     View<const float> xv;
     View<float> ov;
@@ -383,17 +379,15 @@ extern "C" int ffwm_conv3x3_forward_nt(const ffwm_tensor4* x, const float* packe
         return FFWM_ERR_SHAPE;
     }
     if (nt != 64 && !(nt == 128 && xv.w == 128)) { set_error("conv3x3_forward: nt must be 64, or 128 with W = 128 (got nt %d, W %d)", nt, xv.w); return FFWM_ERR_ARG; }
+    if (!cv_math_ok(math)) { set_error("conv3x3_forward: math must be 0 (3xTF32) or 1 (3xBF16)"); return FFWM_ERR_ARG; }
     if ((int64_t)ov.n * ov.c * ov.h == 0) return FFWM_OK;
     if (ov.n > 65535 || ceil_div(ov.c, nt) > 65535) { set_error("conv3x3_forward: grid too large"); return FFWM_ERR_TOO_LARGE; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    rc = nt == 128    ? launch_conv3x3<128, 128>(xv, packed, bias, ov, st)
-         : xv.w == 128 ? launch_conv3x3<128>(xv, packed, bias, ov, st)
-         : xv.w == 64 ? launch_conv3x3<64>(xv, packed, bias, ov, st)
-         : xv.w == 32 ? launch_conv3x3<32>(xv, packed, bias, ov, st)
-                      : launch_conv3x3<16>(xv, packed, bias, ov, st);
+    rc = nt == 128    ? launch_conv3x3<128, 128>(xv, packed, bias, ov, math, st)
+         : xv.w == 128 ? launch_conv3x3<128>(xv, packed, bias, ov, math, st)
+         : xv.w == 64 ? launch_conv3x3<64>(xv, packed, bias, ov, math, st)
+         : xv.w == 32 ? launch_conv3x3<32>(xv, packed, bias, ov, math, st)
+                      : launch_conv3x3<16>(xv, packed, bias, ov, math, st);
     if (rc) return rc;
     return check_launch("conv3x3_forward");
-}
-extern "C" int ffwm_conv3x3_forward(const ffwm_tensor4* x, const float* packed, const float* bias, const ffwm_tensor4* out, void* stream) {
-    return ffwm_conv3x3_forward_nt(x, packed, bias, out, 64, stream);
 }

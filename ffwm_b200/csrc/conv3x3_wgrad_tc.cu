@@ -2,7 +2,7 @@
 // cores, fp32 in / fp32 out, 3xTF32 operand split (same accuracy contract as conv3x3_tc.cu).
 //
 // Validated on a B200 (round 2, call 1: 13 parity cases <= 1.6e-5 of max|dW|; cuDNN's strict-fp32 weight gradient
-// measures 3-7e-5 on the same inputs).  Operand math is a template parameter like conv3x3_tc.cu's (option CONV_MATH):
+// measures 3-7e-5 on the same inputs).  Operand math is a template parameter like conv3x3_tc.cu's (the `math` argument):
 // 3xTF32 (4 pixels per 16-byte chunk, K = 8 pixels per MMA) or 3xBF16 (8 pixels per chunk, K = 16 pixels per MMA:
 // same shared-memory tiles, half the MMAs).  The text below describes the 3xTF32 geometry; PPC = pixels per chunk.
 //
@@ -125,11 +125,10 @@ conv3x3_wgrad_tc_kernel(View<const float> x, View<const float> go, float* __rest
             const int s = st0 + k;
             const int j0 = (s % g.ncb) * g.nch, rr = s / g.ncb, y = rr % g.h, b = rr / g.h;
             unsigned char* sbase = wg_smem + buf * WG_STAGE;
-            // one item at a time: its loads (up to 3 chunks x PPC pixels per lane) are all in flight before its stores;
-            // the compiler overlaps the next item's loads with this item's split + stores
+            // all loads of the stage in flight first (up to 5 items x 3 chunks x PPC pixels per lane), then split + store
+            float v[WG_ITEMS_PER_WARP][3][PPC];
 #pragma unroll
             for (int i = 0; i < WG_ITEMS_PER_WARP; ++i) {
-                float v[3][PPC];
                 const int it = warp + i * (WG_PRODUCERS / 32);               // warp-uniform
                 if (it >= WG_ITEMS) continue;
                 const float* rowp;
@@ -154,23 +153,28 @@ conv3x3_wgrad_tc_kernel(View<const float> x, View<const float> go, float* __rest
                     for (int m = 0; m < PPC; ++m) {
                         const int p = jbase + cc + m * g.s4;
                         const bool ok = rok && cc < nchunk && (unsigned)p < (unsigned)g.w;
-                        v[q][m] = ok ? __ldg(rowp + (int64_t)p * sw) : 0.f;
+                        v[i][q][m] = ok ? __ldg(rowp + (int64_t)p * sw) : 0.f;
                     }
                 }
                 if (i < 2 && do_bias) {                                      // A item (zeros where the row / chunk does not exist)
 #pragma unroll
                     for (int q = 0; q < 3; ++q)
 #pragma unroll
-                        for (int m = 0; m < PPC; ++m) bsum[i] += v[q][m];
+                        for (int m = 0; m < PPC; ++m) bsum[i] += v[i][q][m];
                 }
+            }
+#pragma unroll
+            for (int i = 0; i < WG_ITEMS_PER_WARP; ++i) {
+                const int it = warp + i * (WG_PRODUCERS / 32);
+                if (it >= WG_ITEMS) continue;
                 const bool isA = it < WG_A_ITEMS;
                 const int row = (isA ? it : it - WG_A_ITEMS) * 8 + r8;
-                const int lbo = isA ? WG_A_LBO : WG_B_LBO, part = isA ? WG_A_PART : WG_B_PART;
+                const int nchunk = isA ? g.nch : g.nch + 2, lbo = isA ? WG_A_LBO : WG_B_LBO, part = isA ? WG_A_PART : WG_B_PART;
                 unsigned char* d0 = sbase + (isA ? 0 : 2 * WG_A_PART) + row * 16;
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
                     const int cc = jq + 4 * q;
-                    if (cc < nchunk) split_store_m<BF>(d0 + cc * lbo, part, v[q]);
+                    if (cc < nchunk) split_store_m<BF>(d0 + cc * lbo, part, v[i][q]);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // my stores -> visible to the tensor core
@@ -283,7 +287,7 @@ conv3x3_wgrad_tc_kernel(View<const float> x, View<const float> go, float* __rest
 // grad_weight (partial sums of the K splits arrive as REDs).  x (B,Cin,H,W), grad_out (B,Cout,H,W), W % 32 == 0.
 // grad_bias (Cout floats, zero-filled by the caller, may be NULL) += sum of grad_out over (b, y, x).
 extern "C" int ffwm_conv3x3_wgrad(const ffwm_tensor4* x, const ffwm_tensor4* grad_out, const ffwm_tensor4* grad_weight,
-                                  float* grad_bias, void* stream) {
+                                  float* grad_bias, int math, void* stream) {
     using namespace ffwm;
     View<const float> xv, gv;
     View<float> wv;
@@ -291,7 +295,8 @@ extern "C" int ffwm_conv3x3_wgrad(const ffwm_tensor4* x, const ffwm_tensor4* gra
     if ((rc = make_view<const float>(x, "x", &xv))) return rc;
     if ((rc = make_view<const float>(grad_out, "grad_out", &gv))) return rc;
     if ((rc = make_view<float>(grad_weight, "grad_weight", &wv))) return rc;
-    const bool bf = opt(OPT_CONV_MATH) != 0;
+    if (math != 0 && math != 1) { set_error("conv3x3_wgrad: math must be 0 (3xTF32) or 1 (3xBF16)"); return FFWM_ERR_ARG; }
+    const bool bf = math != 0;
     if (xv.w % 32 != 0 || xv.w <= 0 || gv.w != xv.w || gv.h != xv.h || gv.n != xv.n || wv.n != gv.c || wv.c != xv.c || wv.h != 3 || wv.w != 3) {
         set_error("conv3x3_wgrad: needs W %% 32 == 0, equal N,H,W and grad_weight (Cout,Cin,3,3) (x %dx%dx%dx%d, grad_out %dx%dx%dx%d, grad_weight %dx%dx%dx%d)",
                   xv.n, xv.c, xv.h, xv.w, gv.n, gv.c, gv.h, gv.w, wv.n, wv.c, wv.h, wv.w);
@@ -301,7 +306,7 @@ extern "C" int ffwm_conv3x3_wgrad(const ffwm_tensor4* x, const ffwm_tensor4* gra
     WgGeo g;
     g.cout = gv.c, g.cin = xv.c, g.h = xv.h, g.w = xv.w;
     g.s4 = xv.w / (bf ? 8 : 4);                 // W % 32 == 0: s4 is a multiple of 4 (3xBF16) / 8 (3xTF32)
-    g.nch = std::min(WG_CH, g.s4);
+    g.nch = g.s4 % WG_CH == 0 ? WG_CH : 4;     // chunks per stage: even, divides s4
     g.ncb = g.s4 / g.nch;
     g.n_ci_tiles = ceil_div(g.cin, WG_NCI);
     const int64_t tiles = (int64_t)ceil_div(g.cout, WG_MT) * g.n_ci_tiles;

@@ -1,0 +1,294 @@
+// conv_gen_wgrad_tc: weight gradient of ANY dense convolution of the path on the tcgen05 tensor cores (kernels up
+// to 7x7, stride 1 or 2, any padding / map size, nn.Conv2d and nn.ConvTranspose2d), fp32 in / fp32 out, 3xBF16 split.
+//
+//   dW[a][b][ky][kx] = sum over (n, y, x) of  S[n, a, y, x] * L[n, b, y*s - p + ky, x*s - p + kx]        (zero padding)
+//
+// S is the tensor on the SMALL side of the strided operation and L the one on the large side: for nn.Conv2d S = grad_out,
+// L = the input (a = Cout, b = Cin); for nn.ConvTranspose2d S = the input, L = grad_out (a = Cin, b = Cout) — in both cases
+// (a, b) are the first two dimensions of the weight as it lies in memory.  Replaces aten::convolution_backward's
+// grad_weight (cuDNN wgrad engines) behind models/base_networks.py:30-57,208-246,274-312,354-437, lightcnn/light_cnn.py:13-26.
+//
+// The contraction runs over PIXELS.  Instead of transposing anything, both operands are staged exactly like the
+// activations of conv_gen_tc.cu — thread = (pixel, group of 8 channels): 8 coalesced loads (lanes = 32 consecutive
+// pixels of a channel plane), one 16-byte slot of 8 channels per bf16 part — and the tensor core reads those tiles as
+// MN-MAJOR operands (instruction-descriptor bits a_major = b_major = 1): in the no-swizzle canonical layout a 16-byte
+// slot is 8 consecutive M (or N) indices of one K index, 8 consecutive K indices are 128 contiguous bytes (LBO = 128 B
+// between K groups of 8), and the next 8 M/N indices follow SBO = 16 B x (pixels per stage) later.  K = 16 pixels per MMA.
+//   * M = 128 channels `a` of S;  N = TG x NB = (tap group) x (channels b of L, a multiple of 8), tap-major, up to 256:
+//     rows of the B tile are L gathered at the tap's shifted position, so L is read once per tap through L1 / L2.
+//   * a stage = 64 pixels of the linearised (n, y, x) range of S (4 K steps x 3 MMAs of the split), ring of 2-3 stages,
+//     producers / issuer / epilogue on mbarriers as in the other tcgen05 kernels.
+//   * split K: the pixel range is cut over blockIdx.y (at most 64 stages per CTA: bounds the truncating fp32 accumulation
+//     chain to 768 updates).  Partial tiles go to a caller-provided workspace with plain 64-byte-per-lane stores and a
+//     second kernel sums the splits into dW in a fixed order: deterministic, no atomics, no zero-fill contract.
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace ffwm {
+
+constexpr int WGG_PRODUCERS = 256;
+constexpr int WGG_KP = 64;                         // pixels per stage
+constexpr int WGG_GROUP = WGG_KP * 16;             // bytes of one 8-channel group of a tile part: [64 pixels][16 B]
+constexpr int WGG_A_PART = 16 * WGG_GROUP;         // 128 channels
+constexpr int WGG_MAX_STAGES = 64;                 // per CTA (accuracy, see conv3x3_wgrad_tc.cu)
+
+struct WggGeo {
+    int n, hs, ws, hl, wl;       // S (n, ca, hs, ws), L (n, cb, hl, wl)
+    int ca, cb, kh, kw, stride, pad;
+    int tg, nb, nn;              // taps per tile, channels b per tile, N = tg * nb
+    int nat, nbt, ntg, tiles;    // tiles over a, b, tap groups
+    int64_t npix;
+    int stages_total, stages_per_split, splits;
+    int b_part, stage_bytes, nstage, tmem_cols;
+};
+
+// MN-major, no-swizzle shared-memory descriptor: same fields as umma_desc (umma.cuh); for this layout the "leading"
+// offset steps to the next group of 8 K indices and the "stride" offset to the next group of 8 M/N indices.
+// (validated on a B200: with the two offsets exchanged every parity case fails)
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t k_group_bytes, uint32_t mn_group_bytes) {
+    return umma_desc(saddr, k_group_bytes, mn_group_bytes);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int m, int n) {
+    return umma_idesc_bf16(m, n) | (1u << 15) | (1u << 16);
+}
+
+__global__ void __launch_bounds__(WGG_PRODUCERS + 32, 1)
+conv_gen_wgrad_tc_kernel(View<const float> S, View<const float> L, float* __restrict__ ws, const __grid_constant__ WggGeo g) {
+    extern __shared__ __align__(128) unsigned char wg_smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wg_smem + g.nstage * g.stage_bytes);     // full[0..2] empty[4..6]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x, split = blockIdx.y;
+    const int tgi = tile % g.ntg, bt = (tile / g.ntg) % g.nbt, at = tile / (g.ntg * g.nbt);
+    const int st0 = split * g.stages_per_split;
+    const int nst = min(g.stages_per_split, g.stages_total - st0);                        // >= 1 (host)
+
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&bars[i], WGG_PRODUCERS);
+            mbar_init(&bars[4 + i], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(g.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < WGG_PRODUCERS / 32) {
+        // ================= producers =================
+        const int px = tid & (WGG_KP - 1), g0 = tid / WGG_KP;              // pixel of the stage, first group (0..3)
+        const int nbg = g.nb / 8;                                          // channel groups per tap
+        const int ngB = g.nn / 8;                                          // groups of the B tile
+        for (int k = 0; k < nst; ++k) {
+            const int slot = k % g.nstage;
+            if (k >= g.nstage) mbar_wait(&bars[4 + slot], ((k / g.nstage) - 1) & 1);
+            unsigned char* sA = wg_smem + slot * g.stage_bytes;
+            unsigned char* sB = sA + 2 * WGG_A_PART;
+            const int64_t p = (int64_t)(st0 + k) * WGG_KP + px;
+            const bool pv = p < g.npix;
+            int xs = 0, ys = 0, img = 0;
+            if (pv) { xs = (int)(p % g.ws); const int64_t q = p / g.ws; ys = (int)(q % g.hs); img = (int)(q / g.hs); }
+            // ---- A: S[img, a, ys, xs] for the 128 channels of the tile, 4 groups of 8 per thread
+            {
+                const float* sp = S.p + img * S.sb + (int64_t)ys * S.sh + (int64_t)xs * S.sw;
+                float v[4][8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int a0 = at * 128 + (g0 + 4 * i) * 8;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[i][j] = (pv && a0 + j < g.ca) ? __ldg(sp + (int64_t)(a0 + j) * S.sc) : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split_store_bf(sA + (g0 + 4 * i) * WGG_GROUP + px * 16, WGG_A_PART, v[i]);
+            }
+            // ---- B: L gathered at the tap's position, groups = (tap of the tile, 8 channels b)
+            const int yl0 = ys * g.stride - g.pad, xl0 = xs * g.stride - g.pad;
+            const float* lp = L.p + img * L.sb;
+            for (int gb = g0; gb < ngB; gb += 16) {                         // 4 groups per pass
+                float v[4][8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int gg = gb + 4 * i;
+                    const int tl = gg / nbg, b0 = bt * g.nb + (gg - tl * nbg) * 8;
+                    const int tap = tgi * g.tg + tl, ky = tap / g.kw, kx = tap - ky * g.kw;
+                    const int yl = yl0 + ky, xl = xl0 + kx;
+                    const bool ok = pv && gg < ngB && tap < g.kh * g.kw && (unsigned)yl < (unsigned)g.hl && (unsigned)xl < (unsigned)g.wl;
+                    const float* q = lp + (int64_t)yl * L.sh + (int64_t)xl * L.sw + (int64_t)b0 * L.sc;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[i][j] = (ok && b0 + j < g.cb) ? __ldg(q + (int64_t)j * L.sc) : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (gb + 4 * i < ngB) split_store_bf(sB + (gb + 4 * i) * WGG_GROUP + px * 16, g.b_part, v[i]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[slot])) : "memory");
+        }
+    } else if (lane == 0) {
+        // ================= issuer =================
+        const uint32_t idesc = umma_idesc_bf16_mn(128, g.nn);
+        for (int k = 0; k < nst; ++k) {
+            const int slot = k % g.nstage;
+            mbar_wait(&bars[slot], (k / g.nstage) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sA = smem_u32(wg_smem + slot * g.stage_bytes), sB = sA + 2 * WGG_A_PART;
+#pragma unroll
+            for (int t = 0; t < WGG_KP / 16; ++t) {                        // K step: pixels 16t .. 16t+15 = 256 bytes into every group
+                const uint64_t dA1 = umma_desc_mn(sA + t * 256, 128, WGG_GROUP), dA2 = dA1 + (uint64_t)(WGG_A_PART >> 4);
+                const uint64_t dB1 = umma_desc_mn(sB + t * 256, 128, WGG_GROUP), dB2 = dB1 + (uint64_t)(g.b_part >> 4);
+                umma_bf16(tmem, dA1, dB1, idesc, k > 0 || t > 0);
+                umma_bf16(tmem, dA1, dB2, idesc, true);
+                umma_bf16(tmem, dA2, dB1, idesc, true);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[4 + slot])) : "memory");
+        }
+    }
+
+    // ---- epilogue: the partial tile [128 a][nn] of this split -> workspace (each lane: runs of 16 consecutive floats)
+    if (warp < WGG_PRODUCERS / 32) {
+        const int last = nst - 1;
+        mbar_wait(&bars[4 + last % g.nstage], (last / g.nstage) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3, half = warp >> 2;
+        float* wp = ws + (((int64_t)split * g.tiles + tile) * 128 + q * 32 + lane) * g.nn;
+        for (int col0 = half * 16; col0 < g.nn; col0 += 32) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<uint4*>(wp + col0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(g.tmem_cols) : "memory");
+}
+
+// dW[a][b][ky][kx] = sum over splits of the partial tiles, in split order (deterministic); overwrites dW.
+__global__ void conv_gen_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int64_t s_a, int64_t s_b, int64_t s_ky,
+                                             int64_t s_kx, WggGeo g) {
+    const int T = g.kh * g.kw;
+    const int64_t total = (int64_t)g.ca * g.cb * T;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int tap = (int)(i % T);
+        const int64_t r = i / T;
+        const int b = (int)(r % g.cb), a = (int)(r / g.cb);
+        const int tile = ((a / 128) * g.nbt + b / g.nb) * g.ntg + tap / g.tg;
+        const int nidx = (tap % g.tg) * g.nb + b % g.nb;
+        const float* p = ws + ((int64_t)tile * 128 + a % 128) * g.nn + nidx;
+        const int64_t split_stride = (int64_t)g.tiles * 128 * g.nn;
+        float acc = 0.f;
+        for (int s = 0; s < g.splits; ++s) acc += p[s * split_stride];
+        const int ky = tap / g.kw, kx = tap - ky * g.kw;
+        dw[a * s_a + b * s_b + ky * s_ky + kx * s_kx] = acc;
+    }
+}
+
+static int wgg_setup(WggGeo& g, int n, int ca, int cb, int hs, int ws_, int hl, int wl, int kh, int kw, int stride, int pad) {
+    if (kh < 1 || kw < 1 || kh > 7 || kw > 7 || (stride != 1 && stride != 2) || pad < 0 || pad > 7) {
+        set_error("conv_wgrad: kernel %dx%d stride %d padding %d is outside 1..7 / {1,2} / 0..7", kh, kw, stride, pad);
+        return FFWM_ERR_ARG;
+    }
+    const int eh = (hs - 1) * stride - 2 * pad + kh, ew = (ws_ - 1) * stride - 2 * pad + kw;   // extent of L the taps reach
+    if (hs < 1 || ws_ < 1 || hl < eh || hl >= eh + stride || wl < ew || wl >= ew + stride) {
+        set_error("conv_wgrad: small side %dx%d and large side %dx%d do not match kernel %dx%d, stride %d, padding %d", hs, ws_, hl, wl, kh,
+                  kw, stride, pad);
+        return FFWM_ERR_SHAPE;
+    }
+    g.n = n, g.hs = hs, g.ws = ws_, g.hl = hl, g.wl = wl, g.ca = ca, g.cb = cb, g.kh = kh, g.kw = kw, g.stride = stride, g.pad = pad;
+    const int T = kh * kw;
+    // N = tg * nb <= 256, a multiple of 16, nb a multiple of 8: fewest staged groups over all tiles wins
+    int64_t best = -1;
+    for (int tg = T; tg >= 1; --tg) {
+        if (T % tg) continue;
+        const int gran = (tg % 2) ? 16 : 8;
+        int nb = (256 / tg) / gran * gran;
+        nb = std::min(nb, (cb + gran - 1) / gran * gran);
+        if (nb < 8) continue;
+        const int64_t tiles_bt = (int64_t)((cb + nb - 1) / nb) * (T / tg);
+        const int64_t cost = tiles_bt * (16 + tg * nb / 8);
+        if (best < 0 || cost < best) best = cost, g.tg = tg, g.nb = nb;
+    }
+    if (best < 0) { set_error("conv_wgrad: no tiling for %d taps", T); return FFWM_ERR_ARG; }
+    g.nn = g.tg * g.nb;
+    g.nat = (ca + 127) / 128, g.nbt = (cb + g.nb - 1) / g.nb, g.ntg = T / g.tg;
+    g.tiles = g.nat * g.nbt * g.ntg;
+    g.npix = (int64_t)n * hs * ws_;
+    const int64_t stages = (g.npix + WGG_KP - 1) / WGG_KP;
+    if (stages > 0x7fffffffLL) { set_error("conv_wgrad: problem too large"); return FFWM_ERR_TOO_LARGE; }
+    g.stages_total = (int)stages;
+    int64_t splits = std::max<int64_t>(1, std::min<int64_t>((stages + 1) / 2, (2 * sm_count() + g.tiles - 1) / g.tiles));
+    g.stages_per_split = (int)std::min<int64_t>((stages + splits - 1) / splits, WGG_MAX_STAGES);
+    g.splits = (int)((stages + g.stages_per_split - 1) / g.stages_per_split);
+    g.b_part = (g.nn / 8) * WGG_GROUP;
+    g.stage_bytes = 2 * WGG_A_PART + 2 * g.b_part;
+    g.nstage = std::max(2, std::min(3, (227 * 1024 - 256) / g.stage_bytes));
+    g.tmem_cols = 32;
+    while (g.tmem_cols < g.nn) g.tmem_cols *= 2;
+    return FFWM_OK;
+}
+
+}  // namespace ffwm
+
+// Bytes of workspace ffwm_conv_wgrad needs for these shapes (0: unsupported arguments, see ffwm_last_error).
+extern "C" int64_t ffwm_conv_wgrad_workspace_bytes(int n, int ca, int cb, int hs, int ws, int hl, int wl, int kh, int kw, int stride, int pad) {
+    ffwm::WggGeo g;
+    if (n <= 0 || ca <= 0 || cb <= 0) return 0;
+    if (ffwm::wgg_setup(g, n, ca, cb, hs, ws, hl, wl, kh, kw, stride, pad)) return 0;
+    return (int64_t)g.splits * g.tiles * 128 * g.nn * (int64_t)sizeof(float);
+}
+
+// grad_weight (Ca, Cb, kh, kw; any strides; OVERWRITTEN) = weight gradient as defined at the top of this file.
+// small (B, Ca, Hs, Ws) and large (B, Cb, Hl, Wl): nn.Conv2d: small = grad_out, large = input; nn.ConvTranspose2d:
+// small = input, large = grad_out.  workspace: ffwm_conv_wgrad_workspace_bytes(...) bytes of device memory.
+extern "C" int ffwm_conv_wgrad(const ffwm_tensor4* small, const ffwm_tensor4* large, const ffwm_tensor4* grad_weight, int stride, int pad,
+                               void* workspace, int64_t workspace_bytes, void* stream) {
+    using namespace ffwm;
+    View<const float> sv, lv;
+    View<float> wv;
+    int rc;
+    if ((rc = make_view<const float>(small, "small", &sv))) return rc;
+    if ((rc = make_view<const float>(large, "large", &lv))) return rc;
+    if ((rc = make_view<float>(grad_weight, "grad_weight", &wv))) return rc;
+    if (sv.n != lv.n || wv.n != sv.c || wv.c != lv.c) {
+        set_error("conv_wgrad: grad_weight %dx%dx%dx%d does not match small %dx%d / large %dx%d channels", wv.n, wv.c, wv.h, wv.w, sv.n, sv.c, lv.n, lv.c);
+        return FFWM_ERR_SHAPE;
+    }
+    if ((int64_t)wv.n * wv.c * wv.h * wv.w == 0) return FFWM_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((int64_t)sv.n * sv.h * sv.w == 0) {      // empty batch: the gradient is zero
+        for (int a = 0; a < wv.n; ++a)
+            for (int b = 0; b < wv.c; ++b)
+                cudaMemset2DAsync(wv.p + a * wv.sb + b * wv.sc, sizeof(float) * wv.sh, 0, sizeof(float) * wv.w, wv.h, st);
+        return FFWM_OK;
+    }
+    WggGeo g;
+    if ((rc = wgg_setup(g, sv.n, sv.c, lv.c, sv.h, sv.w, lv.h, lv.w, wv.h, wv.w, stride, pad))) return rc;
+    const int64_t need = (int64_t)g.splits * g.tiles * 128 * g.nn * (int64_t)sizeof(float);
+    if (!workspace || workspace_bytes < need) { set_error("conv_wgrad: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes, (long long)need); return FFWM_ERR_SHAPE; }
+    if (g.splits > 65535) { set_error("conv_wgrad: grid too large"); return FFWM_ERR_TOO_LARGE; }
+    cudaError_t e = cudaFuncSetAttribute(conv_gen_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("conv_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
+    conv_gen_wgrad_tc_kernel<<<dim3(g.tiles, g.splits), WGG_PRODUCERS + 32, g.nstage * g.stage_bytes + 128, st>>>(sv, lv, static_cast<float*>(workspace), g);
+    if ((rc = check_launch("conv_wgrad"))) return rc;
+    const int64_t total = (int64_t)g.ca * g.cb * g.kh * g.kw;
+    conv_gen_wgrad_reduce_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 4096), 256, 0, st>>>(
+        static_cast<const float*>(workspace), wv.p, wv.sb, wv.sc, (int64_t)wv.sh, (int64_t)wv.sw, g);
+    return check_launch("conv_wgrad (reduce)");
+}

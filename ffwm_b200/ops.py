@@ -53,40 +53,84 @@ def grid_warp_backward(images, flow, grad_output, grad_images, grad_flow):
            L.t4(grad_images), L.t4(grad_flow), L.dtype_code(images))
 
 
-def conv3x3_pack_weights(weight, dgrad=False, nt=64):
+def conv3x3_pack_weights(weight, dgrad=False, nt=64, math=L.MATH_BF16X3):
     """(Cout,Cin,3,3) fp32 CUDA weight -> packed image for conv3x3_forward (dgrad: for the data gradient).
-    nt: output channels per CTA the image is laid out for (64; 128 is experimental, W = 128 only)."""
+    nt: output channels per CTA the image is laid out for (64, or 128 for W = 128); math: L.MATH_TF32X3 / L.MATH_BF16X3."""
     import ctypes
     import torch
     dev = L.require_cuda(weight)
     cout, cin = weight.shape[:2]
-    n = L.lib().ffwm_conv3x3_packed_floats_nt(int(cin if dgrad else cout), int(cout if dgrad else cin), int(nt))
+    n = L.lib().ffwm_conv3x3_packed_floats(int(cin if dgrad else cout), int(cout if dgrad else cin), int(nt), int(math))
     if n <= 0:
-        raise ValueError("conv3x3_pack_weights: bad shape or nt (cout %d, cin %d, nt %d)" % (cout, cin, nt))
+        raise ValueError("conv3x3_pack_weights: bad shape, nt or math (cout %d, cin %d, nt %d, math %d)" % (cout, cin, nt, math))
     packed = torch.empty(n, dtype=torch.float32, device=weight.device)
-    L.call("ffwm_conv3x3_pack_weights_nt", dev, L.t4(weight), int(bool(dgrad)), ctypes.c_void_p(packed.data_ptr()),
-           ctypes.c_int64(n), int(nt))
+    L.call("ffwm_conv3x3_pack_weights", dev, L.t4(weight), int(bool(dgrad)), ctypes.c_void_p(packed.data_ptr()),
+           ctypes.c_int64(n), int(nt), int(math))
     return packed
 
 
-def conv3x3_forward(x, packed, bias, out, nt=64):
+def conv3x3_forward(x, packed, bias, out, nt=64, math=L.MATH_BF16X3):
     import ctypes
     dev = L.require_cuda(x, packed, out)
-    L.call("ffwm_conv3x3_forward_nt", dev, L.t4(x), ctypes.c_void_p(packed.data_ptr()),
-           ctypes.c_void_p(bias.data_ptr() if bias is not None else None), L.t4(out), int(nt))
+    L.call("ffwm_conv3x3_forward", dev, L.t4(x), ctypes.c_void_p(packed.data_ptr()),
+           ctypes.c_void_p(bias.data_ptr() if bias is not None else None), L.t4(out), int(nt), int(math))
 
 
-def conv3x3_wgrad(x, grad_out, grad_weight, grad_bias=None):
+def conv_pack_weights(weight, in_major, stride, pad, transposed, math=L.MATH_BF16X3):
+    """Packed image of a (d0, d1, kh, kw) fp32 CUDA weight for conv_forward (csrc/conv_gen_tc.cu).  in_major: dim 0 is
+    the INPUT channel of the operation (ConvTranspose2d forward, Conv2d data gradient)."""
+    import ctypes
+    import torch
+    dev = L.require_cuda(weight)
+    n_out, n_in = (weight.size(1), weight.size(0)) if in_major else (weight.size(0), weight.size(1))
+    n = L.lib().ffwm_conv_packed_bytes(int(n_out), int(n_in), int(weight.size(2)), int(weight.size(3)), int(math))
+    if n <= 0:
+        raise ValueError("conv_pack_weights: unsupported weight shape %s" % (tuple(weight.shape),))
+    packed = torch.empty(n, dtype=torch.uint8, device=weight.device)
+    L.call("ffwm_conv_pack_weights", dev, L.t4(weight), int(bool(in_major)), int(stride), int(pad), int(bool(transposed)), int(math),
+           ctypes.c_void_p(packed.data_ptr()), ctypes.c_int64(n))
+    return packed
+
+
+def conv_forward(x, packed, bias, out, kh, kw, stride, pad, transposed, math=L.MATH_BF16X3):
+    """out = conv2d / conv_transpose2d(x, W, bias, stride, pad) on tcgen05, W packed by conv_pack_weights."""
+    import ctypes
+    dev = L.require_cuda(x, out)
+    L.require_cuda(packed)
+    if bias is not None and not (bias.is_cuda and bias.is_contiguous() and bias.dtype == x.dtype and bias.numel() == out.size(1)):
+        raise ValueError("conv_forward: bias must be a contiguous fp32 CUDA tensor of Cout elements")
+    L.call("ffwm_conv_forward", dev, L.t4(x), ctypes.c_void_p(packed.data_ptr()),
+           ctypes.c_void_p(bias.data_ptr() if bias is not None else None), L.t4(out), int(kh), int(kw), int(stride), int(pad),
+           int(bool(transposed)), int(math))
+
+
+def conv_wgrad(small, large, grad_weight, stride, pad):
+    """grad_weight (Ca,Cb,kh,kw; overwritten) = weight gradient of a convolution (csrc/conv_gen_wgrad_tc.cu).
+    nn.Conv2d: small = grad_out, large = input; nn.ConvTranspose2d: small = input, large = grad_out."""
+    import ctypes
+    import torch
+    dev = L.require_cuda(small, large, grad_weight)
+    n = L.lib().ffwm_conv_wgrad_workspace_bytes(int(small.size(0)), int(small.size(1)), int(large.size(1)), int(small.size(2)),
+                                                int(small.size(3)), int(large.size(2)), int(large.size(3)),
+                                                int(grad_weight.size(2)), int(grad_weight.size(3)), int(stride), int(pad))
+    if n <= 0:
+        raise RuntimeError("conv_wgrad: unsupported shapes: %s" % L.lib().ffwm_last_error().decode())
+    ws = torch.empty(n, dtype=torch.uint8, device=small.device)
+    L.call("ffwm_conv_wgrad", dev, L.t4(small), L.t4(large), L.t4(grad_weight), int(stride), int(pad),
+           ctypes.c_void_p(ws.data_ptr()), ctypes.c_int64(n))
+
+
+def conv3x3_wgrad(x, grad_out, grad_weight, grad_bias=None, math=L.MATH_BF16X3):
     """grad_weight (Cout,Cin,3,3, zero-filled by the caller) += weight gradient of the 3x3/s1/p1 convolution;
     grad_bias (Cout, contiguous fp32, zero-filled) += grad_out.sum((0,2,3)) if given.
-    EXPERIMENTAL (not yet run on a B200): see csrc/conv3x3_wgrad_tc.cu."""
+    Parity-green on a B200, not faster than cuDNN's fp32 engines: opt-in (ffwm_b200/conv.py FFWM_WGRAD_TC=1)."""
     import ctypes
     dev = L.require_cuda(x, grad_out, grad_weight, grad_bias)
     if grad_bias is not None and not (grad_bias.is_contiguous() and grad_bias.numel() == grad_out.size(1)
                                       and grad_bias.dtype == grad_out.dtype):
         raise ValueError("conv3x3_wgrad: grad_bias must be a contiguous fp32 tensor of Cout elements")
     L.call("ffwm_conv3x3_wgrad", dev, L.t4(x), L.t4(grad_out), L.t4(grad_weight),
-           ctypes.c_void_p(grad_bias.data_ptr() if grad_bias is not None else None))
+           ctypes.c_void_p(grad_bias.data_ptr() if grad_bias is not None else None), int(math))
 
 
 def mfm_forward(x, out):

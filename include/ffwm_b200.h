@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define FFWM_ABI_VERSION 1
+#define FFWM_ABI_VERSION 2
 
 enum { FFWM_F32 = 0, FFWM_F64 = 1 };
 
@@ -128,38 +128,56 @@ int ffwm_grid_warp_backward(const ffwm_tensor4* images, const ffwm_tensor4* flow
 int ffwm_set_option(const char* name, int value);
 int ffwm_get_option(const char* name);
 
-/* ---- 3x3 / stride 1 / pad 1 convolution on the tcgen05 tensor cores (fp32 in/out, 3xTF32) --------
- * Replaces the cuDNN call behind nn.Conv2d(Cin, Cout, 3, 1, 1).forward (models/base_networks.py:218-222,
- * 235-246: the generator's ResidualBlock / ConvBlock convolutions) for maps of width 128, 64, 32 or 16, and — with
- * weights packed with dgrad=1 — its data gradient.  Weights are packed once per weight update. */
-
-/* number of floats of the packed image of a (cout, cin, 3, 3) weight */
-int64_t ffwm_conv3x3_packed_floats(int cout, int cin);
-
-/* weight (Cout,Cin,3,3) fp32 (any strides) -> packed; dgrad=1 packs the weights of the data-gradient
- * convolution (channels swapped, taps flipped; needs ffwm_conv3x3_packed_floats(cin, cout) floats). */
-int ffwm_conv3x3_pack_weights(const ffwm_tensor4* weight, int dgrad, float* packed, int64_t packed_floats, void* stream);
-
+/* ---- 3x3 / stride 1 / pad 1 convolution on the tcgen05 tensor cores (csrc/conv3x3_tc.cu; fp32 in/out) -----------------
+ * Replaces the cuDNN call behind nn.Conv2d(Cin, Cout, 3, 1, 1).forward (models/base_networks.py:218-222,235-246: the
+ * generator's ResidualBlock / ConvBlock convolutions, and every other 3x3 stride-1 layer of the path) for maps of width
+ * 128, 64, 32 or 16, and — with weights packed with dgrad=1 — its data gradient.  Weights are packed once per update.
+ *   nt   = output channels per CTA (the MMA N) the image is laid out for: 64, or 128 (W = 128 only);
+ *   math = operand split: FFWM_MATH_TF32X3 (a = hi + lo in tf32, three MMAs: library-grade fp32 accuracy, used for
+ *          forward passes) or FFWM_MATH_BF16X3 (two bf16 parts, three MMAs at twice the rate: used for gradients, which
+ *          are linear in the operand error).  pack and forward must agree on nt and math. */
+enum { FFWM_MATH_TF32X3 = 0, FFWM_MATH_BF16X3 = 1 };
+int64_t ffwm_conv3x3_packed_floats(int cout, int cin, int nt, int math);
+/* weight (Cout,Cin,3,3) fp32 (any strides) -> packed; dgrad=1 packs the weights of the data-gradient convolution
+ * (channels swapped, taps flipped; needs ffwm_conv3x3_packed_floats(cin, cout, nt, math) floats). */
+int ffwm_conv3x3_pack_weights(const ffwm_tensor4* weight, int dgrad, float* packed, int64_t packed_floats, int nt, int math, void* stream);
 /* out (B,Cout,H,W) = conv2d(x (B,Cin,H,W), weight, bias, stride 1, padding 1), W in {128,64,32,16}; bias may be NULL. */
-int ffwm_conv3x3_forward(const ffwm_tensor4* x, const float* packed, const float* bias, const ffwm_tensor4* out, void* stream);
-
-/* The same three with an explicit CTA tile: nt = output channels per CTA (the MMA N) the weights are packed for.
- * nt = 64 is what the functions above use.  nt = 128 (W = 128 only) halves the shared-memory operand traffic per
- * FLOP; it is EXPERIMENTAL — written after the round-1 GPU budget was spent, not yet run on a B200 — and nothing
- * selects it unless asked to (ffwm_b200/conv.py: FFWM_CONV_NT128=1). */
-int64_t ffwm_conv3x3_packed_floats_nt(int cout, int cin, int nt);
-int ffwm_conv3x3_pack_weights_nt(const ffwm_tensor4* weight, int dgrad, float* packed, int64_t packed_floats, int nt, void* stream);
-int ffwm_conv3x3_forward_nt(const ffwm_tensor4* x, const float* packed, const float* bias, const ffwm_tensor4* out, int nt, void* stream);
+int ffwm_conv3x3_forward(const ffwm_tensor4* x, const float* packed, const float* bias, const ffwm_tensor4* out, int nt, int math, void* stream);
 
 /* Weight gradient of the same convolution (the grad_weight output of aten::convolution_backward behind
- * nn.Conv2d(Cin, Cout, 3, 1, 1), models/base_networks.py:218-222,235-246), tcgen05, 3xTF32:
+ * nn.Conv2d(Cin, Cout, 3, 1, 1), models/base_networks.py:218-222,235-246), tcgen05, split-K with fp32 REDs:
  *   grad_weight (Cout,Cin,3,3) += sum_{b,y,x} grad_out[b,co,y,x] * x[b,ci,y+ky-1,x+kx-1]   (zero padding)
- * grad_weight accumulates (zero-fill it: the K splits arrive as fp32 REDs); x (B,Cin,H,W), grad_out (B,Cout,H,W),
- * W % 32 == 0, any strides.  grad_bias (Cout floats, zero-filled, or NULL) += sum_{b,y,x} grad_out[b,co,y,x] — the
- * bias gradient falls out of staging grad_out and replaces a separate reduction.  EXPERIMENTAL: compiled and checked by a CPU emulation of its indexing, not yet run on
- * a B200 (written after the round-1 GPU budget was spent) — callers opt in with FFWM_WGRAD_TC=1. */
+ * grad_weight accumulates (zero-fill it); x (B,Cin,H,W), grad_out (B,Cout,H,W), W % 32 == 0, any strides.
+ * grad_bias (Cout floats, zero-filled, or NULL) += sum_{b,y,x} grad_out[b,co,y,x] (falls out of staging grad_out).
+ * Parity-green on a B200 (<= 1.6e-5 of max|dW|; cuDNN's fp32 engines measure 3-7e-5) but not faster than cuDNN's fp32
+ * weight gradient on the step's shapes (profiles/r02c_conv_wgrad_bf16.txt): callers opt in (FFWM_WGRAD_TC=1). */
 int ffwm_conv3x3_wgrad(const ffwm_tensor4* x, const ffwm_tensor4* grad_out, const ffwm_tensor4* grad_weight,
-                       float* grad_bias, void* stream);
+                       float* grad_bias, int math, void* stream);
+
+/* ---- general dense convolution on the tcgen05 tensor cores (csrc/conv_gen_tc.cu; fp32 in/out; math as above) ----------
+ * Replaces the cuDNN calls behind nn.Conv2d / nn.ConvTranspose2d for every other shape of the path: kernels up to 7x7,
+ * stride 1 or 2, any padding and map size (models/base_networks.py:30-57 conv / deconv / predict_flow, :208-246, :274-312
+ * generator stem, strided encoders, 1x1 residual inputs, :354-437 discriminator; lightcnn/light_cnn.py:13-26 5x5 / 1x1
+ * MFM layers; models/losses.py:398-519 VGG19 blocks 4-5), and the data gradient of each (aten::convolution_backward's
+ * grad_input).  groups = 1, dilation = 1, zero padding. */
+int64_t ffwm_conv_packed_bytes(int n_out, int n_in, int kh, int kw, int math);
+/* in_major = 0: weight[n_out][n_in][kh][kw] (Conv2d forward, ConvTranspose2d data gradient);
+ * in_major = 1: weight[n_in][n_out][kh][kw] (ConvTranspose2d forward, Conv2d data gradient).  Any strides. */
+int ffwm_conv_pack_weights(const ffwm_tensor4* weight, int in_major, int stride, int pad, int transposed, int math, void* packed,
+                           int64_t packed_bytes, void* stream);
+/* transposed = 0: out = conv2d(x, W, bias, stride, pad);  transposed = 1: out = conv_transpose2d(x, W, bias, stride, pad)
+ * with out's H, W in [(Hi-1)*stride - 2*pad + kh, +stride) (output_padding; as a data gradient: the forward input size).
+ * bias (Cout floats) may be NULL.  Layers too small to fill the GPU split K; their partial sums meet as fp32 REDs. */
+int ffwm_conv_forward(const ffwm_tensor4* x, const void* packed, const float* bias, const ffwm_tensor4* out, int kh, int kw,
+                      int stride, int pad, int transposed, int math, void* stream);
+
+/* Weight gradient of the same family (csrc/conv_gen_wgrad_tc.cu; aten::convolution_backward's grad_weight):
+ *   grad_weight[a][b][ky][kx] = sum_{n,y,x} small[n,a,y,x] * large[n,b,y*stride-pad+ky,x*stride-pad+kx]   (OVERWRITTEN)
+ * nn.Conv2d: small = grad_out, large = input; nn.ConvTranspose2d: small = input, large = grad_out; (a, b) are the first
+ * two dimensions of the weight either way.  Deterministic (split-K partials in `workspace`, summed in a fixed order). */
+int64_t ffwm_conv_wgrad_workspace_bytes(int n, int ca, int cb, int hs, int ws, int hl, int wl, int kh, int kw, int stride, int pad);
+int ffwm_conv_wgrad(const ffwm_tensor4* small, const ffwm_tensor4* large, const ffwm_tensor4* grad_weight, int stride, int pad,
+                    void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- LightCNN max-feature-map activation (lightcnn/light_cnn.py:13-26: `torch.max(out[0], out[1])` over the two
  * channel halves of the preceding conv / linear output) and its gradient, one streaming kernel each; ATen's

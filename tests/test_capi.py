@@ -69,38 +69,38 @@ def test_conv_entry_points_validate_without_gpu():
     from ffwm_b200 import _lib
     lib = _lib.lib()
     null = ctypes.c_void_p(0)
-    assert _lib.get_option("CONV_MATH") == 1 and _lib.get_option("DISABLE_TILED") == 0 and _lib.get_option("NO_SUCH") == -1
-    old = _lib.set_option("CONV_MATH", 0)                           # 3xTF32: K blocks of 8 channels
-    assert lib.ffwm_conv3x3_packed_floats_nt(195, 195, 64) == lib.ffwm_conv3x3_packed_floats(195, 195) == 4 * 25 * 9216
-    assert lib.ffwm_conv3x3_packed_floats_nt(195, 195, 128) == 2 * 25 * 18432
-    _lib.set_option("CONV_MATH", 1)                                 # 3xBF16: K blocks of 16 channels, same bytes each
-    assert lib.ffwm_conv3x3_packed_floats_nt(195, 195, 64) == 4 * 13 * 9216
-    _lib.set_option("CONV_MATH", old)
+    assert _lib.get_option("DISABLE_TILED") == 0 and _lib.get_option("NO_SUCH") == -1
+    assert _lib.set_option("FORCE_TILED", 1) == 0 and _lib.get_option("FFWM_FORCE_TILED") == 1 and _lib.set_option("FORCE_TILED", 0) == 1
     with pytest.raises(ValueError):
         _lib.set_option("NO_SUCH", 1)
-    assert lib.ffwm_conv3x3_packed_floats_nt(195, 195, 96) == 0 and lib.ffwm_conv3x3_packed_floats_nt(0, 8, 64) == 0
+    TF, BF = _lib.MATH_TF32X3, _lib.MATH_BF16X3
+    assert lib.ffwm_conv3x3_packed_floats(195, 195, 64, TF) == 4 * 25 * 9216           # 3xTF32: K blocks of 8 channels
+    assert lib.ffwm_conv3x3_packed_floats(195, 195, 128, TF) == 2 * 25 * 18432
+    assert lib.ffwm_conv3x3_packed_floats(195, 195, 64, BF) == 4 * 13 * 9216           # 3xBF16: K blocks of 16, same bytes each
+    assert lib.ffwm_conv3x3_packed_floats(195, 195, 96, BF) == 0 and lib.ffwm_conv3x3_packed_floats(0, 8, 64, BF) == 0
+    assert lib.ffwm_conv3x3_packed_floats(195, 195, 64, 2) == 0
     x64, o64 = torch.zeros(1, 8, 4, 64), torch.zeros(1, 128, 4, 64)
     fake = ctypes.c_void_p(16)                                      # non-null "packed" pointer, never dereferenced
-    rc = lib.ffwm_conv3x3_forward_nt(_lib.t4(x64), fake, null, _lib.t4(o64), 128, null)
+    rc = lib.ffwm_conv3x3_forward(_lib.t4(x64), fake, null, _lib.t4(o64), 128, BF, null)
     assert rc == -3 and b"nt must be 64" in lib.ffwm_last_error()  # the 128-channel tile exists for W = 128 only
-    rc = lib.ffwm_conv3x3_forward_nt(_lib.t4(x64), fake, null, _lib.t4(o64), 32, null)
+    rc = lib.ffwm_conv3x3_forward(_lib.t4(x64), fake, null, _lib.t4(o64), 32, BF, null)
     assert rc == -3
-    rc = lib.ffwm_conv3x3_forward_nt(_lib.t4(torch.zeros(1, 8, 4, 48)), fake, null, _lib.t4(torch.zeros(1, 8, 4, 48)), 64, null)
+    rc = lib.ffwm_conv3x3_forward(_lib.t4(torch.zeros(1, 8, 4, 48)), fake, null, _lib.t4(torch.zeros(1, 8, 4, 48)), 64, TF, null)
     assert rc == -2                                                 # width not in {128, 64, 32, 16}
     w = torch.zeros(16, 8, 3, 3)
-    rc = lib.ffwm_conv3x3_pack_weights_nt(_lib.t4(w), 0, fake, ctypes.c_int64(10), 64, null)
+    rc = lib.ffwm_conv3x3_pack_weights(_lib.t4(w), 0, fake, ctypes.c_int64(10), 64, BF, null)
     assert rc == -2 and b"too small" in lib.ffwm_last_error()
-    rc = lib.ffwm_conv3x3_pack_weights_nt(_lib.t4(w), 0, fake, ctypes.c_int64(1 << 20), 100, null)
+    rc = lib.ffwm_conv3x3_pack_weights(_lib.t4(w), 0, fake, ctypes.c_int64(1 << 20), 100, BF, null)
     assert rc == -3
     # weight gradient: W % 32, matching shapes, (Cout,Cin,3,3) target
     x, go = torch.zeros(1, 8, 4, 48), torch.zeros(1, 16, 4, 48)
-    rc = lib.ffwm_conv3x3_wgrad(_lib.t4(x), _lib.t4(go), _lib.t4(w), null, null)
+    rc = lib.ffwm_conv3x3_wgrad(_lib.t4(x), _lib.t4(go), _lib.t4(w), null, BF, null)
     assert rc == -2 and b"W % 32" in lib.ffwm_last_error()
     x, go = torch.zeros(1, 8, 4, 64), torch.zeros(1, 16, 4, 64)
-    rc = lib.ffwm_conv3x3_wgrad(_lib.t4(x), _lib.t4(go), _lib.t4(torch.zeros(16, 9, 3, 3)), null, null)
+    rc = lib.ffwm_conv3x3_wgrad(_lib.t4(x), _lib.t4(go), _lib.t4(torch.zeros(16, 9, 3, 3)), null, BF, null)
     assert rc == -2
     e = torch.zeros(0, 8, 4, 64)
-    assert lib.ffwm_conv3x3_wgrad(_lib.t4(e), _lib.t4(torch.zeros(0, 16, 4, 64)), _lib.t4(w), null, null) == 0
+    assert lib.ffwm_conv3x3_wgrad(_lib.t4(e), _lib.t4(torch.zeros(0, 16, 4, 64)), _lib.t4(w), null, BF, null) == 0
     # max-feature-map: sizes and pointers
     assert lib.ffwm_mfm_forward(null, null, ctypes.c_int64(0), ctypes.c_int64(5), null) == 0
     assert lib.ffwm_mfm_forward(null, null, ctypes.c_int64(2), ctypes.c_int64(5), null) == -1
@@ -150,26 +150,27 @@ def test_guided_filter_box_sums():
 
 
 def test_packed_weight_cache_invalidation(monkeypatch):
-    """conv._packed (opt-in FFWM_CACHE_PACKED): frozen leaves are packed once per (direction, tile) and re-packed
+    """conv._packed (FFWM_CACHE_PACKED, default on): frozen leaves are packed once per (direction, tile) and re-packed
     after any in-place update; trainable or derived weights are never cached.  (Packing itself is CUDA-only: mocked.)"""
     from ffwm_b200 import conv
     calls = []
-    monkeypatch.setattr(conv.ops, "conv3x3_pack_weights", lambda w, dgrad=False, nt=64: calls.append((dgrad, nt)) or object())
+    monkeypatch.setattr(conv.ops, "conv3x3_pack_weights", lambda w, dgrad=False, nt=64, math=1: calls.append((dgrad, nt)) or object())
     monkeypatch.setattr(conv, "CACHE_PACKED", True)
     w = torch.nn.Parameter(torch.zeros(8, 4, 3, 3), requires_grad=False)
-    a = conv._packed(w, False, 64)
-    assert conv._packed(w, False, 64) is a and len(calls) == 1
-    assert conv._packed(w, True, 64) is not a and conv._packed(w, False, 128) is not a and len(calls) == 3
+    a = conv._packed(w, False, 64, 1)
+    assert conv._packed(w, False, 64, 1) is a and len(calls) == 1
+    assert conv._packed(w, True, 64, 1) is not a and conv._packed(w, False, 128, 1) is not a and len(calls) == 3
+    assert conv._packed(w, False, 64, 0) is not a and len(calls) == 4         # another operand math: another image
     with torch.no_grad():
         w.add_(1.0)                                       # optimizer step / load_state_dict: version counter moves
-    assert conv._packed(w, False, 64) is not a and len(calls) == 4
+    assert conv._packed(w, False, 64, 1) is not a and len(calls) == 5
     w.data = torch.ones(8, 4, 3, 3)                       # storage swapped
-    conv._packed(w, False, 64)
-    assert len(calls) == 5
+    conv._packed(w, False, 64, 1)
+    assert len(calls) == 6
     t = torch.nn.Parameter(torch.zeros(8, 4, 3, 3))       # trainable: never cached
-    conv._packed(t, False, 64), conv._packed(t, False, 64)
-    conv._packed(w * 2, False, 64), conv._packed(w * 2, False, 64)   # derived (spectral norm): a new tensor per call
-    assert len(calls) == 9
+    conv._packed(t, False, 64, 1), conv._packed(t, False, 64, 1)
+    conv._packed(w * 2, False, 64, 1), conv._packed(w * 2, False, 64, 1)   # derived (spectral norm): a new tensor per call
+    assert len(calls) == 10
     monkeypatch.setattr(conv, "CACHE_PACKED", False)
-    conv._packed(w, False, 64), conv._packed(w, False, 64)
-    assert len(calls) == 11
+    conv._packed(w, False, 64, 1), conv._packed(w, False, 64, 1)
+    assert len(calls) == 12

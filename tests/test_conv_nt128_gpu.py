@@ -26,7 +26,7 @@ def test_conv3x3_forward_nt128_matches_fp64(b, cin, cout, h):
     want = F.conv2d(x.double(), w.double(), bias.double(), padding=1)
     xd, wd, bd = x.to(DEV), w.to(DEV), bias.to(DEV)
     out = torch.full((b, cout, h, 128), float("nan"), device=DEV)
-    ops.conv3x3_forward(xd, ops.conv3x3_pack_weights(wd, nt=128), bd, out, nt=128)
+    ops.conv3x3_forward(xd, ops.conv3x3_pack_weights(wd, nt=128), bd, out, nt=128)      # default math: 3xBF16
     torch.cuda.synchronize()
     assert rel(out.cpu(), want) <= (3e-5 if cin * 9 < 2048 else 5e-5)      # default operand math (3xBF16)
     out64 = torch.empty_like(out)

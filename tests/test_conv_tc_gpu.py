@@ -1,5 +1,5 @@
 """tcgen05 3x3 convolution (ffwm_b200/csrc/conv3x3_tc.cu) against PyTorch float64 on the same inputs, in both
-operand maths (option CONV_MATH: 0 = 3xTF32 split, 1 = 3xBF16 split, the default).
+operand maths (the `math` argument: 3xTF32 split — what forward passes use — and 3xBF16 split — gradients).
 Tolerance, relative to max|ref|: 2e-5 (5e-5 for K = 9*Cin > 2048) for 3xTF32, 3e-5 (5e-5) for 3xBF16 — both splits
 give fp32-level accuracy (cuDNN strict fp32 measures 1e-5..5e-5 on the same inputs, cuDNN TF32 2e-4..3e-4); the path's
 contract is 1e-4 (BASELINE north star).  SURVEY 7 "hard parts"."""
@@ -15,13 +15,23 @@ def rel(a, b):
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 
 
+class _Ops:
+    """ffwm_b200.ops with the operand math of this parametrisation bound to the convolution calls."""
+
+    def __init__(self, math):
+        from ffwm_b200 import ops as o
+        self.o, self.math, self.math_tol = o, math, 3e-5 if math else 2e-5
+
+    def conv3x3_pack_weights(self, w, **kw):
+        return self.o.conv3x3_pack_weights(w, math=self.math, **kw)
+
+    def conv3x3_forward(self, *a, **kw):
+        return self.o.conv3x3_forward(*a, math=self.math, **kw)
+
+
 @pytest.fixture(scope="module", params=[1, 0], ids=["bf16x3", "tf32x3"])
 def ops(request):
-    from ffwm_b200 import _lib, ops as o
-    old = _lib.set_option("CONV_MATH", request.param)
-    o.math_tol = 3e-5 if request.param else 2e-5
-    yield o
-    _lib.set_option("CONV_MATH", old)
+    return _Ops(request.param)
 
 
 @pytest.mark.parametrize("b,cin,cout,h,width", [(1, 8, 64, 4, 128), (2, 16, 64, 8, 128), (1, 3, 64, 128, 128), (2, 195, 195, 10, 128),

@@ -77,16 +77,30 @@ def test_generator_refuses_cpu_tensors(nets):
 
 
 # ------------------------------------------------------------------ GPU: every net, f64 and f32
-# fp32 tolerances (relative to max|ref|, reference = float64 CPU): plain conv stacks 2e-3 on cuDNN
-# FFMA, 1e-2 where the 3x3 layers run on the tcgen05 3xTF32 kernel (FlowNet: measured 7e-3 on the first
-# layer's weight gradient after 30 conv+BN(batch of 2) layers of back-propagation); the
-# generator's flow gradients pass through ~60 conv+BN(batch of 2) layers (3e-2).  LightCNN's
-# max-feature-map is piecewise linear: rounding flips a few max selections and reroutes their
-# gradient, so its input gradient is the noisiest quantity here — measured on B200 (scripts/
-# diag_lightcnn.py): forward 2e-5 / gradient max 4e-2, L2 1e-2 with the tcgen05 3xTF32 convolutions,
-# forward 9e-7 / gradient max 6e-3, L2 1.5e-3 with cuDNN FFMA fp32.  The float64 runs are the tight
-# check (1e-8; float64 never takes the tensor-core path).
-F32_TOL = {"flownet16": 1e-2, "netD": 2e-3, "lightcnn": 8e-2, "netG": 3e-2}
+# fp32 tolerances relative to max|ref| (reference = the reference's modules in float64 on the CPU), set from the
+# measurement on a B200 in profiles/r02h_network_accuracy.txt — (outputs, gradients), with what was measured:
+#                product (tcgen05, 3xTF32 forwards / 3xBF16 gradients)    cuDNN strict fp32      cuDNN TF32 (torch default)
+#   flownet16    1.2e-5 , 2.0e-5                                          1.4e-5 , 8.5e-6        4.5e-3 , 7.7e-2
+#   netD         1.5e-6 , 1.2e-5                                          1.3e-6 , 5.8e-7        5.2e-4 , 4.0e-2
+#   lightcnn     3.7e-5 , 4.1e-2                                          8.7e-7 , 5.7e-3        7.8e-4 , 1.3e-1
+#   netG         5.3e-5 , 2.5e-2                                          3.1e-5 , 1.4e-2        5.5e-3 , 1.8e-1
+# FlowNet and the discriminator are well conditioned and held to 1e-4 — the path's contract — end to end, gradients
+# included (30 conv + BatchNorm(batch of 2) layers of back-propagation).  LightCNN's max-feature-map is piecewise
+# linear: rounding flips a few max selections and reroutes their gradient, and the generator's gradients pass through
+# ~60 spectral-normed conv + BatchNorm layers; there even cuDNN's strict fp32 is 0.6-1.4e-2 away from float64, so those
+# gradients are held to a few times that.  LightCNN has no normalisation layers, so the tensor core's truncating fp32
+# accumulation (a systematic ~1e-6 shrink per layer) adds up over its 29 layers: outputs 4e-5.  The float64 runs are
+# the tight check (1e-8; float64 never takes the tensor-core path).
+F32_TOL = {"flownet16": (1e-4, 1e-4), "netD": (1e-4, 1e-4), "lightcnn": (1e-4, 8e-2), "netG": (2e-4, 5e-2)}
+
+
+def check_split(got, want, tol_out, tol_grad):
+    assert set(got) == set(want)
+    for k in want:
+        scale = max(float(np.abs(want[k]).max()), 1e-30)
+        err = float(np.abs(got[k] - want[k]).max()) / scale
+        rtol = tol_grad if k.startswith("grad/") else tol_out
+        assert err <= rtol, "%s: rel err %.3e > %.1e" % (k, err, rtol)
 
 
 @pytest.mark.gpu
@@ -94,7 +108,7 @@ F32_TOL = {"flownet16": 1e-2, "netD": 2e-3, "lightcnn": 8e-2, "netG": 3e-2}
 @pytest.mark.parametrize("which", ["flownet16", "netD", "lightcnn", "netG"])
 def test_networks_match_reference_on_gpu(nets, which, dt):
     B, L = nets
-    rtol = 1e-8 if dt == torch.float64 else F32_TOL[which]
+    tol_out, tol_grad = (1e-8, 1e-8) if dt == torch.float64 else F32_TOL[which]
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     dev = torch.device("cuda", 0)
@@ -106,4 +120,4 @@ def test_networks_match_reference_on_gpu(nets, which, dt):
         got = MC.run_lightcnn(MC.fill_state(L.LightCNN_29Layers(num_classes=100), dt).to(dev))
     else:
         got = MC.run_netg(MC.fill_state(B.FFWM(sn=True), dt).to(dev))
-    check(got, gold(which), rtol)
+    check_split(got, gold(which), tol_out, tol_grad)
