@@ -51,6 +51,10 @@ SIGNATURES = {
     "ffwm_conv_forward": [_T4P, _VP, _VP, _T4P, _I, _I, _I, _I, _I, _I, _VP],
     "ffwm_conv_wgrad_workspace_bytes": [_I] * 11,
     "ffwm_conv_wgrad": [_T4P, _T4P, _T4P, _I, _I, _VP, ctypes.c_int64, _VP],
+    "ffwm_affine_reg_forward": [_T4P, _VP, _T4P, _I, _I, _VP],
+    "ffwm_affine_reg_backward": [_T4P, _VP, _T4P, _T4P, _I, _I, _VP],
+    "ffwm_corr_max_workspace_bytes": [_I, _I, _I],
+    "ffwm_corr_max": [_T4P, _T4P, ctypes.c_float, _VP, _VP, ctypes.c_int64, _VP],
     "ffwm_mfm_forward": [_VP, _VP, ctypes.c_int64, ctypes.c_int64, _VP],
     "ffwm_mfm_backward": [_VP, _VP, _VP, ctypes.c_int64, ctypes.c_int64, _VP],
     "ffwm_guided_filter_forward": [_VP, _VP, _VP, _VP, _VP, ctypes.c_int64, _I, _I, _I, ctypes.c_float, _VP],
@@ -81,7 +85,8 @@ def lib():
             fn.restype = {"ffwm_last_error": ctypes.c_char_p, "ffwm_kernel_launches": ctypes.c_ulonglong,
                           "ffwm_conv3x3_packed_floats": ctypes.c_int64,
                           "ffwm_conv_packed_bytes": ctypes.c_int64,
-                          "ffwm_conv_wgrad_workspace_bytes": ctypes.c_int64}.get(name, ctypes.c_int)
+                          "ffwm_conv_wgrad_workspace_bytes": ctypes.c_int64,
+                          "ffwm_corr_max_workspace_bytes": ctypes.c_int64}.get(name, ctypes.c_int)
         if l.ffwm_abi_version() != ABI_VERSION:
             raise ImportError("ffwm_b200: ABI version mismatch (library %d, binding %d)"
                               % (l.ffwm_abi_version(), ABI_VERSION))

@@ -35,6 +35,29 @@ def _cuda_only(t):
         raise NotImplementedError  # models/external_function.py:37-38
 
 
+class AffineResidualFunction(Function):
+    """Per-window affine-fit residual w^T Q w / kz^2 of one grid plane (csrc/affine_reg.cu): the fused form of the
+    reference's conv2d -> LocalAttnReshape -> BlockExtractor -> multiply -> avg_pool2d chain (models/losses.py:211-219)."""
+
+    @staticmethod
+    def forward(ctx, grid, q, kz):
+        _cuda_only(grid)
+        grid = grid.contiguous()
+        ctx.save_for_backward(grid, q)
+        ctx.kz = kz
+        out = grid.new_empty((grid.size(0), 1, grid.size(2) - kz + 1, grid.size(3) - kz + 1))
+        ops.affine_reg_forward(grid, q, out, kz)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        grid, q = ctx.saved_tensors
+        grad_grid = torch.zeros_like(grid)                   # scatter target
+        ops.affine_reg_backward(grid, q, grad_out.contiguous(), grad_grid, ctx.kz)
+        return grad_grid, None, None
+
+
 class BlockExtractorFunction(Function):
     """models/external_function.py:19-56."""
 

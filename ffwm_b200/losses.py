@@ -24,9 +24,15 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import base_networks
+from . import base_networks, ops
 from .conv import Conv2d
-from .external_function import BlockExtractor, LocalAttnReshape, Resample2d, grid_warp
+from .external_function import AffineResidualFunction, BlockExtractor, LocalAttnReshape, Resample2d, grid_warp
+
+# the affine regularisation as one kernel per direction (csrc/affine_reg.cu) and the correlation column-max of
+# PerceptualCorrectness as a fused tcgen05 GEMM + running max (csrc/corr_max.cu) instead of the reference's chains of
+# library ops; FFWM_FUSED_AFFINE=0 / FFWM_FUSED_CORRMAX=0 restore those chains (A/B runs, and what the CPU tests exercise).
+FUSED_AFFINE = os.environ.get("FFWM_FUSED_AFFINE", "1") == "1"
+FUSED_CORRMAX = os.environ.get("FFWM_FUSED_CORRMAX", "1") == "1"
 
 
 class GANLoss(nn.Module):
@@ -208,6 +214,10 @@ class AffineRegularizationLoss(nn.Module):
         return self.calculate_loss(grid[:, 0:1], weights) + self.calculate_loss(grid[:, 1:2], weights)
 
     def calculate_loss(self, grid, weights):
+        if FUSED_AFFINE and grid.is_cuda and self.kz in (3, 5, 7):
+            # the whole chain below is w^T (K^T K) w / kz^2 per window: one kernel per direction (csrc/affine_reg.cu)
+            q = weights.reshape(self.kz ** 2, self.kz ** 2).contiguous()
+            return torch.mean(AffineResidualFunction.apply(grid, q, self.kz)) * self.kz ** 2
         results = F.conv2d(grid, weights)                       # [b, kz*kz, h', w']
         b, _, h, w = results.size()
         kernels_new = self.reshape(results, self.kz)            # K6: [b,1,kz*h',kz*w']
@@ -386,10 +396,15 @@ class PerceptualCorrectness(nn.Module):
         b, c, h, w = target_vgg.shape
         flow = F.interpolate(flow, [h, w])
         target_all = target_vgg.view(b, c, -1)                          # [b, C, N2]
-        source_all = source_vgg.view(b, c, -1).transpose(1, 2)          # [b, N2, C]
-        source_norm = source_all / (source_all.norm(dim=2, keepdim=True) + self.eps)
-        target_norm = target_all / (target_all.norm(dim=1, keepdim=True) + self.eps)
-        correction_max = self._column_max(source_norm, target_norm)     # [b, N2]
+        if (FUSED_CORRMAX and ops.corr_max_supported(target_vgg) and source_vgg.shape == target_vgg.shape
+                and not (source_vgg.requires_grad or target_vgg.requires_grad)):
+            # normalisation + [N2 x N2] product + max over the source axis without materialising anything (csrc/corr_max.cu)
+            correction_max = ops.corr_max(source_vgg, target_vgg, self.eps)
+        else:
+            source_all = source_vgg.view(b, c, -1).transpose(1, 2)      # [b, N2, C]
+            source_norm = source_all / (source_all.norm(dim=2, keepdim=True) + self.eps)
+            target_norm = target_all / (target_all.norm(dim=1, keepdim=True) + self.eps)
+            correction_max = self._column_max(source_norm, target_norm)     # [b, N2]
         input_sample = self._sample(source_vgg, flow, use_bilinear_sampling).view(b, c, -1)
         correction_sample = F.cosine_similarity(input_sample, target_all)
         loss_map = torch.exp(-correction_sample / (correction_max + self.eps))

@@ -120,6 +120,45 @@ def conv_wgrad(small, large, grad_weight, stride, pad):
            ctypes.c_void_p(ws.data_ptr()), ctypes.c_int64(n))
 
 
+def affine_reg_forward(grid, q, out, kz):
+    """out (B,1,H-kz+1,W-kz+1) = w^T Q w / kz^2 per kz x kz window of grid (B,1,H,W); q: (kz^2, kz^2) contiguous, same dtype."""
+    import ctypes
+    dev = L.require_cuda(grid, q, out)
+    if not (q.is_contiguous() and q.numel() == kz ** 4):
+        raise ValueError("affine_reg: Q must be a contiguous (kz^2, kz^2) matrix")
+    L.call("ffwm_affine_reg_forward", dev, L.t4(grid), ctypes.c_void_p(q.data_ptr()), L.t4(out), int(kz), L.dtype_code(grid))
+
+
+def affine_reg_backward(grid, q, grad_out, grad_grid, kz):
+    import ctypes
+    dev = L.require_cuda(grid, q, grad_out, grad_grid)
+    if not (q.is_contiguous() and q.numel() == kz ** 4):
+        raise ValueError("affine_reg: Q must be a contiguous (kz^2, kz^2) matrix")
+    L.call("ffwm_affine_reg_backward", dev, L.t4(grid), ctypes.c_void_p(q.data_ptr()), L.t4(grad_out), L.t4(grad_grid), int(kz),
+           L.dtype_code(grid))
+
+
+def corr_max_supported(x):
+    return x.is_cuda and x.dtype == __import__("torch").float32 and x.dim() == 4 and x.size(1) % 64 == 0 and x.size(1) <= 256
+
+
+def corr_max(source, target, eps):
+    """(B, H*W) column max of the cosine correlation between every source and target pixel (csrc/corr_max.cu)."""
+    import ctypes
+    import torch
+    dev = L.require_cuda(source, target)
+    source, target = source.contiguous(), target.contiguous()
+    b, c, h, w = source.shape
+    n = L.lib().ffwm_corr_max_workspace_bytes(int(b), int(c), int(h * w))
+    if n <= 0:
+        raise ValueError("corr_max: unsupported shape %s (C must be a multiple of 64 up to 256)" % (tuple(source.shape),))
+    ws = torch.empty(n, dtype=torch.uint8, device=source.device)
+    out = torch.empty((b, h * w), dtype=torch.float32, device=source.device)
+    L.call("ffwm_corr_max", dev, L.t4(source), L.t4(target), ctypes.c_float(eps), ctypes.c_void_p(out.data_ptr()),
+           ctypes.c_void_p(ws.data_ptr()), ctypes.c_int64(n))
+    return out
+
+
 def conv3x3_wgrad(x, grad_out, grad_weight, grad_bias=None, math=L.MATH_BF16X3):
     """grad_weight (Cout,Cin,3,3, zero-filled by the caller) += weight gradient of the 3x3/s1/p1 convolution;
     grad_bias (Cout, contiguous fp32, zero-filled) += grad_out.sum((0,2,3)) if given.

@@ -179,6 +179,27 @@ int64_t ffwm_conv_wgrad_workspace_bytes(int n, int ca, int cb, int hs, int ws, i
 int ffwm_conv_wgrad(const ffwm_tensor4* small, const ffwm_tensor4* large, const ffwm_tensor4* grad_weight, int stride, int pad,
                     void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- affine regularisation of FlowNet pre-training as one kernel per direction (csrc/affine_reg.cu) -------
+ * Replaces the five-pass chain of models/losses.py:211-219 (conv2d with the fixed (kz^2,1,kz,kz) kernel ->
+ * LocalAttnReshape -> BlockExtractor(flow = kz//2) -> multiply -> avg_pool2d):
+ *   out[b,0,y,x] = w^T Q w / kz^2,  w = the kz x kz window of grid (B,1,H,W) at (y,x),  out (B,1,H-kz+1,W-kz+1);
+ * Q (kz^2 x kz^2, row-major, device memory, dtype of the call) is the reference's K^T K; kz in {3,5,7}.
+ * backward: grad_grid (B,1,H,W) ACCUMULATES (zero-fill it) the gradient of sum(grad_out * out). */
+int ffwm_affine_reg_forward(const ffwm_tensor4* grid, const void* q, const ffwm_tensor4* out, int kz, int dtype, void* stream);
+int ffwm_affine_reg_backward(const ffwm_tensor4* grid, const void* q, const ffwm_tensor4* grad_out, const ffwm_tensor4* grad_grid,
+                             int kz, int dtype, void* stream);
+
+/* ---- correlation column-max of PerceptualCorrectness (csrc/corr_max.cu) ------------------------------------
+ * Replaces models/losses.py:347-353 (per-pixel cosine normalisation, bmm to a [b, N2, N2] product — 1.07 GB per sample at
+ * relu1_1 — and max over the source axis) with a normalising prepass + one tcgen05 GEMM whose epilogue keeps a running
+ * column max (3xBF16 split, fp32 accumulation):
+ *   cmax[b, j] = max_i < source[b,:,i] / (|source[b,:,i]| + eps) , target[b,:,j] / (|target[b,:,j]| + eps) >
+ * source, target (B, C, H, W) fp32, contiguous planes, C a multiple of 64 up to 256; cmax (B, H*W) floats.
+ * workspace: ffwm_corr_max_workspace_bytes(B, C, H*W) bytes of device memory (0 = unsupported shape). */
+int64_t ffwm_corr_max_workspace_bytes(int b, int c, int n);
+int ffwm_corr_max(const ffwm_tensor4* source, const ffwm_tensor4* target, float eps, float* cmax, void* workspace,
+                  int64_t workspace_bytes, void* stream);
+
 /* ---- LightCNN max-feature-map activation (lightcnn/light_cnn.py:13-26: `torch.max(out[0], out[1])` over the two
  * channel halves of the preceding conv / linear output) and its gradient, one streaming kernel each; ATen's
  * semantics incl. NaN propagation and tie splitting.  x (n, 2*chw) and out (n, chw) contiguous fp32; chw = C*H*W.
