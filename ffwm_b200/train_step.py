@@ -91,9 +91,11 @@ class FFWMTrainer:
         if distributed is not None:
             distributed.broadcast_module_states([self.netG, self.netD, self.flowNetF, self.flowNetB, self.lightCNN,
                                                  self.criterionPerceptual])
-            self.avg_D = GradAverager(list(self.netD.parameters()), distributed)
+            # eager steps launch the bucket all-reduces from inside the backward pass; CUDA-graph steps reduce one flat
+            # buffer per averager between two graph replays (parallel.GradAverager)
+            self.avg_D = GradAverager(list(self.netD.parameters()), distributed, in_backward=not graph)
             self.avg_G = GradAverager(list(self.netG.parameters()) + list(self.flowNetF.parameters())
-                                      + list(self.flowNetB.parameters()), distributed)
+                                      + list(self.flowNetB.parameters()), distributed, in_backward=not graph)
 
     # ------------------------------------------------------------------ input
     def set_input(self, batch):
@@ -185,16 +187,28 @@ class FFWMTrainer:
         self.loss_G = self.loss_iden + self.loss_l1 + self.loss_prc + self.loss_illu + self.loss_fc + self.loss_adv
         self.loss_G.backward()
 
+    def _zero_D(self):
+        if self.avg_D is not None:
+            self.avg_D.zero()              # data parallel: the gradients live in the averager's persistent buckets
+        else:
+            self._zero(self.optimizers_D)
+
+    def _zero_G(self):
+        if self.avg_G is not None:
+            self.avg_G.zero()
+        else:
+            self._zero(self.optimizers_G)
+
     def optimize_parameters(self):
         self.forward()
         set_requires_grad(self.netD, True)
-        self._zero(self.optimizers_D)
-        self.backward_D()
+        self._zero_D()
+        self.backward_D()                  # data parallel: bucket all-reduces start inside the backward pass (hooks)
         if self.avg_D is not None:
             self.avg_D.average()
         self._step(self.optimizers_D)
         set_requires_grad(self.netD, False)
-        self._zero(self.optimizers_G)
+        self._zero_G()
         self.backward_G()
         if self.avg_G is not None:
             self.avg_G.average()
@@ -209,9 +223,12 @@ class FFWMTrainer:
 
         Single process: one graph.  Data parallel: three graphs sharing one memory pool,
             [forward, backward_D]  | all-reduce D grads |  [step D, backward_G]  | all-reduce G,F grads |  [step G,F]
-        with the NCCL all-reduces issued eagerly between the replays (collectives are kept out of
-        the captured region on purpose: nothing about the capture depends on the communicator)."""
+        with the NCCL all-reduces issued eagerly between the replays, each ONE collective over the averager's persistent
+        flat gradient buffer (the captured backward passes accumulate straight into it: no pack / unpack copies, NCCL
+        AVG instead of a scaling pass).  Capturing the collectives into a single graph was measured and rejected
+        (parallel.GradAverager)."""
         assert self.device.type == "cuda" and self._capturable, "construct the trainer with graph=True"
+        flat_grads = self.avg_G is not None and self.avg_G.overlap      # gradients live in the averagers' flat buffers
         if segmented is None:
             segmented = self.avg_D is not None
         self._static = {k: (v.to(self.device).clone() if torch.is_tensor(v) else v) for k, v in example_batch.items()}
@@ -224,7 +241,8 @@ class FFWMTrainer:
                 self.optimize_parameters()
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
-        self._zero(self.optimizers)
+        if not flat_grads:
+            self._zero(self.optimizers)
         from . import _lib
         self._bind(self._static)
         n0 = _lib.kernel_launches()
@@ -238,13 +256,13 @@ class FFWMTrainer:
             with torch.cuda.graph(g1):
                 self.forward()
                 set_requires_grad(self.netD, True)
-                self._zero(self.optimizers_D)
+                self._zero_D()
                 self.backward_D()
             pool = g1.pool()
             with torch.cuda.graph(g2, pool=pool):
                 self._step(self.optimizers_D)
                 set_requires_grad(self.netD, False)
-                self._zero(self.optimizers_G)
+                self._zero_G()
                 self.backward_G()
             with torch.cuda.graph(g3, pool=pool):
                 self._step(self.optimizers_G)

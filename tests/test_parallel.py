@@ -1,4 +1,5 @@
 """Data-parallel plumbing on CPU: world_size 2, gloo."""
+import copy
 import os
 import socket
 
@@ -16,7 +17,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, overlap):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -28,27 +29,34 @@ def _worker(rank, world, port, q):
         d.broadcast_module_states([net, unused])
         w0 = net[0].weight.detach().clone()
         params = list(net.parameters()) + list(unused.parameters())
-        avg = GradAverager(params, d, bucket_bytes=64)    # tiny buckets: several all-reduces in flight
+        avg = GradAverager(params, d, bucket_bytes=64, overlap=overlap)    # tiny buckets: several all-reduces in flight
         results = []
-        for step in range(2):
-            for p in params:
-                p.grad = None
-            x = torch.full((4, 5), float(rank + 1 + step))
-            net(x).sum().backward()
-            local = [p.grad.numpy().copy() for p in net.parameters()]
+        for step in range(3):
+            avg.zero()                                    # (overlap: zero-fills the persistent buckets from step 2 on)
+            x = torch.full((4, 5), float(rank + 1 + step)) + torch.arange(20.).view(4, 5) * (rank + 1)
+            # this rank's own gradient, from a hook-free twin (in overlap mode the buckets are already being reduced
+            # while backward runs, so p.grad cannot be read "before the average")
+            twin = copy.deepcopy(net)
+            local = [g.numpy().copy() for g in torch.autograd.grad(twin(x).pow(2).sum(), list(twin.parameters()))]
+            net(x).pow(2).sum().backward()
             avg.average()
             results.append((local, [p.grad.numpy().copy() for p in net.parameters()]))
         assert all(p.grad is None for p in unused.parameters())
+        if overlap:                                       # the gradients live in the flat buckets: no pack / unpack copies
+            flats = [f for f, _ in avg._plan]
+            assert all(any(p.grad.data_ptr() >= f.data_ptr() and p.grad.data_ptr() < f.data_ptr() + f.numel() * 4 for f in flats)
+                       for p in net.parameters())
         q.put((rank, w0.numpy(), results))     # numpy: plain pickling, no shared-memory handles
     finally:
         dist.destroy_process_group()
 
 
-def test_grad_averager_and_broadcast_world2():
+@pytest.mark.parametrize("overlap", [True, False], ids=["overlapped-buckets", "pack-after-backward"])
+def test_grad_averager_and_broadcast_world2(overlap):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, overlap)) for r in range(2)]
     for p in procs:
         p.start()
     out = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
@@ -57,7 +65,7 @@ def test_grad_averager_and_broadcast_world2():
         assert p.exitcode == 0
     (_, w_a, res_a), (_, w_b, res_b) = out
     assert (w_a == w_b).all()                          # broadcast made the replicas identical
-    for step in range(2):
+    for step in range(3):
         (loc_a, avg_a), (loc_b, avg_b) = res_a[step], res_b[step]
         for la, lb, ga, gb in zip(loc_a, loc_b, avg_a, avg_b):
             assert abs(ga - (la + lb) / 2).max() <= 1e-6 * max(1.0, abs(ga).max())
