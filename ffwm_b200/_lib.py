@@ -55,6 +55,7 @@ SIGNATURES = {
     "ffwm_affine_reg_backward": [_T4P, _VP, _T4P, _T4P, _I, _I, _VP],
     "ffwm_corr_max_workspace_bytes": [_I, _I, _I],
     "ffwm_corr_max": [_T4P, _T4P, ctypes.c_float, _VP, _VP, ctypes.c_int64, _VP],
+    "ffwm_ingest_u8": [_VP, _VP, _VP, _I, _I, _I, _I, _VP],
     "ffwm_mfm_forward": [_VP, _VP, ctypes.c_int64, ctypes.c_int64, _VP],
     "ffwm_mfm_backward": [_VP, _VP, _VP, ctypes.c_int64, ctypes.c_int64, _VP],
     "ffwm_guided_filter_forward": [_VP, _VP, _VP, _VP, _VP, ctypes.c_int64, _I, _I, _I, ctypes.c_float, _VP],

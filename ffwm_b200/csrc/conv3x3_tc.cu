@@ -198,11 +198,10 @@ conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const f
         constexpr int NR = (G::IN_ROWS + PH - 1) / PH;             // rows per thread
         const int px = tid % WI, kc = (tid / WI) & 1, ph = tid / (2 * WI);
         const float* gp0 = x.p + b * x.sb + (int64_t)(y0 - 1) * x.sh + px * x.sw;
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int buf = kb & 1;
-            if (kb >= 2) mbar_wait(&bars[4 + buf], ((kb >> 1) - 1) & 1);          // MMAs of K block kb-2 done
+        // The loads go to registers, so K block kb+1 is LOADED before K block kb is split and stored (software pipeline,
+        // two register sets): L2 / HBM latency hides behind a whole K-block period.
+        auto load_kb = [&](int kb, float (&v)[NR][CPS]) {
             const int c0 = kb * KB + kc * CPS;
-            float v[NR][CPS];
 #pragma unroll
             for (int i = 0; i < NR; ++i) {
                 const int rr = ph + i * PH;
@@ -211,6 +210,10 @@ conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const f
                 for (int j = 0; j < CPS; ++j)
                     v[i][j] = (ok && c0 + j < x.c) ? __ldg(gp0 + (int64_t)(c0 + j) * x.sc + rr * x.sh) : 0.f;
             }
+        };
+        auto store_kb = [&](int kb, float (&v)[NR][CPS]) {
+            const int buf = kb & 1;
+            if (kb >= 2) mbar_wait(&bars[4 + buf], ((kb >> 1) - 1) & 1);          // MMAs of K block kb-2 done
             unsigned char* sA = cv_smem + buf * G::STAGE + kc * G::A_CHUNK;
 #pragma unroll
             for (int i = 0; i < NR; ++i) {
@@ -228,6 +231,16 @@ conv3x3_tc_kernel(View<const float> x, const float* __restrict__ packed, const f
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // my stores -> visible to the tensor core
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[buf])) : "memory");
+        };
+        float va[NR][CPS], vb[NR][CPS];
+        load_kb(0, va);
+        for (int kb = 0; kb < nkb; kb += 2) {
+            if (kb + 1 < nkb) load_kb(kb + 1, vb);
+            store_kb(kb, va);
+            if (kb + 1 < nkb) {
+                if (kb + 2 < nkb) load_kb(kb + 2, va);
+                store_kb(kb + 1, vb);
+            }
         }
     } else if (lane == 0) {
         // ================= issuer: weight copies + MMAs =================

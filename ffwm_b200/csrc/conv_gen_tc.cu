@@ -206,19 +206,11 @@ conv_gen_tc_kernel(View<const float> x, const unsigned char* __restrict__ packed
         const int ya = a * g.is, xb = b * g.is;
         const float* base = x.p + img * x.sb + (int64_t)ya * x.sh + (int64_t)xb * x.sw;
         const unsigned char* pk = packed + c.packed_off + (int64_t)cob * units * g.b_unit;
-        for (int k = 0; k < nst; ++k) {
-            const int slot = k % g.nstage;
-            if (k >= g.nstage) mbar_wait(&bars[4 + slot], ((k / g.nstage) - 1) & 1);    // MMAs that read this slot are done
+        // The gathers go to REGISTERS, so they do not depend on a free shared-memory slot: the loads of stage k+1 are
+        // issued before stage k is split and stored (software pipeline, two register sets) and their L2 / HBM latency
+        // hides behind a whole stage period instead of stalling every stage.
+        auto load_stage = [&](int k, float (&v)[GN_MAXU][CPS]) {
             const int u0 = (s0 + k) * g.upst, nu = min(g.upst, units - u0);
-            unsigned char* st = gn_smem + slot * g.stage_bytes;
-            if (tid == 0) {                                            // weights of the stage: one bulk copy
-                const uint32_t bar = smem_u32(&bars[slot]), bytes = (uint32_t)(nu * g.b_unit);
-                asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(st + a_stage)),
-                             "l"(pk + (int64_t)u0 * g.b_unit), "r"(bytes), "r"(bar)
-                             : "memory");
-            }
-            float v[GN_MAXU][CPS];
 #pragma unroll
             for (int u = 0; u < GN_MAXU; ++u) {
                 if (u < nu) {
@@ -231,11 +223,34 @@ conv_gen_tc_kernel(View<const float> x, const unsigned char* __restrict__ packed
                     for (int j = 0; j < CPS; ++j) v[u][j] = (ok && c0 + j < g.cin) ? __ldg(gp + (int64_t)j * x.sc) : 0.f;
                 }
             }
+        };
+        auto store_stage = [&](int k, float (&v)[GN_MAXU][CPS]) {
+            const int slot = k % g.nstage;
+            if (k >= g.nstage) mbar_wait(&bars[4 + slot], ((k / g.nstage) - 1) & 1);    // MMAs that read this slot are done
+            const int u0 = (s0 + k) * g.upst, nu = min(g.upst, units - u0);
+            unsigned char* st = gn_smem + slot * g.stage_bytes;
+            if (tid == 0) {                                            // weights of the stage: one bulk copy
+                const uint32_t bar = smem_u32(&bars[slot]), bytes = (uint32_t)(nu * g.b_unit);
+                asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(st + a_stage)),
+                             "l"(pk + (int64_t)u0 * g.b_unit), "r"(bytes), "r"(bar)
+                             : "memory");
+            }
 #pragma unroll
             for (int u = 0; u < GN_MAXU; ++u)
                 if (u < nu) split_store_m<BF>(st + u * GN_A_UNIT + kc * 2048 + m * 16, 4096, v[u]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[slot])) : "memory");
+        };
+        float va[GN_MAXU][CPS], vb[GN_MAXU][CPS];
+        load_stage(0, va);
+        for (int k = 0; k < nst; k += 2) {
+            if (k + 1 < nst) load_stage(k + 1, vb);
+            store_stage(k, va);
+            if (k + 1 < nst) {
+                if (k + 2 < nst) load_stage(k + 2, va);
+                store_stage(k + 1, vb);
+            }
         }
     } else if (lane == 0) {
         // ================= issuer =================

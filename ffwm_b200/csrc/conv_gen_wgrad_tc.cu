@@ -89,33 +89,29 @@ conv_gen_wgrad_tc_kernel(View<const float> S, View<const float> L, float* __rest
         const int px = tid & (WGG_KP - 1), g0 = tid / WGG_KP;              // pixel of the stage, first group (0..3)
         const int nbg = g.nb / 8;                                          // channel groups per tap
         const int ngB = g.nn / 8;                                          // groups of the B tile
-        for (int k = 0; k < nst; ++k) {
-            const int slot = k % g.nstage;
-            if (k >= g.nstage) mbar_wait(&bars[4 + slot], ((k / g.nstage) - 1) & 1);
-            unsigned char* sA = wg_smem + slot * g.stage_bytes;
-            unsigned char* sB = sA + 2 * WGG_A_PART;
+        // A stage is staged in chunks of 4 groups (32 values) per thread: chunk 0 = the 128 channels of S, chunks 1.. =
+        // 16 groups of the gathered L tile each.  The gathers go to registers, so chunk i+1 is LOADED before chunk i is
+        // split and stored (two register sets): global latency hides behind the previous chunk instead of stalling.
+        const int nchunk = 1 + (ngB + 15) / 16;
+        const int total = nst * nchunk;
+        auto load_chunk = [&](int ci, float (&v)[4][8]) {
+            const int k = ci / nchunk, j = ci - k * nchunk;
             const int64_t p = (int64_t)(st0 + k) * WGG_KP + px;
             const bool pv = p < g.npix;
             int xs = 0, ys = 0, img = 0;
             if (pv) { xs = (int)(p % g.ws); const int64_t q = p / g.ws; ys = (int)(q % g.hs); img = (int)(q / g.hs); }
-            // ---- A: S[img, a, ys, xs] for the 128 channels of the tile, 4 groups of 8 per thread
-            {
+            if (j == 0) {                                                  // S[img, a, ys, xs], 4 groups of 8 channels
                 const float* sp = S.p + img * S.sb + (int64_t)ys * S.sh + (int64_t)xs * S.sw;
-                float v[4][8];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int a0 = at * 128 + (g0 + 4 * i) * 8;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[i][j] = (pv && a0 + j < g.ca) ? __ldg(sp + (int64_t)(a0 + j) * S.sc) : 0.f;
+                    for (int e = 0; e < 8; ++e) v[i][e] = (pv && a0 + e < g.ca) ? __ldg(sp + (int64_t)(a0 + e) * S.sc) : 0.f;
                 }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) split_store_bf(sA + (g0 + 4 * i) * WGG_GROUP + px * 16, WGG_A_PART, v[i]);
-            }
-            // ---- B: L gathered at the tap's position, groups = (tap of the tile, 8 channels b)
-            const int yl0 = ys * g.stride - g.pad, xl0 = xs * g.stride - g.pad;
-            const float* lp = L.p + img * L.sb;
-            for (int gb = g0; gb < ngB; gb += 16) {                         // 4 groups per pass
-                float v[4][8];
+            } else {                                                       // L gathered at the tap's position
+                const int yl0 = ys * g.stride - g.pad, xl0 = xs * g.stride - g.pad;
+                const float* lp = L.p + img * L.sb;
+                const int gb = g0 + 16 * (j - 1);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int gg = gb + 4 * i;
@@ -125,14 +121,39 @@ conv_gen_wgrad_tc_kernel(View<const float> S, View<const float> L, float* __rest
                     const bool ok = pv && gg < ngB && tap < g.kh * g.kw && (unsigned)yl < (unsigned)g.hl && (unsigned)xl < (unsigned)g.wl;
                     const float* q = lp + (int64_t)yl * L.sh + (int64_t)xl * L.sw + (int64_t)b0 * L.sc;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[i][j] = (ok && b0 + j < g.cb) ? __ldg(q + (int64_t)j * L.sc) : 0.f;
+                    for (int e = 0; e < 8; ++e) v[i][e] = (ok && b0 + e < g.cb) ? __ldg(q + (int64_t)e * L.sc) : 0.f;
                 }
+            }
+        };
+        auto store_chunk = [&](int ci, float (&v)[4][8]) {
+            const int k = ci / nchunk, j = ci - k * nchunk;
+            const int slot = k % g.nstage;
+            unsigned char* sA = wg_smem + slot * g.stage_bytes;
+            if (j == 0) {
+                if (k >= g.nstage) mbar_wait(&bars[4 + slot], ((k / g.nstage) - 1) & 1);    // MMAs that read this slot are done
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split_store_bf(sA + (g0 + 4 * i) * WGG_GROUP + px * 16, WGG_A_PART, v[i]);
+            } else {
+                unsigned char* sB = sA + 2 * WGG_A_PART;
+                const int gb = g0 + 16 * (j - 1);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     if (gb + 4 * i < ngB) split_store_bf(sB + (gb + 4 * i) * WGG_GROUP + px * 16, g.b_part, v[i]);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[slot])) : "memory");
+            if (j == nchunk - 1) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[slot])) : "memory");
+            }
+        };
+        float va[4][8], vb[4][8];
+        load_chunk(0, va);
+        for (int ci = 0; ci < total; ci += 2) {
+            if (ci + 1 < total) load_chunk(ci + 1, vb);
+            store_chunk(ci, va);
+            if (ci + 1 < total) {
+                if (ci + 2 < total) load_chunk(ci + 2, va);
+                store_chunk(ci + 1, vb);
+            }
         }
     } else if (lane == 0) {
         // ================= issuer =================

@@ -159,6 +159,20 @@ def corr_max(source, target, eps):
     return out
 
 
+def ingest_u8(src, flip, out):
+    """out (B,C,H,W) fp32 = src (B,H,W,C) uint8 transposed, flipped left-right where flip[b] (uint8, or None), / 255."""
+    import ctypes
+    import torch
+    dev = L.require_cuda(out)
+    if not (src.is_cuda and src.dtype == torch.uint8 and src.is_contiguous() and out.is_contiguous() and out.dtype == torch.float32
+            and src.dim() == 4 and out.shape == (src.size(0), src.size(3), src.size(1), src.size(2))):
+        raise ValueError("ingest_u8: src (B,H,W,C) uint8 and out (B,C,H,W) float32, both dense CUDA tensors")
+    if flip is not None and not (flip.is_cuda and flip.dtype == torch.uint8 and flip.is_contiguous() and flip.numel() == src.size(0)):
+        raise ValueError("ingest_u8: flip must be B uint8 flags on the device")
+    L.call("ffwm_ingest_u8", dev, ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(flip.data_ptr() if flip is not None else None),
+           ctypes.c_void_p(out.data_ptr()), int(src.size(0)), int(src.size(1)), int(src.size(2)), int(src.size(3)))
+
+
 def conv3x3_wgrad(x, grad_out, grad_weight, grad_bias=None, math=L.MATH_BF16X3):
     """grad_weight (Cout,Cin,3,3, zero-filled by the caller) += weight gradient of the 3x3/s1/p1 convolution;
     grad_bias (Cout, contiguous fp32, zero-filled) += grad_out.sum((0,2,3)) if given.

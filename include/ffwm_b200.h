@@ -200,6 +200,13 @@ int64_t ffwm_corr_max_workspace_bytes(int b, int c, int n);
 int ffwm_corr_max(const ffwm_tensor4* source, const ffwm_tensor4* target, float eps, float* cmax, void* workspace,
                   int64_t workspace_bytes, void* stream);
 
+/* ---- input pipeline, tensor half (csrc/ingest.cu) -----------------------------------------------------------
+ * Replaces the per-sample host work of data/face_dataset.py:66-80 (left-right flip `img[:, ::-1, :]`, HWC -> CHW transpose,
+ * astype(float32), div(255)) for a whole batch: the batch crosses PCIe as uint8 and is converted on the device.
+ * dst (B,C,H,W) float32 = transpose(src (B,H,W,C) uint8, flipped left-right where flip[b] != 0) / 255; flip may be NULL;
+ * C in {1,3}; dense tensors.  Bit-identical to the reference's numpy / torch arithmetic. */
+int ffwm_ingest_u8(const void* src, const void* flip, float* dst, int b, int h, int w, int c, void* stream);
+
 /* ---- LightCNN max-feature-map activation (lightcnn/light_cnn.py:13-26: `torch.max(out[0], out[1])` over the two
  * channel halves of the preceding conv / linear output) and its gradient, one streaming kernel each; ATen's
  * semantics incl. NaN propagation and tie splitting.  x (n, 2*chw) and out (n, chw) contiguous fp32; chw = C*H*W.
