@@ -36,8 +36,8 @@ SHAPES = (("dres2 195->195 @128", 195, 195, 128), ("att2 128->128 @128", 128, 12
 
 
 def wgrad_bench(out_path):
-    """tcgen05 weight gradient (csrc/conv3x3_wgrad_tc.cu, incl. the zero fill of its target) vs cuDNN's strict-fp32
-    and TF32 weight gradients on the same shapes; errors against float64."""
+    """tcgen05 weight gradient (csrc/conv_gen_wgrad_tc.cu: split-K kernel + reduction) vs cuDNN's strict-fp32 and TF32
+    weight gradients on the same shapes; errors against float64."""
     from ffwm_b200 import ops
     dev = torch.device("cuda", 0)
     torch.backends.cudnn.benchmark = True
@@ -64,7 +64,6 @@ def wgrad_bench(out_path):
         w64 = w.double().requires_grad_()
         F.conv2d(x.double(), w64, None, padding=1).backward(go.double())
         ref = w64.grad
-        err_mine = float((gw.double() - ref).abs().max() / ref.abs().max())
         err_gen = float((gw2.double() - ref).abs().max() / ref.abs().max())
         torch.backends.cudnn.allow_tf32 = False
         t_fp32 = timeit(lambda: cudnn_wgrad(go, x, w))
@@ -72,18 +71,17 @@ def wgrad_bench(out_path):
         torch.backends.cudnn.allow_tf32 = True
         t_tf32 = timeit(lambda: cudnn_wgrad(go, x, w))
         err_tf32 = float((cudnn_wgrad(go, x, w).double() - ref).abs().max() / ref.abs().max())
-        rows.append(dict(shape=name, cin=cin, cout=cout, gflop=flop / 1e9, ms_tcgen05=t_mine, ms_cudnn_fp32=t_fp32, ms_general=t_gen,
-                         tflops_general=flop / t_gen / 1e9, err_general=err_gen,
-                         ms_cudnn_tf32=t_tf32, tflops_tcgen05=flop / t_mine / 1e9, err_tcgen05=err_mine,
+        rows.append(dict(shape=name, cin=cin, cout=cout, gflop=flop / 1e9, ms_cudnn_fp32=t_fp32, ms_tcgen05=t_gen,
+                         tflops_tcgen05=flop / t_gen / 1e9, err_tcgen05=err_gen, ms_cudnn_tf32=t_tf32,
                          err_cudnn_fp32=err_fp32, err_cudnn_tf32=err_tf32))
         del ref, w64
     os.makedirs(os.path.dirname(out_path), exist_ok=True)
     json.dump(rows, open(out_path, "w"), indent=1)
-    print("%-22s %8s %8s %8s %8s %8s %9s %9s %9s %9s" % ("wgrad shape", "3x3 ms", "gen ms", "fp32 ms", "tf32 ms", "gen TF/s", "err 3x3", "err gen", "err fp32", "err tf32"))
+    print("%-22s %8s %8s %8s %8s %9s %9s %9s" % ("wgrad shape", "tc ms", "fp32 ms", "tf32 ms", "TF/s", "err tc", "err fp32", "err tf32"))
     for r in rows:
-        print("%-22s %8.3f %8.3f %8.3f %8.3f %8.1f %9.1e %9.1e %9.1e %9.1e" % (
-            r["shape"], r["ms_tcgen05"], r["ms_general"], r["ms_cudnn_fp32"], r["ms_cudnn_tf32"], r["tflops_general"],
-            r["err_tcgen05"], r["err_general"], r["err_cudnn_fp32"], r["err_cudnn_tf32"]))
+        print("%-22s %8.3f %8.3f %8.3f %8.1f %9.1e %9.1e %9.1e" % (
+            r["shape"], r["ms_tcgen05"], r["ms_cudnn_fp32"], r["ms_cudnn_tf32"], r["tflops_tcgen05"],
+            r["err_tcgen05"], r["err_cudnn_fp32"], r["err_cudnn_tf32"]))
 
 
 def nt128_bench(out_path):
@@ -165,7 +163,7 @@ def gen_bench(out_path):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
-    ap.add_argument("--wgrad", action="store_true", help="measure the experimental tcgen05 weight gradient instead")
+    ap.add_argument("--wgrad", action="store_true", help="measure the tcgen05 weight gradient instead")
     ap.add_argument("--nt128", action="store_true", help="A/B the experimental 128-channel CTA tile on the W = 128 shapes")
     ap.add_argument("--gen", action="store_true", help="the general kernel (conv_gen_tc.cu) on the other shapes of the path")
     args = ap.parse_args()

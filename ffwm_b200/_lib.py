@@ -45,7 +45,6 @@ SIGNATURES = {
     "ffwm_conv3x3_packed_floats": [_I, _I, _I, _I],
     "ffwm_conv3x3_pack_weights": [_T4P, _I, _VP, ctypes.c_int64, _I, _I, _VP],
     "ffwm_conv3x3_forward": [_T4P, _VP, _VP, _T4P, _I, _I, _VP],
-    "ffwm_conv3x3_wgrad": [_T4P, _T4P, _T4P, _VP, _I, _VP],
     "ffwm_conv_packed_bytes": [_I, _I, _I, _I, _I],
     "ffwm_conv_pack_weights": [_T4P, _I, _I, _I, _I, _I, _VP, ctypes.c_int64, _VP],
     "ffwm_conv_forward": [_T4P, _VP, _VP, _T4P, _I, _I, _I, _I, _I, _I, _VP],

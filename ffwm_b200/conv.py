@@ -8,14 +8,10 @@ three decoder scales, FlowNet's 3x3 layers down to 32x32, VGG19's blocks 1-3 and
 layers at 64 and 32.  Everything else (strided 4x4 / 7x7 / 5x5 / 1x1 layers,
 maps of 16x16 and below) stays on cuDNN (library).
 
-    forward        conv3x3_tc (implicit GEMM, 3xTF32 split: fp32-level accuracy)
-    grad input     the same kernel with the weights packed transposed + flipped
-    grad weight    cuDNN (`aten.convolution_backward`, weight/bias outputs only) by default;
-                   FFWM_WGRAD_TC=1 opts in to the tcgen05 weight-gradient kernel (csrc/conv3x3_wgrad_tc.cu),
-                   which is EXPERIMENTAL: written after the round-1 GPU budget was spent, checked by a CPU
-                   emulation of its indexing only, not yet run or measured on a B200
-FFWM_CONV_NT128=1 selects 128 (instead of 64) output channels per CTA for the W = 128 layers with more than
-64 output channels — also experimental and unmeasured; the validated kernels are bit-identical either way.
+    forward        conv3x3_tc (implicit GEMM, 3xTF32 split: library-grade fp32 accuracy)
+    grad input     the same kernel with the weights packed transposed + flipped (3xBF16 split)
+    grad weight    csrc/conv_gen_wgrad_tc.cu (MN-major tcgen05 GEMM over pixels, deterministic split-K), for every layer
+FFWM_CONV_NT128=0 selects 64 (instead of 128) output channels per CTA for the W = 128 layers with more than 64 of them.
 
 The module is a drop-in `nn.Conv2d`: same parameters, same state_dict keys, spectral norm hooks work
 unchanged (the weight is re-packed on every call: 0.02 ms).
@@ -39,11 +35,6 @@ MATH_BWD = int(os.environ.get("FFWM_CONV_MATH_BWD", ops.L.MATH_BF16X3))
 # The kernel also handles width 16, but there a map is one or two CTAs per (image, channel tile) with a
 # long serial K loop: measured slower than cuDNN inside the train step (98.4 -> 101.8 ms), so it is off.
 WIDTHS = (128, 64, 32)
-WGRAD_TC = os.environ.get("FFWM_WGRAD_TC", "0") == "1"     # experimental, unmeasured: off unless asked for
-# its CTA tile is 128 output x 48 input channels: layers far below that (flow heads, RGB reconstructions,
-# the first convolutions on 3 channels: 0.7 % of the weight-gradient FLOPs of the step) stay on cuDNN
-WGRAD_MIN_COUT, WGRAD_MIN_CIN = 32, 16
-WGRAD_GEN_3X3 = os.environ.get("FFWM_WGRAD_GEN_3X3", "0") == "1"     # A/B: the general weight-gradient kernel for these layers too
 # experimental, unmeasured: 128 output channels per CTA for the W = 128 layers with more than 64 of them
 NT128 = os.environ.get("FFWM_CONV_NT128", "1") == "1"
 
@@ -114,20 +105,8 @@ class Conv3x3TCFunction(Function):
             gx = torch.empty_like(x)
             nt = _nt(grad_out.size(3), weight.size(1))
             ops.conv3x3_forward(grad_out, _packed(weight, True, nt, MATH_BWD), None, gx, nt=nt, math=MATH_BWD)
-        if WGRAD_GEN and WGRAD_GEN_3X3 and (ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])):
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             gw, gb = _wgrad(grad_out, x, weight, ctx.has_bias, 1, 1, False, 0, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
-        elif WGRAD_TC and weight.size(0) >= WGRAD_MIN_COUT and weight.size(1) >= WGRAD_MIN_CIN:
-            want_b = ctx.has_bias and ctx.needs_input_grad[2]
-            if ctx.needs_input_grad[1]:
-                gw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
-                gb = grad_out.new_zeros(weight.size(0)) if want_b else None    # falls out of staging grad_out
-                ops.conv3x3_wgrad(x, grad_out, gw, gb, math=MATH_BWD)
-            elif want_b:
-                gb = grad_out.sum((0, 2, 3))
-        elif ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            _, gw, gb = torch.ops.aten.convolution_backward(
-                grad_out, x, weight, [weight.size(0)] if ctx.has_bias else None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
-                [False, bool(ctx.needs_input_grad[1]), bool(ctx.has_bias and ctx.needs_input_grad[2])])
         return gx, gw, gb
 
 

@@ -76,7 +76,6 @@ enum Opt {
     OPT_DISABLE_QUAD,
     OPT_GQ_SCALAR_FILL,
     OPT_SCATTER_SCALAR_FLUSH,
-    OPT_WGRAD_DIRECT_EPILOGUE,
     OPT_COUNT
 };
 int opt(int id);

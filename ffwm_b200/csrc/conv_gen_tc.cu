@@ -45,6 +45,7 @@ constexpr int GN_A_UNIT = 2 * 2 * 128 * 16;      // [part][k-chunk][128 pixels][
 constexpr int GN_SMEM_LIMIT = 227 * 1024 - 256;
 
 struct GnTap { int8_t dy, dx; uint8_t ky, kx; };
+__device__ const float gn_zero[4] = {0.f, 0.f, 0.f, 0.f};   // where the loads of an out-of-image tap are pointed
 struct GnClass {
     int oy0, ox0;         // first output row / column of the class
     int hc, wc;           // class grid
@@ -209,18 +210,28 @@ conv_gen_tc_kernel(View<const float> x, const unsigned char* __restrict__ packed
         // The gathers go to REGISTERS, so they do not depend on a free shared-memory slot: the loads of stage k+1 are
         // issued before stage k is split and stored (software pipeline, two register sets) and their L2 / HBM latency
         // hides behind a whole stage period instead of stalling every stage.
+        // A load is `base + j * stride` with an immediate j; an out-of-image tap (or a pixel past the end) turns base into a
+        // zero word and the stride into 0 instead of predicating every load; only the last K block of a tensor whose
+        // channel count is not a multiple of the slot width takes the predicated path (warp-uniform).
         auto load_stage = [&](int k, float (&v)[GN_MAXU][CPS]) {
             const int u0 = (s0 + k) * g.upst, nu = min(g.upst, units - u0);
+            int kb = u0 / c.ntaps, t = u0 - kb * c.ntaps;
 #pragma unroll
             for (int u = 0; u < GN_MAXU; ++u) {
                 if (u < nu) {
-                    const int unit = u0 + u, kb = unit / c.ntaps, t = unit - kb * c.ntaps;
                     const GnTap tp = g.taps[c.tap0 + t];
                     const bool ok = pv && (unsigned)(ya + tp.dy) < (unsigned)g.hi && (unsigned)(xb + tp.dx) < (unsigned)g.wi;
                     const int c0 = kb * (2 * CPS) + kc * CPS;
-                    const float* gp = base + (int64_t)tp.dy * x.sh + (int64_t)tp.dx * x.sw + (int64_t)c0 * x.sc;
+                    const float* gp = ok ? base + (int64_t)tp.dy * x.sh + (int64_t)tp.dx * x.sw + (int64_t)c0 * x.sc : gn_zero;
+                    const int64_t str = ok ? x.sc : 0;
+                    if (c0 + CPS <= g.cin) {
 #pragma unroll
-                    for (int j = 0; j < CPS; ++j) v[u][j] = (ok && c0 + j < g.cin) ? __ldg(gp + (int64_t)j * x.sc) : 0.f;
+                        for (int j = 0; j < CPS; ++j) v[u][j] = __ldg(gp + j * str);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CPS; ++j) v[u][j] = c0 + j < g.cin ? __ldg(gp + j * str) : 0.f;
+                    }
+                    if (++t == c.ntaps) { t = 0; ++kb; }
                 }
             }
         };

@@ -17,7 +17,7 @@
 //   * M = 128 channels `a` of S;  N = TG x NB = (tap group) x (channels b of L, a multiple of 8), tap-major, up to 256:
 //     rows of the B tile are L gathered at the tap's shifted position, so L is read once per tap through L1 / L2.
 //   * a stage = 64 pixels of the linearised (n, y, x) range of S (4 K steps x 3 MMAs of the split), ring of 2-3 stages,
-//     producers / issuer / epilogue on mbarriers as in the other tcgen05 kernels.
+//     16 producer warps / issuer / epilogue (8 of the producer warps) on mbarriers as in the other tcgen05 kernels.
 //   * split K: the pixel range is cut over blockIdx.y (at most 64 stages per CTA: bounds the truncating fp32 accumulation
 //     chain to 768 updates).  Partial tiles go to a caller-provided workspace with plain 64-byte-per-lane stores and a
 //     second kernel sums the splits into dW in a fixed order: deterministic, no atomics, no zero-fill contract.
@@ -31,11 +31,13 @@
 
 namespace ffwm {
 
-constexpr int WGG_PRODUCERS = 256;
+constexpr int WGG_PRODUCERS = 512;                // 16 producer warps (4 per scheduler: the gathers are latency- and issue-bound)
+constexpr int WGG_GQ = WGG_PRODUCERS / 64;         // group quarters: thread -> (pixel of the stage, first group)
+__device__ const float wgg_zero[4] = {0.f, 0.f, 0.f, 0.f};   // where the loads of an out-of-image tap are pointed
 constexpr int WGG_KP = 64;                         // pixels per stage
 constexpr int WGG_GROUP = WGG_KP * 16;             // bytes of one 8-channel group of a tile part: [64 pixels][16 B]
 constexpr int WGG_A_PART = 16 * WGG_GROUP;         // 128 channels
-constexpr int WGG_MAX_STAGES = 64;                 // per CTA (accuracy, see conv3x3_wgrad_tc.cu)
+constexpr int WGG_MAX_STAGES = 64;                 // per CTA: the tensor core adds into its fp32 accumulators with truncation, so the error grows with the chain (768 updates: ~1.5e-5 of max|dW| measured)
 
 struct WggGeo {
     int n, hs, ws, hl, wl;       // S (n, ca, hs, ws), L (n, cb, hl, wl)
@@ -86,73 +88,85 @@ conv_gen_wgrad_tc_kernel(View<const float> S, View<const float> L, float* __rest
 
     if (warp < WGG_PRODUCERS / 32) {
         // ================= producers =================
-        const int px = tid & (WGG_KP - 1), g0 = tid / WGG_KP;              // pixel of the stage, first group (0..3)
+        // Everything that does not depend on the stage is formed once: the thread's 2 groups of S channels and its up to
+        // 4 groups of the gathered L tile (tap, first channel, valid channel count) — the stage loop is loads, splits and
+        // stores only; the pixel coordinates advance incrementally (no 64-bit division per stage).  A load is
+        // `base + e * stride` with an immediate e; an out-of-image tap (or a pixel past the end) turns base into a zero
+        // word and the stride into 0 instead of predicating eight loads.
+        constexpr int NA = 16 / WGG_GQ, NB = 32 / WGG_GQ;                   // groups per thread
+        const int px = tid & (WGG_KP - 1), g0 = tid / WGG_KP;              // pixel of the stage, first group (0..7)
         const int nbg = g.nb / 8;                                          // channel groups per tap
         const int ngB = g.nn / 8;                                          // groups of the B tile
-        // A stage is staged in chunks of 4 groups (32 values) per thread: chunk 0 = the 128 channels of S, chunks 1.. =
-        // 16 groups of the gathered L tile each.  The gathers go to registers, so chunk i+1 is LOADED before chunk i is
-        // split and stored (two register sets): global latency hides behind the previous chunk instead of stalling.
-        const int nchunk = 1 + (ngB + 15) / 16;
-        const int total = nst * nchunk;
-        auto load_chunk = [&](int ci, float (&v)[4][8]) {
-            const int k = ci / nchunk, j = ci - k * nchunk;
-            const int64_t p = (int64_t)(st0 + k) * WGG_KP + px;
-            const bool pv = p < g.npix;
-            int xs = 0, ys = 0, img = 0;
-            if (pv) { xs = (int)(p % g.ws); const int64_t q = p / g.ws; ys = (int)(q % g.hs); img = (int)(q / g.hs); }
-            if (j == 0) {                                                  // S[img, a, ys, xs], 4 groups of 8 channels
-                const float* sp = S.p + img * S.sb + (int64_t)ys * S.sh + (int64_t)xs * S.sw;
+        const int T = g.kh * g.kw;
+        int64_t a_off[NA];
+        int a_cnt[NA];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int a0 = at * 128 + (g0 + 4 * i) * 8;
+        for (int i = 0; i < NA; ++i) {
+            const int a0 = at * 128 + (g0 + WGG_GQ * i) * 8;
+            a_off[i] = (int64_t)a0 * S.sc;
+            a_cnt[i] = max(0, min(8, g.ca - a0));
+        }
+        int64_t b_off[NB];
+        int b_kyx[NB], b_cnt[NB];                                          // ky | kx << 8; valid channels (0: group unused)
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) v[i][e] = (pv && a0 + e < g.ca) ? __ldg(sp + (int64_t)(a0 + e) * S.sc) : 0.f;
-                }
-            } else {                                                       // L gathered at the tap's position
-                const int yl0 = ys * g.stride - g.pad, xl0 = xs * g.stride - g.pad;
-                const float* lp = L.p + img * L.sb;
-                const int gb = g0 + 16 * (j - 1);
+        for (int j = 0; j < NB; ++j) {
+            const int gg = g0 + WGG_GQ * j;
+            const int tl = gg / nbg, b0 = bt * g.nb + (gg - tl * nbg) * 8;
+            const int tap = tgi * g.tg + tl, ky = tap / g.kw, kx = tap - ky * g.kw;
+            const bool ok = gg < ngB && tap < T;
+            b_kyx[j] = ky | (kx << 8);
+            b_cnt[j] = ok ? max(0, min(8, g.cb - b0)) : 0;
+            b_off[j] = (int64_t)b0 * L.sc + (int64_t)ky * L.sh + (int64_t)kx * L.sw;
+        }
+        // 8 channels at `q`, `str` elements apart; cnt < 8 only for the last group of a tensor (warp-uniform)
+        auto load8 = [](const float* q, int64_t str, int cnt, float (&v)[8]) {
+            if (cnt == 8) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int gg = gb + 4 * i;
-                    const int tl = gg / nbg, b0 = bt * g.nb + (gg - tl * nbg) * 8;
-                    const int tap = tgi * g.tg + tl, ky = tap / g.kw, kx = tap - ky * g.kw;
-                    const int yl = yl0 + ky, xl = xl0 + kx;
-                    const bool ok = pv && gg < ngB && tap < g.kh * g.kw && (unsigned)yl < (unsigned)g.hl && (unsigned)xl < (unsigned)g.wl;
-                    const float* q = lp + (int64_t)yl * L.sh + (int64_t)xl * L.sw + (int64_t)b0 * L.sc;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[i][e] = (ok && b0 + e < g.cb) ? __ldg(q + (int64_t)e * L.sc) : 0.f;
-                }
-            }
-        };
-        auto store_chunk = [&](int ci, float (&v)[4][8]) {
-            const int k = ci / nchunk, j = ci - k * nchunk;
-            const int slot = k % g.nstage;
-            unsigned char* sA = wg_smem + slot * g.stage_bytes;
-            if (j == 0) {
-                if (k >= g.nstage) mbar_wait(&bars[4 + slot], ((k / g.nstage) - 1) & 1);    // MMAs that read this slot are done
-#pragma unroll
-                for (int i = 0; i < 4; ++i) split_store_bf(sA + (g0 + 4 * i) * WGG_GROUP + px * 16, WGG_A_PART, v[i]);
+                for (int e = 0; e < 8; ++e) v[e] = __ldg(q + e * str);
             } else {
-                unsigned char* sB = sA + 2 * WGG_A_PART;
-                const int gb = g0 + 16 * (j - 1);
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (gb + 4 * i < ngB) split_store_bf(sB + (gb + 4 * i) * WGG_GROUP + px * 16, g.b_part, v[i]);
-            }
-            if (j == nchunk - 1) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[slot])) : "memory");
+                for (int e = 0; e < 8; ++e) v[e] = e < cnt ? __ldg(q + e * str) : 0.f;
             }
         };
-        float va[4][8], vb[4][8];
-        load_chunk(0, va);
-        for (int ci = 0; ci < total; ci += 2) {
-            if (ci + 1 < total) load_chunk(ci + 1, vb);
-            store_chunk(ci, va);
-            if (ci + 1 < total) {
-                if (ci + 2 < total) load_chunk(ci + 2, va);
-                store_chunk(ci + 1, vb);
+        // pixel of this thread in the first stage; later stages advance by WGG_KP pixels
+        int64_t p = (int64_t)st0 * WGG_KP + px;
+        int xs = (int)(p % g.ws), ys = (int)((p / g.ws) % g.hs), img = (int)(p / ((int64_t)g.ws * g.hs));
+        for (int k = 0; k < nst; ++k) {
+            const bool pv = p < g.npix;
+            const float* sp = pv ? S.p + img * S.sb + (int64_t)ys * S.sh + (int64_t)xs * S.sw : wgg_zero;
+            const int64_t s_str = pv ? S.sc : 0;
+            const int yl0 = ys * g.stride - g.pad, xl0 = xs * g.stride - g.pad;
+            const float* lp = L.p + img * L.sb + (int64_t)yl0 * L.sh + (int64_t)xl0 * L.sw;
+            float va[NA][8], vb[NB][8];
+#pragma unroll
+            for (int i = 0; i < NA; ++i) load8(pv ? sp + a_off[i] : wgg_zero, s_str, a_cnt[i], va[i]);
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                if (g0 + WGG_GQ * j < ngB) {                               // uniform over the 64 threads of a group quarter
+                    const int ky = b_kyx[j] & 255, kx = b_kyx[j] >> 8;
+                    const bool ok = pv && (unsigned)(yl0 + ky) < (unsigned)g.hl && (unsigned)(xl0 + kx) < (unsigned)g.wl;
+                    load8(ok ? lp + b_off[j] : wgg_zero, ok ? L.sc : 0, b_cnt[j], vb[j]);
+                }
+            }
+            const int slot = k % g.nstage;
+            if (k >= g.nstage) mbar_wait(&bars[4 + slot], ((k / g.nstage) - 1) & 1);        // MMAs that read this slot are done
+            unsigned char* sA = wg_smem + slot * g.stage_bytes;
+            unsigned char* sB = sA + 2 * WGG_A_PART;
+#pragma unroll
+            for (int i = 0; i < NA; ++i) split_store_bf(sA + (g0 + WGG_GQ * i) * WGG_GROUP + px * 16, WGG_A_PART, va[i]);
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+                if (g0 + WGG_GQ * j < ngB) split_store_bf(sB + (g0 + WGG_GQ * j) * WGG_GROUP + px * 16, g.b_part, vb[j]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[slot])) : "memory");
+            // next stage: WGG_KP pixels further along (n, y, x)
+            p += WGG_KP;
+            xs += WGG_KP;
+            if (xs >= g.ws) {
+                const int q = xs / g.ws;
+                xs -= q * g.ws;
+                ys += q;
+                if (ys >= g.hs) { const int r = ys / g.hs; ys -= r * g.hs; img += r; }
             }
         }
     } else if (lane == 0) {
@@ -176,7 +190,7 @@ conv_gen_wgrad_tc_kernel(View<const float> S, View<const float> L, float* __rest
     }
 
     // ---- epilogue: the partial tile [128 a][nn] of this split -> workspace (each lane: runs of 16 consecutive floats)
-    if (warp < WGG_PRODUCERS / 32) {
+    if (warp < 8) {
         const int last = nst - 1;
         mbar_wait(&bars[4 + last % g.nstage], (last / g.nstage) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

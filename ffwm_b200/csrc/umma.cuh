@@ -1,5 +1,5 @@
 // tcgen05 / mbarrier building blocks shared by the tensor-core convolution kernels
-// (conv3x3_tc.cu: forward + data gradient, conv3x3_wgrad_tc.cu: weight gradient).
+// (conv3x3_tc.cu, conv_gen_tc.cu: forward + data gradient; conv_gen_wgrad_tc.cu: weight gradient; corr_max.cu).
 // Every encoding here was validated on a B200 through conv3x3_tc.cu's parity tests.
 #pragma once
 #include <cuda_bf16.h>

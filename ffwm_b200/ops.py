@@ -173,19 +173,6 @@ def ingest_u8(src, flip, out):
            ctypes.c_void_p(out.data_ptr()), int(src.size(0)), int(src.size(1)), int(src.size(2)), int(src.size(3)))
 
 
-def conv3x3_wgrad(x, grad_out, grad_weight, grad_bias=None, math=L.MATH_BF16X3):
-    """grad_weight (Cout,Cin,3,3, zero-filled by the caller) += weight gradient of the 3x3/s1/p1 convolution;
-    grad_bias (Cout, contiguous fp32, zero-filled) += grad_out.sum((0,2,3)) if given.
-    Parity-green on a B200, not faster than cuDNN's fp32 engines: opt-in (ffwm_b200/conv.py FFWM_WGRAD_TC=1)."""
-    import ctypes
-    dev = L.require_cuda(x, grad_out, grad_weight, grad_bias)
-    if grad_bias is not None and not (grad_bias.is_contiguous() and grad_bias.numel() == grad_out.size(1)
-                                      and grad_bias.dtype == grad_out.dtype):
-        raise ValueError("conv3x3_wgrad: grad_bias must be a contiguous fp32 tensor of Cout elements")
-    L.call("ffwm_conv3x3_wgrad", dev, L.t4(x), L.t4(grad_out), L.t4(grad_weight),
-           ctypes.c_void_p(grad_bias.data_ptr() if grad_bias is not None else None), int(math))
-
-
 def mfm_forward(x, out):
     """out (N,C,...) = elementwise max of the two channel halves of x (N,2C,...); contiguous fp32 CUDA tensors.
     EXPERIMENTAL (not yet run on a B200): see csrc/mfm.cu."""

@@ -144,16 +144,6 @@ int ffwm_conv3x3_pack_weights(const ffwm_tensor4* weight, int dgrad, float* pack
 /* out (B,Cout,H,W) = conv2d(x (B,Cin,H,W), weight, bias, stride 1, padding 1), W in {128,64,32,16}; bias may be NULL. */
 int ffwm_conv3x3_forward(const ffwm_tensor4* x, const float* packed, const float* bias, const ffwm_tensor4* out, int nt, int math, void* stream);
 
-/* Weight gradient of the same convolution (the grad_weight output of aten::convolution_backward behind
- * nn.Conv2d(Cin, Cout, 3, 1, 1), models/base_networks.py:218-222,235-246), tcgen05, split-K with fp32 REDs:
- *   grad_weight (Cout,Cin,3,3) += sum_{b,y,x} grad_out[b,co,y,x] * x[b,ci,y+ky-1,x+kx-1]   (zero padding)
- * grad_weight accumulates (zero-fill it); x (B,Cin,H,W), grad_out (B,Cout,H,W), W % 32 == 0, any strides.
- * grad_bias (Cout floats, zero-filled, or NULL) += sum_{b,y,x} grad_out[b,co,y,x] (falls out of staging grad_out).
- * Parity-green on a B200 (<= 1.6e-5 of max|dW|; cuDNN's fp32 engines measure 3-7e-5) but not faster than cuDNN's fp32
- * weight gradient on the step's shapes (profiles/r02c_conv_wgrad_bf16.txt): callers opt in (FFWM_WGRAD_TC=1). */
-int ffwm_conv3x3_wgrad(const ffwm_tensor4* x, const ffwm_tensor4* grad_out, const ffwm_tensor4* grad_weight,
-                       float* grad_bias, int math, void* stream);
-
 /* ---- general dense convolution on the tcgen05 tensor cores (csrc/conv_gen_tc.cu; fp32 in/out; math as above) ----------
  * Replaces the cuDNN calls behind nn.Conv2d / nn.ConvTranspose2d for every other shape of the path: kernels up to 7x7,
  * stride 1 or 2, any padding and map size (models/base_networks.py:30-57 conv / deconv / predict_flow, :208-246, :274-312
@@ -171,7 +161,8 @@ int ffwm_conv_pack_weights(const ffwm_tensor4* weight, int in_major, int stride,
 int ffwm_conv_forward(const ffwm_tensor4* x, const void* packed, const float* bias, const ffwm_tensor4* out, int kh, int kw,
                       int stride, int pad, int transposed, int math, void* stream);
 
-/* Weight gradient of the same family (csrc/conv_gen_wgrad_tc.cu; aten::convolution_backward's grad_weight):
+/* Weight gradient of EVERY convolution of the path, the 3x3 stride-1 layers included (csrc/conv_gen_wgrad_tc.cu;
+ * aten::convolution_backward's grad_weight; 3xBF16 split, <= 1.5e-5 of max|dW| where cuDNN's fp32 engines measure 3-7e-5):
  *   grad_weight[a][b][ky][kx] = sum_{n,y,x} small[n,a,y,x] * large[n,b,y*stride-pad+ky,x*stride-pad+kx]   (OVERWRITTEN)
  * nn.Conv2d: small = grad_out, large = input; nn.ConvTranspose2d: small = input, large = grad_out; (a, b) are the first
  * two dimensions of the weight either way.  Deterministic (split-K partials in `workspace`, summed in a fixed order). */

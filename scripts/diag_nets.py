@@ -34,15 +34,13 @@ def run(which):
 
 CONFIGS = [("library fp32", dict(ENABLED=False)),
            ("library TF32 (torch default)", dict(ENABLED=False, TF32=True)),
-           ("3x3: tcgen05 fwd, library dgrad", dict(ENABLED=True, GENERAL=False, WGRAD_GEN=False, WGRAD_TC=False, _DIAG_DGRAD_LIB=True)),
-           ("3x3: library fwd, tcgen05 dgrad", dict(ENABLED=True, GENERAL=False, WGRAD_GEN=False, WGRAD_TC=False, _DIAG_FWD_LIB=True)),
-           ("3x3 tcgen05, 3xBF16 forwards", dict(ENABLED=True, GENERAL=False, WGRAD_GEN=False, WGRAD_TC=False, MATH=1)),
-           ("everything, 3xBF16 forwards", dict(ENABLED=True, GENERAL=True, WGRAD_GEN=True, WGRAD_GEN_3X3=False, WGRAD_TC=False, MATH=1)),
-           ("3x3 tcgen05 only", dict(ENABLED=True, GENERAL=False, WGRAD_GEN=False, WGRAD_TC=False)),
-           ("3x3 + general fwd/dgrad", dict(ENABLED=True, GENERAL=True, WGRAD_GEN=False, WGRAD_TC=False)),
-           ("+ general wgrad", dict(ENABLED=True, GENERAL=True, WGRAD_GEN=True, WGRAD_GEN_3X3=False, WGRAD_TC=False)),
-           ("+ general wgrad for 3x3 too", dict(ENABLED=True, GENERAL=True, WGRAD_GEN=True, WGRAD_GEN_3X3=True, WGRAD_TC=False)),
-           ("+ 3x3 wgrad kernel", dict(ENABLED=True, GENERAL=True, WGRAD_GEN=True, WGRAD_GEN_3X3=False, WGRAD_TC=True))]
+           ("3x3: tcgen05 fwd, library dgrad", dict(ENABLED=True, GENERAL=False, WGRAD_GEN=False, _DIAG_DGRAD_LIB=True)),
+           ("3x3: library fwd, tcgen05 dgrad", dict(ENABLED=True, GENERAL=False, WGRAD_GEN=False, _DIAG_FWD_LIB=True)),
+           ("3x3 tcgen05, 3xBF16 forwards", dict(ENABLED=True, GENERAL=False, WGRAD_GEN=False, MATH=1)),
+           ("everything, 3xBF16 forwards", dict(ENABLED=True, GENERAL=True, WGRAD_GEN=True, MATH=1)),
+           ("3x3 tcgen05 only", dict(ENABLED=True, GENERAL=False, WGRAD_GEN=False)),
+           ("3x3 + general fwd/dgrad", dict(ENABLED=True, GENERAL=True, WGRAD_GEN=False)),
+           ("product default (all convolutions on tcgen05)", dict(ENABLED=True, GENERAL=True, WGRAD_GEN=True))]
 for which in sys.argv[1:] or ["flownet16", "netD", "lightcnn", "netG"]:
     want = gold(which)
     for name, cfg in CONFIGS:

@@ -92,15 +92,23 @@ def test_conv_entry_points_validate_without_gpu():
     assert rc == -2 and b"too small" in lib.ffwm_last_error()
     rc = lib.ffwm_conv3x3_pack_weights(_lib.t4(w), 0, fake, ctypes.c_int64(1 << 20), 100, BF, null)
     assert rc == -3
-    # weight gradient: W % 32, matching shapes, (Cout,Cin,3,3) target
-    x, go = torch.zeros(1, 8, 4, 48), torch.zeros(1, 16, 4, 48)
-    rc = lib.ffwm_conv3x3_wgrad(_lib.t4(x), _lib.t4(go), _lib.t4(w), null, BF, null)
-    assert rc == -2 and b"W % 32" in lib.ffwm_last_error()
-    x, go = torch.zeros(1, 8, 4, 64), torch.zeros(1, 16, 4, 64)
-    rc = lib.ffwm_conv3x3_wgrad(_lib.t4(x), _lib.t4(go), _lib.t4(torch.zeros(16, 9, 3, 3)), null, BF, null)
+    # general convolution family: geometry is validated before any launch
+    assert lib.ffwm_conv_packed_bytes(195, 195, 3, 3, BF) == 13 * 9 * 208 * 64 and lib.ffwm_conv_packed_bytes(195, 195, 3, 3, TF) == 25 * 9 * 208 * 64
+    assert lib.ffwm_conv_packed_bytes(8, 8, 8, 8, BF) == 0                                   # more than 49 taps
+    x, o = torch.zeros(1, 8, 8, 8), torch.zeros(1, 16, 5, 4)
+    rc = lib.ffwm_conv_forward(_lib.t4(x), fake, null, _lib.t4(o), 3, 3, 2, 1, 0, BF, null)
+    assert rc == -2 and b"does not match" in lib.ffwm_last_error()
+    rc = lib.ffwm_conv_forward(_lib.t4(x), fake, null, _lib.t4(torch.zeros(1, 16, 4, 4)), 3, 3, 3, 1, 0, BF, null)
+    assert rc == -3                                                                          # stride 3
+    assert lib.ffwm_conv_wgrad_workspace_bytes(1, 16, 8, 4, 4, 8, 8, 3, 3, 2, 1) > 0
+    assert lib.ffwm_conv_wgrad_workspace_bytes(1, 16, 8, 4, 4, 9, 9, 3, 3, 1, 1) == 0        # sides do not match
+    rc = lib.ffwm_conv_wgrad(_lib.t4(torch.zeros(1, 16, 4, 4)), _lib.t4(x), _lib.t4(torch.zeros(16, 9, 3, 3)), 2, 1, fake, ctypes.c_int64(1 << 30), null)
+    assert rc == -2                                                                          # grad_weight channels
+    assert lib.ffwm_corr_max_workspace_bytes(2, 64, 1024) > 0 and lib.ffwm_corr_max_workspace_bytes(2, 96, 1024) == 0
+    rc = lib.ffwm_affine_reg_forward(_lib.t4(torch.zeros(1, 1, 8, 8)), fake, _lib.t4(torch.zeros(1, 1, 5, 5)), 4, 0, null)
+    assert rc == -3
+    rc = lib.ffwm_ingest_u8(fake, null, fake, 1, 4, 4, 2, null)
     assert rc == -2
-    e = torch.zeros(0, 8, 4, 64)
-    assert lib.ffwm_conv3x3_wgrad(_lib.t4(e), _lib.t4(torch.zeros(0, 16, 4, 64)), _lib.t4(w), null, BF, null) == 0
     # max-feature-map: sizes and pointers
     assert lib.ffwm_mfm_forward(null, null, ctypes.c_int64(0), ctypes.c_int64(5), null) == 0
     assert lib.ffwm_mfm_forward(null, null, ctypes.c_int64(2), ctypes.c_int64(5), null) == -1

@@ -165,7 +165,7 @@ def test_modules_autograd_match_fp64(case):
 
 
 # ---------------------------------------------------------------- weight gradient (csrc/conv_gen_wgrad_tc.cu)
-WGRAD_TOL = 4e-5      # of max|ref|; chains are capped at 768 accumulator updates per CTA (conv3x3_wgrad_tc.cu measures 1.6e-5)
+WGRAD_TOL = 4e-5      # of max|ref|; chains are capped at 768 accumulator updates per CTA (1.5e-5 measured on the step's shapes)
 
 
 @pytest.mark.parametrize("b,cin,cout,h,w,k,s,p", CONV_CASES + [(8, 195, 195, 128, 128, 3, 1, 1), (2, 64, 64, 64, 64, 3, 1, 1)])
