@@ -51,14 +51,7 @@ def wgrad_bench(out_path):
         x = torch.randn(8, cin, r, r, device=dev)
         go = torch.randn(8, cout, r, r, device=dev)
         w = torch.zeros(cout, cin, 3, 3, device=dev)
-        gw = torch.zeros_like(w)
         flop = 2.0 * 8 * r * r * cin * cout * 9
-
-        def mine():
-            gw.zero_()
-            ops.conv3x3_wgrad(x, go, gw)
-
-        t_mine = timeit(mine)
         gw2 = torch.empty_like(w)
         t_gen = timeit(lambda: ops.conv_wgrad(go, x, gw2, 1, 1))
         w64 = w.double().requires_grad_()

@@ -25,7 +25,7 @@
 //   * N = NT output channels, a runtime multiple of 16 up to 256 chosen per layer (195 -> 208, 384 -> 2 x 192,
 //     2 -> 16): the instruction descriptor, the TMEM allocation and the shared-memory carve-up are runtime values.
 //   * a stage = U = 3 or 4 consecutive units of the flattened (k-block, tap) sequence, ring of 2-4 stages, producers
-//     (8 warps) / issuer (1 thread) / epilogue (the producer warps) synchronised by mbarriers as in conv3x3_tc.cu.
+//     (16 warps) / issuer (1 thread) / epilogue (8 of the producer warps) synchronised by mbarriers as in conv3x3_tc.cu.
 //   * layers whose M x N tiles do not fill the GPU split the K sequence over several CTAs (blockIdx.z); partial sums
 //     meet as fp32 REDs in the (then zero-filled here) output, bias added by split 0.
 #include <cuda_bf16.h>
@@ -38,7 +38,7 @@
 
 namespace ffwm {
 
-constexpr int GN_PRODUCERS = 256;
+constexpr int GN_PRODUCERS = 512;                // 16 producer warps: thread = (pixel, k-chunk, unit parity); 4 warps per scheduler hide the gather latency
 constexpr int GN_MAXTAPS = 49;
 constexpr int GN_MAXU = 4;                       // units per stage
 constexpr int GN_A_UNIT = 2 * 2 * 128 * 16;      // [part][k-chunk][128 pixels][16 B]
@@ -199,7 +199,7 @@ conv_gen_tc_kernel(View<const float> x, const unsigned char* __restrict__ packed
 
     if (warp < GN_PRODUCERS / 32) {
         // ================= producers: gather the activations of the stage's units =================
-        const int m = tid & 127, kc = tid >> 7;
+        const int m = tid & 127, kc = (tid >> 7) & 1, uh = tid >> 8;       // this thread stages the units u with (u & 1) == uh
         const int64_t p = (int64_t)blockIdx.x * 128 + m;
         const bool pv = p < npix;
         int a = 0, b = 0, img = 0;
@@ -213,12 +213,12 @@ conv_gen_tc_kernel(View<const float> x, const unsigned char* __restrict__ packed
         // A load is `base + j * stride` with an immediate j; an out-of-image tap (or a pixel past the end) turns base into a
         // zero word and the stride into 0 instead of predicating every load; only the last K block of a tensor whose
         // channel count is not a multiple of the slot width takes the predicated path (warp-uniform).
-        auto load_stage = [&](int k, float (&v)[GN_MAXU][CPS]) {
+        auto load_stage = [&](int k, float (&v)[GN_MAXU / 2][CPS]) {
             const int u0 = (s0 + k) * g.upst, nu = min(g.upst, units - u0);
-            int kb = u0 / c.ntaps, t = u0 - kb * c.ntaps;
+            int kb = (u0 + uh) / c.ntaps, t = (u0 + uh) - kb * c.ntaps;
 #pragma unroll
-            for (int u = 0; u < GN_MAXU; ++u) {
-                if (u < nu) {
+            for (int uu = 0; uu < GN_MAXU / 2; ++uu) {
+                if (2 * uu + uh < nu) {
                     const GnTap tp = g.taps[c.tap0 + t];
                     const bool ok = pv && (unsigned)(ya + tp.dy) < (unsigned)g.hi && (unsigned)(xb + tp.dx) < (unsigned)g.wi;
                     const int c0 = kb * (2 * CPS) + kc * CPS;
@@ -226,16 +226,17 @@ conv_gen_tc_kernel(View<const float> x, const unsigned char* __restrict__ packed
                     const int64_t str = ok ? x.sc : 0;
                     if (c0 + CPS <= g.cin) {
 #pragma unroll
-                        for (int j = 0; j < CPS; ++j) v[u][j] = __ldg(gp + j * str);
+                        for (int j = 0; j < CPS; ++j) v[uu][j] = __ldg(gp + j * str);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < CPS; ++j) v[u][j] = c0 + j < g.cin ? __ldg(gp + j * str) : 0.f;
+                        for (int j = 0; j < CPS; ++j) v[uu][j] = c0 + j < g.cin ? __ldg(gp + j * str) : 0.f;
                     }
-                    if (++t == c.ntaps) { t = 0; ++kb; }
+                    t += 2;                                            // two units further (ntaps may be 1: wrap repeatedly)
+                    while (t >= c.ntaps) { t -= c.ntaps; ++kb; }
                 }
             }
         };
-        auto store_stage = [&](int k, float (&v)[GN_MAXU][CPS]) {
+        auto store_stage = [&](int k, float (&v)[GN_MAXU / 2][CPS]) {
             const int slot = k % g.nstage;
             if (k >= g.nstage) mbar_wait(&bars[4 + slot], ((k / g.nstage) - 1) & 1);    // MMAs that read this slot are done
             const int u0 = (s0 + k) * g.upst, nu = min(g.upst, units - u0);
@@ -248,12 +249,12 @@ conv_gen_tc_kernel(View<const float> x, const unsigned char* __restrict__ packed
                              : "memory");
             }
 #pragma unroll
-            for (int u = 0; u < GN_MAXU; ++u)
-                if (u < nu) split_store_m<BF>(st + u * GN_A_UNIT + kc * 2048 + m * 16, 4096, v[u]);
+            for (int uu = 0; uu < GN_MAXU / 2; ++uu)
+                if (2 * uu + uh < nu) split_store_m<BF>(st + (2 * uu + uh) * GN_A_UNIT + kc * 2048 + m * 16, 4096, v[uu]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[slot])) : "memory");
         };
-        float va[GN_MAXU][CPS], vb[GN_MAXU][CPS];
+        float va[GN_MAXU / 2][CPS], vb[GN_MAXU / 2][CPS];
         load_stage(0, va);
         for (int k = 0; k < nst; k += 2) {
             if (k + 1 < nst) load_stage(k + 1, vb);
@@ -283,8 +284,8 @@ conv_gen_tc_kernel(View<const float> x, const unsigned char* __restrict__ packed
         }
     }
 
-    // ---- epilogue (producer warps): TMEM -> registers -> NCHW global (lanes = consecutive pixels of the class)
-    if (warp < GN_PRODUCERS / 32) {
+    // ---- epilogue (8 of the producer warps): TMEM -> registers -> NCHW global (lanes = consecutive pixels of the class)
+    if (warp < 8) {
         const int last = nst - 1;
         mbar_wait(&bars[4 + last % g.nstage], (last / g.nstage) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

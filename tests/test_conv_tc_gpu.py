@@ -79,7 +79,7 @@ def test_conv3x3_rejects_other_widths(ops):
 
 
 def test_conv_module_autograd_matches_cudnn_fp64():
-    """ffwm_b200.conv.Conv2d: forward and grad_input on tcgen05, grad_weight/bias on cuDNN."""
+    """ffwm_b200.conv.Conv2d: forward, grad_input and grad_weight on tcgen05 (bias gradient: a torch reduction)."""
     from ffwm_b200 import _lib
     from ffwm_b200.conv import Conv2d
     torch.manual_seed(0)
@@ -89,7 +89,7 @@ def test_conv_module_autograd_matches_cudnn_fp64():
     n0 = _lib.kernel_launches()
     out = m(x)
     out.backward(go)
-    assert _lib.kernel_launches() - n0 == 4                  # pack + conv, forward and data gradient
+    assert _lib.kernel_launches() - n0 == 6                  # pack + conv (forward, data gradient); weight gradient + its split-K reduction
     xr = x.detach().double().requires_grad_(True)
     wr = m.weight.detach().double().requires_grad_(True)
     br = m.bias.detach().double().requires_grad_(True)
