@@ -101,12 +101,48 @@ class TrainStepWorkload:
         return None      # filled by bench.py from the measured step time (see step_roofline)
 
     def step_roofline(self, pk, ms_per_step):
-        tflops = GFLOP_PER_IMAGE * BATCH / 1e3 / (ms_per_step * 1e-3)
-        return {"kernel": "whole step (convolutions are ~99% of the FLOPs: 3x3 stride-1 layers on the tcgen05 kernel, the rest on cuDNN)", "bound": "tensor",
-                "achieved": tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": tflops / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"],
-                "note": "algorithmic 447.0 GFLOP/image (conv+matmul fwd+bwd; the reference's unused LightCNN weight gradients skipped) / measured step time; "
-                        "peak is the measured sustained bf16 tensor rate, the math here is %s" % ("tf32" if self.tf32 else "fp32")}
+        """`roofline` of the train-step line: the step's dominant hand-written kernel — conv3x3_tc on netG's dres2 layers
+        (195->195 @128x128, batch 8: 89.7 GFLOP per launch, the largest single-layer share of the step's FLOPs) — timed
+        live with CUDA events right after the timed region, in the operand math its forward pass uses (3xTF32: three
+        tf32 MMAs per product), against the cuBLAS TF32 rate measured in this same run.  The whole-step figure
+        (algorithmic FLOPs / step time) is reported next to it."""
+        import json
+        from ffwm_b200 import _lib, ops
+        step_tflops = GFLOP_PER_IMAGE * BATCH / 1e3 / (ms_per_step * 1e-3)
+        out = {"kernel": "conv3x3_tc_kernel<128,128> forward, netG dres2 195->195 @128x128 x batch 8 (3xTF32 operand split)",
+               "bound": "tensor", "unit": "TFLOP/s", "peak_source": "cuBLAS tf32 GEMM 8192^3 measured in this run (bench.py tensor_peaks)",
+               "whole_step_TFLOP/s": round(step_tflops, 2),
+               "whole_step_note": "447.0 algorithmic GFLOP/image (conv+matmul fwd+bwd) x 8 / measured step time; "
+                                  "%.4f of the measured sustained bf16 rate" % (step_tflops / pk["bf16_tflops_sustained"])}
+        try:
+            cin = cout = 195
+            x = torch.randn(BATCH, cin, 128, 128, device=self.dev)
+            w = torch.randn(cout, cin, 3, 3, device=self.dev) / (cin * 9) ** 0.5
+            o = torch.empty(BATCH, cout, 128, 128, device=self.dev)
+            packed = ops.conv3x3_pack_weights(w, nt=128, math=_lib.MATH_TF32X3)
+            for _ in range(3):
+                ops.conv3x3_forward(x, packed, None, o, nt=128, math=_lib.MATH_TF32X3)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(10):
+                ops.conv3x3_forward(x, packed, None, o, nt=128, math=_lib.MATH_TF32X3)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            gflop = 2.0 * BATCH * 128 * 128 * cin * cout * 9 / 1e9
+            from bench import tensor_peaks
+            peak = tensor_peaks(self.dev.index or 0, iters=5).get("tf32_tflops")
+            issued = 3 * gflop / ms
+            out.update({"achieved": round(issued, 1), "achieved_note": "issued tensor math = 3 x algorithmic (%.1f useful TFLOP/s, %.4f ms per launch)" % (gflop / ms, ms),
+                        "algorithmic_GFLOP_per_launch": round(gflop, 2), "peak": peak, "frac": round(issued / peak, 4) if peak else None})
+            tp = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+            out["traffic"] = json.load(open(tp)).get("conv3x3_tc_dres2") if os.path.exists(tp) else None
+            out["algorithmic_bytes_per_launch"] = 4 * BATCH * 128 * 128 * (cin + cout) + 4 * cin * cout * 9
+        except Exception as e:          # noqa: BLE001 - the bench line must survive
+            out.update({"achieved": round(step_tflops, 2), "peak": pk["bf16_tflops_sustained"], "frac": step_tflops / pk["bf16_tflops_sustained"],
+                        "traffic": None, "error": repr(e)})
+        return out
 
     # the step's dominant hand-written kernel (conv3x3_tc: 55 % of the step's convolution FLOPs), on its three
     # heaviest layer shapes (SURVEY 8a a13), batch = the step's batch

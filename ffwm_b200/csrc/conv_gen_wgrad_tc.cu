@@ -216,20 +216,22 @@ conv_gen_wgrad_tc_kernel(View<const float> S, View<const float> L, float* __rest
 }
 
 // dW[a][b][ky][kx] = sum over splits of the partial tiles, in split order (deterministic); overwrites dW.
+// One thread per element of a partial tile, in the workspace's own order: the reads of every split are coalesced; the
+// (few) writes into dW are scattered by the tile -> (a, b, tap) mapping.
 __global__ void conv_gen_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int64_t s_a, int64_t s_b, int64_t s_ky,
                                              int64_t s_kx, WggGeo g) {
     const int T = g.kh * g.kw;
-    const int64_t total = (int64_t)g.ca * g.cb * T;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int tap = (int)(i % T);
-        const int64_t r = i / T;
-        const int b = (int)(r % g.cb), a = (int)(r / g.cb);
-        const int tile = ((a / 128) * g.nbt + b / g.nb) * g.ntg + tap / g.tg;
-        const int nidx = (tap % g.tg) * g.nb + b % g.nb;
-        const float* p = ws + ((int64_t)tile * 128 + a % 128) * g.nn + nidx;
-        const int64_t split_stride = (int64_t)g.tiles * 128 * g.nn;
+    const int64_t per_split = (int64_t)g.tiles * 128 * g.nn;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per_split; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i % g.nn);
+        const int64_t r = i / g.nn;
+        const int al = (int)(r % 128), tile = (int)(r / 128);
+        const int tgi = tile % g.ntg, bt = (tile / g.ntg) % g.nbt, at = tile / (g.ntg * g.nbt);
+        const int tl = n / g.nb, bl = n - tl * g.nb;
+        const int a = at * 128 + al, b = bt * g.nb + bl, tap = tgi * g.tg + tl;
+        if (a >= g.ca || b >= g.cb || tap >= T) continue;
         float acc = 0.f;
-        for (int s = 0; s < g.splits; ++s) acc += p[s * split_stride];
+        for (int s = 0; s < g.splits; ++s) acc += ws[s * per_split + i];
         const int ky = tap / g.kw, kx = tap - ky * g.kw;
         dw[a * s_a + b * s_b + ky * s_ky + kx * s_kx] = acc;
     }
@@ -322,8 +324,8 @@ extern "C" int ffwm_conv_wgrad(const ffwm_tensor4* small, const ffwm_tensor4* la
     if (e != cudaSuccess) { set_error("conv_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
     conv_gen_wgrad_tc_kernel<<<dim3(g.tiles, g.splits), WGG_PRODUCERS + 32, g.nstage * g.stage_bytes + 128, st>>>(sv, lv, static_cast<float*>(workspace), g);
     if ((rc = check_launch("conv_wgrad"))) return rc;
-    const int64_t total = (int64_t)g.ca * g.cb * g.kh * g.kw;
-    conv_gen_wgrad_reduce_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 4096), 256, 0, st>>>(
+    const int64_t total = (int64_t)g.tiles * 128 * g.nn;
+    conv_gen_wgrad_reduce_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 8 * sm_count()), 256, 0, st>>>(
         static_cast<const float*>(workspace), wv.p, wv.sb, wv.sc, (int64_t)wv.sh, (int64_t)wv.sw, g);
     return check_launch("conv_wgrad (reduce)");
 }
