@@ -72,10 +72,19 @@ def _packed_gen(weight, in_major, stride, pad, transposed, math):
                    lambda: ops.conv_pack_weights(weight, in_major, stride, pad, transposed, math))
 
 
-def eligible(x, weight, stride, padding, dilation, groups, padding_mode="zeros"):
+def _bias_ok(bias, weight, x, out_dim=0):
+    return bias is None or (bias.is_cuda and bias.device == x.device and bias.dtype == torch.float32 and bias.is_contiguous()
+                            and bias.numel() == weight.size(out_dim))
+
+
+def eligible(x, weight, stride, padding, dilation, groups, padding_mode="zeros", bias=None):
+    """3x3 / stride 1 / pad 1 at W in {128, 64, 32} -> conv3x3_tc.  Anything the kernel would mis-read (channel mismatch,
+    foreign bias, batch beyond the grid limit) is NOT eligible and reaches F.conv2d, which raises / handles it as torch does."""
     return (ENABLED and x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.dim() == 4
+            and weight.device == x.device and x.size(1) == weight.size(1) and 0 < x.size(0) <= 65535
             and x.size(3) in WIDTHS and tuple(weight.shape[2:]) == (3, 3) and tuple(stride) == (1, 1)
-            and tuple(padding) == (1, 1) and tuple(dilation) == (1, 1) and groups == 1 and padding_mode == "zeros")
+            and tuple(padding) == (1, 1) and tuple(dilation) == (1, 1) and groups == 1 and padding_mode == "zeros"
+            and _bias_ok(bias, weight, x))
 
 
 _DIAG_FWD_LIB = _DIAG_DGRAD_LIB = False      # scripts/diag_nets.py only: one direction on the library
@@ -95,6 +104,7 @@ class Conv3x3TCFunction(Function):
         return out
 
     @staticmethod
+    @torch.autograd.function.once_differentiable          # double backward (gradient penalties) is not provided: fails loudly
     def backward(ctx, grad_out):
         x, weight = ctx.saved_tensors
         grad_out = grad_out.contiguous()
@@ -121,9 +131,11 @@ def _sym(v):
     return v[0] if len(v) == 2 and v[0] == v[1] else None
 
 
-def eligible_general(x, weight, stride, padding, dilation, groups, padding_mode="zeros", output_padding=(0, 0), transposed=False):
+def eligible_general(x, weight, stride, padding, dilation, groups, padding_mode="zeros", output_padding=(0, 0), transposed=False,
+                     bias=None):
     if not (ENABLED and GENERAL and x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.dim() == 4
-            and groups == 1 and padding_mode == "zeros" and isinstance(padding, (tuple, list, int))):
+            and weight.device == x.device and groups == 1 and padding_mode == "zeros" and isinstance(padding, (tuple, list, int))
+            and _bias_ok(bias, weight, x, 1 if transposed else 0)):
         return False
     s, p, d, op = _sym(stride), _sym(padding), _sym(dilation), _sym(output_padding)
     kh, kw = weight.shape[2:]
@@ -215,9 +227,9 @@ class ConvTGenFunction(Function):
 
 def conv2d(x, weight, bias, stride=(1, 1), padding=(0, 0), dilation=(1, 1), groups=1):
     """F.conv2d with the tcgen05 paths for eligible calls."""
-    if eligible(x, weight, stride, padding, dilation, groups):
+    if eligible(x, weight, stride, padding, dilation, groups, bias=bias):
         return Conv3x3TCFunction.apply(x, weight, bias)
-    if eligible_general(x, weight, stride, padding, dilation, groups):
+    if eligible_general(x, weight, stride, padding, dilation, groups, bias=bias):
         return ConvGenFunction.apply(x, weight, bias, _sym(stride), _sym(padding))
     return torch.nn.functional.conv2d(x, weight, bias, stride, padding, dilation, groups)
 
@@ -225,9 +237,9 @@ def conv2d(x, weight, bias, stride=(1, 1), padding=(0, 0), dilation=(1, 1), grou
 class Conv2d(nn.Conv2d):
     def _conv_forward(self, input, weight, bias):
         if isinstance(self.padding, tuple):
-            if eligible(input, weight, self.stride, self.padding, self.dilation, self.groups, self.padding_mode):
+            if eligible(input, weight, self.stride, self.padding, self.dilation, self.groups, self.padding_mode, bias=bias):
                 return Conv3x3TCFunction.apply(input, weight, bias)
-            if eligible_general(input, weight, self.stride, self.padding, self.dilation, self.groups, self.padding_mode):
+            if eligible_general(input, weight, self.stride, self.padding, self.dilation, self.groups, self.padding_mode, bias=bias):
                 return ConvGenFunction.apply(input, weight, bias, _sym(self.stride), _sym(self.padding))
         return super()._conv_forward(input, weight, bias)
 
@@ -238,6 +250,6 @@ class ConvTranspose2d(nn.ConvTranspose2d):
     def forward(self, input, output_size=None):
         if (output_size is None and isinstance(self.padding, tuple)
                 and eligible_general(input, self.weight, self.stride, self.padding, self.dilation, self.groups, self.padding_mode,
-                                     self.output_padding, transposed=True)):
+                                     self.output_padding, transposed=True, bias=self.bias)):
             return ConvTGenFunction.apply(input, self.weight, self.bias, _sym(self.stride), _sym(self.padding), _sym(self.output_padding))
         return super().forward(input, output_size)

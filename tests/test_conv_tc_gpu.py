@@ -100,3 +100,18 @@ def test_conv_module_autograd_matches_cudnn_fp64():
     # not eligible (width 48): falls back to the library convolution, same module
     y = m(torch.randn(1, 20, 8, 48, device=DEV))
     assert y.shape == (1, 70, 8, 48)
+
+
+def test_ineligible_calls_reach_torch():
+    """Anything the tcgen05 kernels would mis-read is not eligible and behaves like nn.Conv2d: a channel mismatch raises
+    torch's own error (instead of reading past the packed weights), double backward fails loudly instead of silently."""
+    from ffwm_b200.conv import Conv2d, eligible
+    m = Conv2d(20, 70, 3, 1, 1).to(DEV)
+    with pytest.raises(RuntimeError):
+        m(torch.randn(1, 21, 8, 128, device=DEV))
+    assert not eligible(torch.randn(1, 21, 8, 128, device=DEV), m.weight, (1, 1), (1, 1), (1, 1), 1, bias=m.bias)
+    assert not eligible(torch.randn(1, 20, 8, 128, device=DEV), m.weight, (1, 1), (1, 1), (1, 1), 1, bias=m.bias.double())
+    x = torch.randn(1, 20, 8, 128, device=DEV, requires_grad=True)
+    (gx,) = torch.autograd.grad(m(x).sum(), x, create_graph=True)
+    with pytest.raises(RuntimeError):
+        gx.sum().backward()
