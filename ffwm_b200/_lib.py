@@ -52,6 +52,10 @@ SIGNATURES = {
     "ffwm_conv_wgrad": [_T4P, _T4P, _T4P, _I, _I, _VP, ctypes.c_int64, _VP],
     "ffwm_affine_reg_forward": [_T4P, _VP, _T4P, _I, _I, _VP],
     "ffwm_affine_reg_backward": [_T4P, _VP, _T4P, _T4P, _I, _I, _VP],
+    "ffwm_batch_norm_workspace_bytes": [_I, _I, ctypes.c_int64],
+    "ffwm_batch_norm_forward": [_VP] * 6 + [ctypes.c_float] * 3 + [_VP] * 3 + [_I, _I, ctypes.c_int64, _VP, ctypes.c_int64, _VP],
+    "ffwm_batch_norm_backward": [_VP] * 7 + [ctypes.c_float] + [_VP] * 4 + [_I, _I, ctypes.c_int64, _VP, ctypes.c_int64, _VP],
+    "ffwm_channel_sum": [_VP, _VP, _I, _I, ctypes.c_int64, _VP, ctypes.c_int64, _VP],
     "ffwm_corr_max_workspace_bytes": [_I, _I, _I],
     "ffwm_corr_max": [_T4P, _T4P, ctypes.c_float, _VP, _VP, ctypes.c_int64, _VP],
     "ffwm_ingest_u8": [_VP, _VP, _VP, _I, _I, _I, _I, _VP],
@@ -86,6 +90,7 @@ def lib():
                           "ffwm_conv3x3_packed_floats": ctypes.c_int64,
                           "ffwm_conv_packed_bytes": ctypes.c_int64,
                           "ffwm_conv_wgrad_workspace_bytes": ctypes.c_int64,
+                          "ffwm_batch_norm_workspace_bytes": ctypes.c_int64,
                           "ffwm_corr_max_workspace_bytes": ctypes.c_int64}.get(name, ctypes.c_int)
         if l.ffwm_abi_version() != ABI_VERSION:
             raise ImportError("ffwm_b200: ABI version mismatch (library %d, binding %d)"

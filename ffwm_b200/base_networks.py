@@ -28,6 +28,7 @@ from torch.nn.utils import spectral_norm
 
 from . import external_function as EF
 from .conv import Conv2d, ConvTranspose2d
+from .norm import BatchNorm2d, as_product_norm, fuse_activations
 from .spectral import batch_spectral_norm
 
 LRELU_SLOPE = 0.2
@@ -55,7 +56,7 @@ def _unit(cin, cout, norm, k=3, stride=1, transposed=False, bias=True):
         op = ConvTranspose2d(cin, cout, kernel_size=4, stride=2, padding=1, bias=True)
     else:
         op = Conv2d(cin, cout, kernel_size=k, stride=stride, padding=(k - 1) // 2, bias=bias)
-    return nn.Sequential(op, norm(cout), nn.LeakyReLU(LRELU_SLOPE, inplace=True))
+    return nn.Sequential(*fuse_activations([op, as_product_norm(norm)(cout), nn.LeakyReLU(LRELU_SLOPE, inplace=True)]))
 
 
 def conv(in_planes, out_planes, norm_layer=nn.BatchNorm2d, kernel_size=3, stride=1):
@@ -153,7 +154,7 @@ class Tanh2(nn.Module):
 
 _ACTIVATIONS = {'relu': nn.ReLU, 'lrelu': lambda: nn.LeakyReLU(LRELU_SLOPE), 'sigmoid': nn.Sigmoid,
                 'tanh': nn.Tanh, 'tanh2': Tanh2}
-_NORMS = {'bn': nn.BatchNorm2d, 'in': nn.InstanceNorm2d}
+_NORMS = {'bn': BatchNorm2d, 'in': nn.InstanceNorm2d}
 
 
 def get_activ(name):
@@ -182,11 +183,18 @@ class ResidualBlock(nn.Module):
         pad = kernel // 2 if sn else kernel
         self.activ = get_activ(activ)
         self.input = _maybe_sn(Conv2d(inc, outc, 1, 1, padding=0), sn)
-        self.blocks = nn.Sequential(_maybe_sn(Conv2d(inc, outc, kernel, 1, pad), sn), get_norm(norm, outc),
-                                    nn.LeakyReLU(LRELU_SLOPE),
-                                    _maybe_sn(Conv2d(outc, outc, kernel, 1, pad), sn), get_norm(norm, outc))
+        self.blocks = nn.Sequential(*fuse_activations([_maybe_sn(Conv2d(inc, outc, kernel, 1, pad), sn), get_norm(norm, outc),
+                                                       nn.LeakyReLU(LRELU_SLOPE),
+                                                       _maybe_sn(Conv2d(outc, outc, kernel, 1, pad), sn), get_norm(norm, outc)]))
 
     def forward(self, x):
+        last = self.blocks[-1]
+        if type(self.activ) is nn.LeakyReLU and isinstance(last, BatchNorm2d) and last.act_slope is None:
+            # the closing batch norm adds the projection and applies the activation in its own kernels (ffwm_b200/norm.py)
+            h = x
+            for m in list(self.blocks)[:-1]:
+                h = m(h)
+            return last(h, residual=self.input(x), act_slope=self.activ.negative_slope)
         return self.activ(self.blocks(x) + self.input(x))
 
 
@@ -196,6 +204,7 @@ def _block(first, outc, activ, norm, res, resk, bn, sn):
         seq.append(get_norm(norm, outc))
     if activ is not None:
         seq.append(get_activ(activ))
+    seq = fuse_activations(seq)
     seq += [ResidualBlock(outc, activ=activ, kernel=resk, norm=norm, sn=sn) for _ in range(res)]
     return nn.Sequential(*seq)
 
@@ -291,15 +300,15 @@ class MSDiscriminator(nn.Module):
         layers = []
         for cin, cout in ((self.inc, c), (c, 2 * c), (2 * c, 4 * c)):      # three stride-2 SN conv blocks
             layers += [spectral_norm(Conv2d(cin, cout, kernel_size=3, stride=2, padding=1)),
-                       nn.BatchNorm2d(cout), nn.LeakyReLU(LRELU_SLOPE, True)]
+                       BatchNorm2d(cout), nn.LeakyReLU(LRELU_SLOPE, True)]
         for _ in range(self.extra_conv_layers):
             layers += [spectral_norm(Conv2d(2 * c, 2 * c, kernel_size=3, bias=True)),
-                       nn.BatchNorm2d(2 * c), nn.LeakyReLU(LRELU_SLOPE, True)]
+                       BatchNorm2d(2 * c), nn.LeakyReLU(LRELU_SLOPE, True)]
         if self.sigmoid:
             layers += [spectral_norm(Conv2d(4 * c, 1, kernel_size=1)), nn.Sigmoid()]
         else:
             layers += [Conv2d(4 * c, 1, kernel_size=1)]
-        return nn.Sequential(*layers)
+        return nn.Sequential(*fuse_activations(layers))
 
     def forward(self, input_tensor):
         total = self.nets[0](input_tensor)

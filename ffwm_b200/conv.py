@@ -157,7 +157,7 @@ def _wgrad(grad_out, x, weight, has_bias, stride, pad, transposed, out_pad, need
         small, large = (x, grad_out) if transposed else (grad_out, x)
         ops.conv_wgrad(small, large, gw, stride, pad)
     if has_bias and need_b:
-        gb = grad_out.sum((0, 2, 3))
+        gb = ops.channel_sum(grad_out) if (grad_out.is_contiguous() and grad_out.numel() > 0) else grad_out.sum((0, 2, 3))
     return gw, gb
 
 

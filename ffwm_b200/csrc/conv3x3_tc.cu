@@ -42,9 +42,9 @@ namespace ffwm {
 
 // Output channels per CTA = MMA N: 64, or 128 for W = 128 (NT is a template parameter).  With N = 64 an MMA reads
 // 4 KB of A and 2 KB of B from shared memory for 33 clk of math (48 clk at 128 B/clk: shared-memory bound, ncu
-// l1tex 72 % / tensor pipe 48 %); N = 128 reads 4 + 4 KB for 66 clk of math.  The N = 128 variant is EXPERIMENTAL
-// (written after the round-1 GPU budget was spent, not yet run): callers opt in per call (nt argument of the
-// *_nt entry points; ffwm_b200/conv.py: FFWM_CONV_NT128=1).
+// l1tex 72 % / tensor pipe 48 %); N = 128 reads 4 + 4 KB for 66 clk of math.  Callers choose per call (the nt argument
+// of the entry points); ffwm_b200/conv.py takes N = 128 wherever W = 128 and Cout > 64 (FFWM_CONV_NT128=0 for the A/B;
+// measured in profiles/r02a_conv_nt128.txt).
 // Operand math (template parameter BF of everything below; chosen per call: the `math` argument of the entry points):
 //   BF = false  3xTF32: a = hi + lo, hi = a & 0xffffe000 (exact in tf32); hi*hi + hi*lo + lo*hi; K block = 8 channels
 //   BF = true   3xBF16: a = b1 + b2 + (dropped), b1 = bf16_rn(a), b2 = bf16_rn(a - b1); b1*b1 + b1*b2 + b2*b1;

@@ -121,39 +121,69 @@ static bool gn_build(GnGeo& g, int kh, int kw, int stride, int pad, int transpos
 // ---------------------------------------------------------------- weight packing
 // packed[class][cob][unit = kb * ntaps + t][part][kchunk][co_local nt][8 ci] (bf16), B[o][c] = w[o*s_o + c*s_c + ky*s_ky + kx*s_kx]
 // (3xTF32: the same with 4 fp32 channels per 16-byte slot and hi / lo parts)
+// One CTA packs an (o_tile output channels) x (one K block of input channels) x (all kh*kw taps) tile: it reads the tile with
+// the weight's contiguous axis innermost (coalesced whichever of the first two dimensions is the input channel), keeps it in
+// shared memory, and writes 16-byte slots in runs of o_tile * 16 contiguous bytes per (class, tap, part, k-chunk).
 template <bool BF>
-__global__ void conv_gen_pack_kernel(const float* __restrict__ w, unsigned char* __restrict__ packed, int64_t s_o, int64_t s_c,
-                                     int64_t s_ky, int64_t s_kx, GnGeo g) {
-    constexpr int CPS = BF ? 8 : 4;                                    // channels per slot
-    const int ci = blockIdx.y;                                         // class
-    const GnClass c = g.cls[ci];
-    const int64_t total = (int64_t)g.ncob * g.nkb * c.ntaps * 2 * g.nt * CPS;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t r = i;
-        const int j = r % CPS; r /= CPS;
-        const int col = r % g.nt; r /= g.nt;
-        const int kc = r % 2; r /= 2;
-        const int t = r % c.ntaps; r /= c.ntaps;
-        const int kb = r % g.nkb; r /= g.nkb;
-        const int cob = (int)r;
-        const int o = cob * g.nt + col, ch = kb * (2 * CPS) + kc * CPS + j;
+__global__ void __launch_bounds__(256) conv_gen_pack_kernel(const float* __restrict__ w, unsigned char* __restrict__ packed, int64_t s_o,
+                                                            int64_t s_c, int64_t s_ky, int64_t s_kx, const __grid_constant__ GnGeo g, int o_shift,
+                                                            int kh, int kw) {
+    constexpr int CPS = BF ? 8 : 4, KB = 2 * CPS, KB_SHIFT = BF ? 4 : 3;   // channels per slot, per K block
+    extern __shared__ float gn_pack_smem[];                            // [o_tile][KB * T + 1] floats, then T tap offsets
+    const int T = kh * kw, RS = KB * T + 1, o_tile = 1 << o_shift;
+    int* toff = reinterpret_cast<int*>(gn_pack_smem + o_tile * RS);
+    const int ogroups = g.nt >> o_shift;
+    const int og = blockIdx.x % ogroups, kb = (blockIdx.x / ogroups) % g.nkb, cob = blockIdx.x / (ogroups * g.nkb);
+    const int o0 = cob * g.nt + og * o_tile, ch0 = kb * KB;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) toff[t] = (int)((t / kw) * s_ky + (t % kw) * s_kx);
+    __syncthreads();
+    // (row r, tap) pairs in memory order, walked without divisions: the index math, not the memory system, bounded the
+    // first version of this kernel (profiles/r02v_pack_reduce.txt)
+    const bool o_outer = s_c <= s_o;                                   // the input channels of one output channel lie closer together
+    const int step_tap = (int)blockDim.x % T, step_r = (int)blockDim.x / T, rows = o_tile * KB;
+    int tap = (int)threadIdx.x % T, r = (int)threadIdx.x / T;
+#pragma unroll 4
+    for (; r < rows;) {
+        const int ch_l = o_outer ? (r & (KB - 1)) : (r >> o_shift), o_l = o_outer ? (r >> KB_SHIFT) : (r & (o_tile - 1));
+        const int o = o0 + o_l, ch = ch0 + ch_l;
         float v = 0.f;
-        if (o < g.cout && ch < g.cin) {
+        if (o < g.cout && ch < g.cin) v = __ldg(w + (o * s_o + ch * s_c) + toff[tap]);
+        gn_pack_smem[o_l * RS + ch_l * T + tap] = v;
+        tap += step_tap;
+        r += step_r;
+        if (tap >= T) tap -= T, ++r;
+    }
+    __syncthreads();
+    for (int ci = 0; ci < g.nclass; ++ci) {
+        const GnClass& c = g.cls[ci];
+        unsigned char* base = packed + c.packed_off + ((int64_t)cob * g.nkb + kb) * c.ntaps * (int64_t)g.b_unit + (og * o_tile) * 16;
+#pragma unroll 2
+        for (int i = threadIdx.x; i < ((c.ntaps * 4) << o_shift); i += blockDim.x) {
+            const int o_l = i & (o_tile - 1), kc = (i >> o_shift) & 1, part = (i >> (o_shift + 1)) & 1, t = i >> (o_shift + 2);
             const GnTap tp = g.taps[c.tap0 + t];
-            v = w[o * s_o + ch * s_c + tp.ky * s_ky + tp.kx * s_kx];
-        }
-        const int64_t unit = ((int64_t)cob * g.nkb + kb) * c.ntaps + t;
-        const int64_t within = ((int64_t)kc * g.nt + col) * CPS + j;
-        if (BF) {
-            __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(packed + c.packed_off);
-            const __nv_bfloat16 b1 = __float2bfloat16_rn(v);
-            base[unit * (2 * 2 * g.nt * 8) + within] = b1;
-            base[unit * (2 * 2 * g.nt * 8) + 2 * g.nt * 8 + within] = __float2bfloat16_rn(v - __bfloat162float(b1));
-        } else {
-            float* base = reinterpret_cast<float*>(packed + c.packed_off);
-            const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-            base[unit * (2 * 2 * g.nt * 4) + within] = hi;
-            base[unit * (2 * 2 * g.nt * 4) + 2 * g.nt * 4 + within] = v - hi;
+            const float* src = gn_pack_smem + o_l * RS + kc * CPS * T + tp.ky * kw + tp.kx;
+            float v[CPS];
+#pragma unroll
+            for (int j = 0; j < CPS; ++j) v[j] = src[j * T];
+            uint32_t h[4];
+            if (BF) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    __nv_bfloat16 e0 = __float2bfloat16_rn(v[2 * j]), e1 = __float2bfloat16_rn(v[2 * j + 1]);
+                    if (part) {
+                        e0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(e0));
+                        e1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(e1));
+                    }
+                    h[j] = (uint32_t)__bfloat16_as_ushort(e0) | ((uint32_t)__bfloat16_as_ushort(e1) << 16);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float hi = __uint_as_float(__float_as_uint(v[j]) & 0xffffe000u);
+                    h[j] = __float_as_uint(part ? v[j] - hi : hi);
+                }
+            }
+            *reinterpret_cast<uint4*>(base + t * g.b_unit + part * (2 * g.nt * 16) + (kc * g.nt + o_l) * 16) = make_uint4(h[0], h[1], h[2], h[3]);
         }
     }
 }
@@ -379,10 +409,16 @@ extern "C" int ffwm_conv_pack_weights(const ffwm_tensor4* weight, int in_major, 
     const int64_t need = ffwm_conv_packed_bytes(n_out, n_in, kh, kw, math);
     if (packed_bytes < need) { set_error("conv_pack_weights: packed buffer too small (%lld < %lld bytes)", (long long)packed_bytes, (long long)need); return FFWM_ERR_SHAPE; }
     const int64_t s_o = weight->stride[in_major ? 1 : 0], s_c = weight->stride[in_major ? 0 : 1];
-    const int blocks = (int)std::min<int64_t>((need / 2 / g.nclass + 255) / 256 + 1, 2048);
+    const int T = kh * kw, kbs = math ? 16 : 8;
+    int o_tile = g.nt % 32 == 0 ? 32 : 16;
+    while (o_tile > 8 && (int64_t)o_tile * (kbs * T + 1) * 4 > 40 * 1024) o_tile /= 2;
+    while (o_tile > 8 && (int64_t)g.ncob * g.nkb * (g.nt / o_tile) < 2 * sm_count()) o_tile /= 2;   // small weights: more, shorter CTAs
+    const int o_shift = o_tile == 32 ? 5 : o_tile == 16 ? 4 : 3;
+    const int64_t ctas = (int64_t)g.ncob * g.nkb * (g.nt / o_tile);
+    if (ctas > 0x7fffffffLL) { set_error("conv_pack_weights: weight too large"); return FFWM_ERR_TOO_LARGE; }
     auto pk = math ? conv_gen_pack_kernel<true> : conv_gen_pack_kernel<false>;
-    pk<<<dim3(blocks, g.nclass), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const float*>(weight->data), static_cast<unsigned char*>(packed), s_o, s_c, weight->stride[2], weight->stride[3], g);
+    pk<<<(unsigned)ctas, 256, ((size_t)o_tile * (kbs * T + 1) + T) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float*>(weight->data), static_cast<unsigned char*>(packed), s_o, s_c, weight->stride[2], weight->stride[3], g, o_shift, kh, kw);
     return check_launch("conv_pack_weights");
 }
 

@@ -216,24 +216,40 @@ conv_gen_wgrad_tc_kernel(View<const float> S, View<const float> L, float* __rest
 }
 
 // dW[a][b][ky][kx] = sum over splits of the partial tiles, in split order (deterministic); overwrites dW.
-// One thread per element of a partial tile, in the workspace's own order: the reads of every split are coalesced; the
-// (few) writes into dW are scattered by the tile -> (a, b, tap) mapping.
-__global__ void conv_gen_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int64_t s_a, int64_t s_b, int64_t s_ky,
-                                             int64_t s_kx, WggGeo g) {
-    const int T = g.kh * g.kw;
+// One CTA per (output row a, chunk of WGG_RED_BC channels b): it adds the splits of that row segment in every tap-group tile
+// (128-byte pieces of workspace rows), lays the sums out as [b][tap] in shared memory and writes them as one contiguous run
+// of dW (a tile holds [tap][b]: writing straight from the workspace order would scatter 4-byte words `taps` apart).
+constexpr int WGG_RED_BC = 32;
+__global__ void __launch_bounds__(128) conv_gen_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int64_t s_a, int64_t s_b,
+                                                                    int64_t s_ky, int64_t s_kx, const __grid_constant__ WggGeo g) {
+    __shared__ float sm[WGG_RED_BC * 50];                              // [32 b][T | 1], T <= 49
+    const int T = g.kh * g.kw, TP = T | 1;
+    const int al = blockIdx.x % 128, bt = (blockIdx.x / 128) % g.nbt, at = blockIdx.x / (128 * g.nbt);
+    const int a = at * 128 + al, b0 = blockIdx.y * WGG_RED_BC;         // b0: first channel of this chunk inside the b tile
+    if (a >= g.ca || bt * g.nb + b0 >= g.cb) return;
     const int64_t per_split = (int64_t)g.tiles * 128 * g.nn;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per_split; i += (int64_t)gridDim.x * blockDim.x) {
-        const int n = (int)(i % g.nn);
-        const int64_t r = i / g.nn;
-        const int al = (int)(r % 128), tile = (int)(r / 128);
-        const int tgi = tile % g.ntg, bt = (tile / g.ntg) % g.nbt, at = tile / (g.ntg * g.nbt);
-        const int tl = n / g.nb, bl = n - tl * g.nb;
-        const int a = at * 128 + al, b = bt * g.nb + bl, tap = tgi * g.tg + tl;
-        if (a >= g.ca || b >= g.cb || tap >= T) continue;
+    const int lane = threadIdx.x & 31;
+    const bool live = b0 + lane < g.nb;
+    for (int tap = threadIdx.x >> 5; tap < T; tap += 4) {              // one warp per tap: 32 consecutive b of one workspace row
+        const int tgi = tap / g.tg, tl = tap - tgi * g.tg;
+        const int tile = (at * g.nbt + bt) * g.ntg + tgi;
+        const float* p = ws + ((int64_t)tile * 128 + al) * g.nn + tl * g.nb + b0 + lane;
         float acc = 0.f;
-        for (int s = 0; s < g.splits; ++s) acc += ws[s * per_split + i];
-        const int ky = tap / g.kw, kx = tap - ky * g.kw;
-        dw[a * s_a + b * s_b + ky * s_ky + kx * s_kx] = acc;
+        if (live) {
+#pragma unroll 8
+            for (int sp = 0; sp < g.splits; ++sp) acc += __ldg(p + sp * per_split);
+        }
+        sm[lane * TP + tap] = acc;
+    }
+    __syncthreads();
+    const int nb_here = min(WGG_RED_BC, min(g.nb - b0, g.cb - (bt * g.nb + b0)));
+    float* row = dw + a * s_a + (int64_t)(bt * g.nb + b0) * s_b;
+    const bool dense = s_kx == 1 && s_ky == g.kw && s_b == T;
+    for (int q = threadIdx.x; q < nb_here * T; q += blockDim.x) {
+        const int bl = q / T, tap = q - bl * T;
+        const float v = sm[bl * TP + tap];
+        if (dense) row[q] = v;
+        else row[bl * s_b + (tap / g.kw) * s_ky + (tap % g.kw) * s_kx] = v;
     }
 }
 
@@ -270,9 +286,19 @@ static int wgg_setup(WggGeo& g, int n, int ca, int cb, int hs, int ws_, int hl, 
     const int64_t stages = (g.npix + WGG_KP - 1) / WGG_KP;
     if (stages > 0x7fffffffLL) { set_error("conv_wgrad: problem too large"); return FFWM_ERR_TOO_LARGE; }
     g.stages_total = (int)stages;
-    int64_t splits = std::max<int64_t>(1, std::min<int64_t>((stages + 1) / 2, (2 * sm_count() + g.tiles - 1) / g.tiles));
-    g.stages_per_split = (int)std::min<int64_t>((stages + splits - 1) / splits, WGG_MAX_STAGES);
-    g.splits = (int)((stages + g.stages_per_split - 1) / g.stages_per_split);
+    // split K over CTAs: one CTA per SM is resident (shared memory), so the kernel takes ceil(tiles * splits / SMs) waves of
+    // (stages per split + ~6 stages of prologue / epilogue); the reduction pass reads `splits` partials per weight.  Pick the
+    // chain length that minimises that, no longer than the accuracy cap.
+    const int cap = std::max(1, std::min(opt(OPT_WGRAD_CHAIN) > 0 ? opt(OPT_WGRAD_CHAIN) : WGG_MAX_STAGES, 1024));
+    const int sms = sm_count();
+    double best_cost = -1.0;
+    for (int sps = (int)std::min<int64_t>(cap, stages); sps >= 1; --sps) {
+        const int64_t sp = (stages + sps - 1) / sps;
+        if (sp > 1 && sps < std::min<int64_t>(cap, 8)) break;             // never shorter than 8 stages unless the whole problem is
+        const int64_t waves = (g.tiles * sp + sms - 1) / sms;
+        const double cost = (double)waves * (sps + 6) + 0.5 * (double)sp;
+        if (best_cost < 0 || cost < best_cost) best_cost = cost, g.stages_per_split = sps, g.splits = (int)sp;
+    }
     g.b_part = (g.nn / 8) * WGG_GROUP;
     g.stage_bytes = 2 * WGG_A_PART + 2 * g.b_part;
     g.nstage = std::max(2, std::min(3, (227 * 1024 - 256) / g.stage_bytes));
@@ -324,8 +350,7 @@ extern "C" int ffwm_conv_wgrad(const ffwm_tensor4* small, const ffwm_tensor4* la
     if (e != cudaSuccess) { set_error("conv_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
     conv_gen_wgrad_tc_kernel<<<dim3(g.tiles, g.splits), WGG_PRODUCERS + 32, g.nstage * g.stage_bytes + 128, st>>>(sv, lv, static_cast<float*>(workspace), g);
     if ((rc = check_launch("conv_wgrad"))) return rc;
-    const int64_t total = (int64_t)g.tiles * 128 * g.nn;
-    conv_gen_wgrad_reduce_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 8 * sm_count()), 256, 0, st>>>(
+    conv_gen_wgrad_reduce_kernel<<<dim3(g.nat * g.nbt * 128, (g.nb + WGG_RED_BC - 1) / WGG_RED_BC), 128, 0, st>>>(
         static_cast<const float*>(workspace), wv.p, wv.sb, wv.sc, (int64_t)wv.sh, (int64_t)wv.sw, g);
     return check_launch("conv_wgrad (reduce)");
 }

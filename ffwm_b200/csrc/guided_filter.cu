@@ -1,10 +1,9 @@
 // Guided filter (models/external_function.py:164-195,239-277: BoxFilter + GuidedFilter.forward) and its gradient
 // with respect to the filtered image x, as four small kernels per direction.
 //
-// STATUS: written after the round-1 GPU budget was spent; compiled for sm_100a, its arithmetic (in particular the
-// hand-derived backward) is checked on the CPU in float64 against autograd of the reference formula
-// (tests/test_guided_filter_math.py), but the kernels have NOT run on a B200 yet.  Opt-in: FFWM_FUSED_GF=1
-// (ffwm_b200/external_function.py), GPU tests opt-in (tests/test_zz_guided_filter_gpu.py).
+// STATUS: default on since round 2 (FFWM_FUSED_GF=0 in ffwm_b200/external_function.py for the A/B).  The hand-derived
+// backward is checked on the CPU in float64 against autograd of the reference formula (tests/test_guided_filter_math.py)
+// and the kernels against the same on a B200 (tests/test_guided_filter_gpu.py).
 //
 // Why: the reference builds every box filter from two cumsums, three slices and a cat per axis, seven box filters
 // per call, three calls per train step plus their autograd mirror — several hundred tiny launches per step

@@ -1,8 +1,8 @@
 // Max-feature-map activation of LightCNN (lightcnn/light_cnn.py:13-26: conv/linear to 2*C channels, split,
 // elementwise max) as one kernel per direction.
 //
-// STATUS: written after the round-1 GPU budget was spent; compiled for sm_100a, not yet run on a B200, so it is
-// opt-in (FFWM_FUSED_MFM=1, ffwm_b200/light_cnn.py) and its GPU tests are opt-in (tests/test_zz_mfm_gpu.py).
+// STATUS: default on since round 2 (FFWM_FUSED_MFM=0 in ffwm_b200/light_cnn.py for the A/B); B200 parity in
+// tests/test_mfm_gpu.py.
 //
 // Why: PyTorch runs torch.max(a, b) as one kernel forward and FOUR per operand backward (eq, where, lt,
 // masked_fill: derivatives.yaml's tie-splitting formula) — 30 MFM layers x 4 LightCNN passes per train step came to

@@ -175,7 +175,7 @@ def ingest_u8(src, flip, out):
 
 def mfm_forward(x, out):
     """out (N,C,...) = elementwise max of the two channel halves of x (N,2C,...); contiguous fp32 CUDA tensors.
-    EXPERIMENTAL (not yet run on a B200): see csrc/mfm.cu."""
+    See csrc/mfm.cu."""
     import ctypes
     dev = L.require_cuda(x, out)
     n, chw = x.size(0), out.numel() // max(x.size(0), 1)
@@ -208,7 +208,7 @@ def _gf_ptrs(*tensors):
 
 def guided_filter_forward(x, y, q, save, scratch, r, eps):
     """q = GuidedFilter(r, eps)(x, y) for (B,C,H,W) x, y; save (5,B,C,H,W), scratch (5,B,C,H,W).
-    EXPERIMENTAL (not yet run on a B200): see csrc/guided_filter.cu."""
+    See csrc/guided_filter.cu."""
     import ctypes
     dev = L.require_cuda(x, y, q, save, scratch)
     b, c, h, w = x.shape
@@ -227,3 +227,66 @@ def guided_filter_backward(x, y, grad_q, save, grad_x, scratch, r):
         raise ValueError("guided_filter_backward: shape mismatch")
     L.call("ffwm_guided_filter_backward", dev, *_gf_ptrs(x, y, grad_q, save, grad_x, scratch), ctypes.c_int64(b * c),
            int(h), int(w), int(r))
+
+
+def _bn_ws(x):
+    import torch
+    n, c, hw = int(x.size(0)), int(x.size(1)), int(x.size(2) * x.size(3))
+    nbytes = L.lib().ffwm_batch_norm_workspace_bytes(n, c, hw)
+    if nbytes <= 0:
+        raise ValueError("batch_norm: unsupported shape %s: %s" % (tuple(x.shape), L.lib().ffwm_last_error().decode()))
+    return n, c, hw, torch.empty(nbytes // 8, dtype=torch.float64, device=x.device), nbytes
+
+
+def _ptr(t):
+    import ctypes
+    return ctypes.c_void_p(t.data_ptr() if t is not None else None)
+
+
+def _bn_check(what, maps, vectors, c):
+    import torch
+    for t in maps:
+        if t is not None and not (t.is_contiguous() and t.dtype == torch.float32 and t.shape == maps[0].shape):
+            raise ValueError("%s: contiguous fp32 (N,C,H,W) maps of one shape expected" % what)
+    for v in vectors:
+        if v is not None and not (v.is_cuda and v.is_contiguous() and v.dtype == torch.float32 and v.numel() == c):
+            raise ValueError("%s: per-channel vectors must be contiguous fp32 CUDA tensors of C elements" % what)
+
+
+def batch_norm_forward(x, residual, gamma, beta, running_mean, running_var, momentum, eps, act_slope, y, save_mean, save_invstd):
+    """Training-mode BatchNorm2d (+ residual add, + LeakyReLU with `act_slope`; 1.0 = none) of a contiguous fp32 (N,C,H,W)
+    map into y; updates running_mean / running_var (None to skip) like torch (csrc/batch_norm.cu)."""
+    import ctypes
+    dev = L.require_cuda(x, residual, y)
+    n, c, hw, ws, nbytes = _bn_ws(x)
+    _bn_check("batch_norm_forward", (x, residual, y), (gamma, beta, running_mean, running_var, save_mean, save_invstd), c)
+    L.call("ffwm_batch_norm_forward", dev, _ptr(x), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
+           ctypes.c_float(momentum), ctypes.c_float(eps), ctypes.c_float(act_slope), _ptr(y), _ptr(save_mean), _ptr(save_invstd),
+           n, c, ctypes.c_int64(hw), _ptr(ws), ctypes.c_int64(nbytes))
+
+
+def batch_norm_backward(x, grad_out, y_out, gamma, beta, save_mean, save_invstd, act_slope, grad_x, grad_residual, grad_gamma, grad_beta):
+    """Gradient of batch_norm_forward: grad_x, grad_gamma, grad_beta (and grad_residual, with y_out = the forward's output,
+    when a residual was added) are overwritten."""
+    import ctypes
+    dev = L.require_cuda(x, grad_out, y_out, grad_x, grad_residual)
+    n, c, hw, ws, nbytes = _bn_ws(x)
+    _bn_check("batch_norm_backward", (x, grad_out, y_out, grad_x, grad_residual), (gamma, beta, save_mean, save_invstd, grad_gamma, grad_beta), c)
+    L.call("ffwm_batch_norm_backward", dev, _ptr(x), _ptr(grad_out), _ptr(y_out), _ptr(gamma), _ptr(beta), _ptr(save_mean), _ptr(save_invstd),
+           ctypes.c_float(act_slope), _ptr(grad_x), _ptr(grad_residual), _ptr(grad_gamma), _ptr(grad_beta), n, c, ctypes.c_int64(hw),
+           _ptr(ws), ctypes.c_int64(nbytes))
+
+
+def channel_sum(x):
+    """(C,) = x.sum((0, 2, 3)) of a contiguous fp32 CUDA (N,C,H,W) map (csrc/batch_norm.cu: the bias gradient of a convolution)."""
+    import ctypes
+    import torch
+    dev = L.require_cuda(x)
+    if not (x.dim() == 4 and x.is_contiguous() and x.dtype == torch.float32 and x.numel() > 0):
+        raise ValueError("channel_sum: a non-empty contiguous fp32 (N,C,H,W) map expected")
+    n, c, hw = int(x.size(0)), int(x.size(1)), int(x.size(2) * x.size(3))
+    nbytes = L.lib().ffwm_batch_norm_workspace_bytes(max(n, 2), c, hw)
+    ws = torch.empty(nbytes // 8, dtype=torch.float64, device=x.device)
+    out = torch.empty(c, dtype=torch.float32, device=x.device)
+    L.call("ffwm_channel_sum", dev, _ptr(x), _ptr(out), n, c, ctypes.c_int64(hw), _ptr(ws), ctypes.c_int64(nbytes))
+    return out

@@ -180,6 +180,29 @@ int ffwm_affine_reg_forward(const ffwm_tensor4* grid, const void* q, const ffwm_
 int ffwm_affine_reg_backward(const ffwm_tensor4* grid, const void* q, const ffwm_tensor4* grad_out, const ffwm_tensor4* grad_grid,
                              int kz, int dtype, void* stream);
 
+/* ---- training-mode BatchNorm2d (+ LeakyReLU, + residual add) as two streaming kernels per direction (csrc/batch_norm.cu) ----
+ * Replaces nn.BatchNorm2d in training mode and the nn.LeakyReLU that follows it in every conv unit of the reference
+ * (models/base_networks.py:15-45, :179-206, :397-410), and `activ(blocks(x) + input(x))` of ResidualBlock (:208-233):
+ *   y = lrelu_slope( (x - mean_c) * gamma_c / sqrt(var_c + eps) + beta_c [+ residual] ),  mean / biased var over (N, H, W);
+ *   running_mean/var (may be NULL) get torch's momentum update (unbiased variance); save_mean / save_invstd (C floats) feed backward.
+ * act_slope = 1: no activation.  x, residual, y, grad_*: contiguous (N, C, H*W) fp32.  Deterministic.
+ * backward: grad_x (overwritten), grad_gamma / grad_beta (C floats, overwritten, may be NULL); when the forward added a
+ * residual, pass y_out (the forward's output: its sign is the activation's) and grad_residual (overwritten with
+ * grad_out * lrelu'(y), the gradient of the residual operand).
+ * workspace: ffwm_batch_norm_workspace_bytes(N, C, H*W) bytes of device memory, no initialisation needed. */
+int64_t ffwm_batch_norm_workspace_bytes(int n, int c, int64_t hw);
+int ffwm_batch_norm_forward(const float* x, const float* residual, const float* gamma, const float* beta, float* running_mean,
+                            float* running_var, float momentum, float eps, float act_slope, float* y, float* save_mean,
+                            float* save_invstd, int n, int c, int64_t hw, void* workspace, int64_t workspace_bytes, void* stream);
+int ffwm_batch_norm_backward(const float* x, const float* grad_out, const float* y_out, const float* gamma, const float* beta,
+                             const float* save_mean, const float* save_invstd, float act_slope, float* grad_x, float* grad_residual,
+                             float* grad_gamma, float* grad_beta, int n, int c, int64_t hw, void* workspace, int64_t workspace_bytes,
+                             void* stream);
+
+/* out[c] = sum over (n, hw) of x (N, C, H*W contiguous fp32): the bias gradient of a convolution (grad_out.sum((0,2,3)) in
+ * aten::convolution_backward), two kernels, deterministic.  workspace: ffwm_batch_norm_workspace_bytes(N, C, H*W) bytes. */
+int ffwm_channel_sum(const float* x, float* out, int n, int c, int64_t hw, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- correlation column-max of PerceptualCorrectness (csrc/corr_max.cu) ------------------------------------
  * Replaces models/losses.py:347-353 (per-pixel cosine normalisation, bmm to a [b, N2, N2] product — 1.07 GB per sample at
  * relu1_1 — and max over the source axis) with a normalising prepass + one tcgen05 GEMM whose epilogue keeps a running
@@ -201,7 +224,7 @@ int ffwm_ingest_u8(const void* src, const void* flip, float* dst, int b, int h, 
 /* ---- LightCNN max-feature-map activation (lightcnn/light_cnn.py:13-26: `torch.max(out[0], out[1])` over the two
  * channel halves of the preceding conv / linear output) and its gradient, one streaming kernel each; ATen's
  * semantics incl. NaN propagation and tie splitting.  x (n, 2*chw) and out (n, chw) contiguous fp32; chw = C*H*W.
- * EXPERIMENTAL: not yet run on a B200 (written after the round-1 GPU budget was spent); opt-in FFWM_FUSED_MFM=1. */
+ * Default on (FFWM_FUSED_MFM=0 for the A/B); B200 parity: tests/test_mfm_gpu.py. */
 int ffwm_mfm_forward(const float* x, float* out, int64_t n, int64_t chw, void* stream);
 int ffwm_mfm_backward(const float* x, const float* grad_out, float* grad_x, int64_t n, int64_t chw, void* stream);
 
@@ -209,8 +232,7 @@ int ffwm_mfm_backward(const float* x, const float* grad_out, float* grad_x, int6
  * with respect to x, four kernels per direction; box sums are truncated window sums taken directly (separable).
  * x, y, q, grad_q, grad_x: (planes = B*C, H, W) contiguous fp32, H and W > 2r+1 (the reference's assert).
  * save: 5*planes*H*W floats written by forward, read by backward; scratch: 5 (forward) / 6 (backward) * planes*H*W.
- * EXPERIMENTAL: arithmetic checked on the CPU (float64, against autograd of the reference formula), kernels not yet
- * run on a B200 (written after the round-1 GPU budget was spent); opt-in FFWM_FUSED_GF=1. */
+ * Default on (FFWM_FUSED_GF=0 for the A/B); B200 parity against autograd of the reference formula: tests/test_guided_filter_gpu.py. */
 int ffwm_guided_filter_forward(const float* x, const float* y, float* q, float* save, float* scratch,
                                int64_t planes, int h, int w, int r, float eps, void* stream);
 int ffwm_guided_filter_backward(const float* x, const float* y, const float* grad_q, const float* save,
