@@ -249,6 +249,9 @@ def main():
 
     # ---- end-to-end leg: host buffers through the public API --------------------------
     note("device leg done: %.2f ms/step" % ms_per_step)
+    if hasattr(wl, "phase_report") and wl.phase_report() is not None:
+        note("phases (ms): %s" % json.dumps(wl.phase_report()))
+        wl.trainer.phase_events = None
     e2e = None
     if not args.no_e2e:
         for _ in range(3):

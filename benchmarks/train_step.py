@@ -61,8 +61,26 @@ class TrainStepWorkload:
                           for k, v in make_batch(BATCH, 1000 + self.rank).items()}
         self.host_batch = make_batch(BATCH, 2000 + self.rank, pin=True)
         if self.use_graph:
-            self.trainer.enable_cuda_graph(self.dev_batch)
+            # FFWM_BENCH_SEGMENTED=1: the three-graph (data-parallel) layout on one GPU too (diagnostic)
+            seg = True if os.environ.get("FFWM_BENCH_SEGMENTED", "0") == "1" else None
+            self.trainer.enable_cuda_graph(self.dev_batch, segmented=seg)
             self.dev_batch = self.trainer._static        # replay in place, no copy
+        if os.environ.get("FFWM_BENCH_PHASES", "0") == "1":
+            self.trainer.phase_events = []
+
+    def phase_report(self):
+        """Mean GPU milliseconds per phase of the segmented step (FFWM_BENCH_PHASES=1): graph k, then the all-reduce after it."""
+        ev = getattr(self.trainer, "phase_events", None)
+        if not ev:
+            return None
+        torch.cuda.synchronize()
+        tot, cnt = {}, {}
+        for (name, e0, _), (_, e1, _) in zip(ev[:-1], ev[1:]):
+            if name == "end":
+                continue
+            tot[name] = tot.get(name, 0.0) + e0.elapsed_time(e1)
+            cnt[name] = cnt.get(name, 0) + 1
+        return {k: round(tot[k] / cnt[k], 3) for k in tot}
 
     def step(self, timed):
         self.trainer.step(self.dev_batch)

@@ -51,7 +51,17 @@ CACHE_PACKED = os.environ.get("FFWM_CACHE_PACKED", "1") == "1"
 
 
 def _cached(weight, key, pack):
-    if not (CACHE_PACKED and weight.is_leaf and not weight.requires_grad):
+    """Packed image of a FROZEN weight, kept on the tensor and re-made when its version counter or storage changes.
+    A weight that has ever been seen with requires_grad=True is never served from the cache again: fused optimizers
+    (torch.optim.Adam(fused=True)) update parameters without bumping `_version`, and the reference toggles
+    requires_grad on the discriminator around the generator's backward pass (models/ffwm_model.py:206-207), so
+    "does not require grad right now" does not mean "frozen"."""
+    if weight.requires_grad:
+        try:
+            weight._ffwm_trainable = True
+        except AttributeError:
+            pass
+    if not (CACHE_PACKED and weight.is_leaf and not weight.requires_grad and not getattr(weight, "_ffwm_trainable", False)):
         return pack()
     cache = getattr(weight, "_ffwm_packed", None)
     if cache is None:

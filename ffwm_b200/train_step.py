@@ -280,6 +280,11 @@ class FFWMTrainer:
         self.graph_kernel_nodes = _lib.kernel_launches() - n0     # ffwm_b200 kernels recorded in the graph(s)
         self.graph_replays = 0
 
+    def _mark(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream(self.device))
+        return e
+
     def _bind(self, batch):
         self.img_S, self.img_F, self.lm_F = batch['img_S'], batch['img_F'], batch['lm_F']
         self.mask_F, self.mask_S = batch['mask_F'].float(), batch['mask_S'].float()
@@ -297,10 +302,17 @@ class FFWMTrainer:
             for k, v in self._static.items():
                 if torch.is_tensor(v):
                     v.copy_(batch[k], non_blocking=True)
-        for graph, averager in self._graphs:
+        timing = getattr(self, "phase_events", None)       # diagnostic: [(name, start, end)] CUDA events per phase
+        for i, (graph, averager) in enumerate(self._graphs):
+            if timing is not None:
+                timing.append(("graph%d" % i, self._mark(), None))
             graph.replay()
+            if timing is not None:
+                timing.append(("allreduce%d" % i, self._mark(), None))
             if averager is not None:
                 averager.average()
+        if timing is not None:
+            timing.append(("end", self._mark(), None))
         self.graph_replays += 1
 
     @staticmethod
