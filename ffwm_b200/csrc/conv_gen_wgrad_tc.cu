@@ -47,6 +47,10 @@ struct WggGeo {
     int64_t npix;
     int stages_total, stages_per_split, splits;
     int b_part, stage_bytes, nstage, tmem_cols;
+    // row mode (stride 1): one B tile per kernel ROW serves all kw taps of that row through descriptor offsets
+    int rows_mode;               // 0: every (tap, channel) column is gathered on its own
+    int seg, rps, bpr, bp;       // pixels per row segment, rows per stage, B pixels per row (seg + kw - 1), per stage (rps * bpr)
+    int kyn;                     // kernel rows per tile (tg = kyn * kw taps)
 };
 
 // MN-major, no-swizzle shared-memory descriptor: same fields as umma_desc (umma.cuh); for this layout the "leading"
@@ -59,6 +63,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int m, int n) {
     return umma_idesc_bf16(m, n) | (1u << 15) | (1u << 16);
 }
 
+template <bool ROWS>
 __global__ void __launch_bounds__(WGG_PRODUCERS + 32, 1)
 conv_gen_wgrad_tc_kernel(View<const float> S, View<const float> L, float* __restrict__ ws, const __grid_constant__ WggGeo g) {
     extern __shared__ __align__(128) unsigned char wg_smem[];
@@ -106,17 +111,38 @@ conv_gen_wgrad_tc_kernel(View<const float> S, View<const float> L, float* __rest
             a_off[i] = (int64_t)a0 * S.sc;
             a_cnt[i] = max(0, min(8, g.ca - a0));
         }
+        // B items of this thread.  Gather mode: NB groups (tap, 8 channels) at the stage pixel px.  Row mode: up to NBR items
+        // (kernel row ky, 8 channels, pixel of the padded row segment): the tile of a kernel row is loaded once, with kw - 1
+        // halo pixels, and the kw taps of that row read it at descriptor offsets of one pixel (16 bytes).
+        constexpr int NBR = 4;
         int64_t b_off[NB];
         int b_kyx[NB], b_cnt[NB];                                          // ky | kx << 8; valid channels (0: group unused)
+        int r_dst[NBR], r_dy[NBR], r_dx[NBR];                              // row mode: smem byte offset, row / column offset from the stage origin
+        if constexpr (!ROWS) {
 #pragma unroll
-        for (int j = 0; j < NB; ++j) {
-            const int gg = g0 + WGG_GQ * j;
-            const int tl = gg / nbg, b0 = bt * g.nb + (gg - tl * nbg) * 8;
-            const int tap = tgi * g.tg + tl, ky = tap / g.kw, kx = tap - ky * g.kw;
-            const bool ok = gg < ngB && tap < T;
-            b_kyx[j] = ky | (kx << 8);
-            b_cnt[j] = ok ? max(0, min(8, g.cb - b0)) : 0;
-            b_off[j] = (int64_t)b0 * L.sc + (int64_t)ky * L.sh + (int64_t)kx * L.sw;
+            for (int j = 0; j < NB; ++j) {
+                const int gg = g0 + WGG_GQ * j;
+                const int tl = gg / nbg, b0 = bt * g.nb + (gg - tl * nbg) * 8;
+                const int tap = tgi * g.tg + tl, ky = tap / g.kw, kx = tap - ky * g.kw;
+                const bool ok = gg < ngB && tap < T;
+                b_kyx[j] = ky | (kx << 8);
+                b_cnt[j] = ok ? max(0, min(8, g.cb - b0)) : 0;
+                b_off[j] = (int64_t)b0 * L.sc + (int64_t)ky * L.sh + (int64_t)kx * L.sw;
+            }
+        } else {
+            const int items = g.kyn * nbg * g.bp, ky0 = tgi * g.kyn;
+#pragma unroll
+            for (int j = 0; j < NBR; ++j) {
+                const int it = tid + WGG_PRODUCERS * j;
+                const int pxh = it % g.bp, gr = (it / g.bp) % nbg, kyi = it / (g.bp * nbg);
+                const int r = pxh / g.bpr, xh = pxh - r * g.bpr;
+                const int b0 = bt * g.nb + gr * 8;
+                b_cnt[j] = it < items ? max(0, min(8, g.cb - b0)) : -1;    // -1: no item
+                b_off[j] = (int64_t)b0 * L.sc;
+                r_dy[j] = r + ky0 + kyi - g.pad;
+                r_dx[j] = xh - g.pad;
+                r_dst[j] = kyi * 2 * g.b_part + gr * (g.bp * 16) + pxh * 16;
+            }
         }
         // 8 channels at `q`, `str` elements apart; cnt < 8 only for the last group of a tensor (warp-uniform)
         auto load8 = [](const float* q, int64_t str, int cnt, float (&v)[8]) {
@@ -140,12 +166,26 @@ conv_gen_wgrad_tc_kernel(View<const float> S, View<const float> L, float* __rest
             float va[NA][8], vb[NB][8];
 #pragma unroll
             for (int i = 0; i < NA; ++i) load8(pv ? sp + a_off[i] : wgg_zero, s_str, a_cnt[i], va[i]);
+            if constexpr (!ROWS) {
 #pragma unroll
-            for (int j = 0; j < NB; ++j) {
-                if (g0 + WGG_GQ * j < ngB) {                               // uniform over the 64 threads of a group quarter
-                    const int ky = b_kyx[j] & 255, kx = b_kyx[j] >> 8;
-                    const bool ok = pv && (unsigned)(yl0 + ky) < (unsigned)g.hl && (unsigned)(xl0 + kx) < (unsigned)g.wl;
-                    load8(ok ? lp + b_off[j] : wgg_zero, ok ? L.sc : 0, b_cnt[j], vb[j]);
+                for (int j = 0; j < NB; ++j) {
+                    if (g0 + WGG_GQ * j < ngB) {                           // uniform over the 64 threads of a group quarter
+                        const int ky = b_kyx[j] & 255, kx = b_kyx[j] >> 8;
+                        const bool ok = pv && (unsigned)(yl0 + ky) < (unsigned)g.hl && (unsigned)(xl0 + kx) < (unsigned)g.wl;
+                        load8(ok ? lp + b_off[j] : wgg_zero, ok ? L.sc : 0, b_cnt[j], vb[j]);
+                    }
+                }
+            } else {
+                // stage origin (first pixel of the stage) from this thread's own pixel: stages never straddle a row segment
+                const int oy = ys - px / g.seg, ox = xs - px % g.seg;
+                const float* lo = L.p + img * L.sb;
+#pragma unroll
+                for (int j = 0; j < NBR; ++j) {
+                    if (b_cnt[j] >= 0) {
+                        const int yl = oy + r_dy[j], xl = ox + r_dx[j];
+                        const bool ok = (unsigned)yl < (unsigned)g.hl && (unsigned)xl < (unsigned)g.wl;
+                        load8(ok ? lo + (int64_t)yl * L.sh + (int64_t)xl * L.sw + b_off[j] : wgg_zero, ok ? L.sc : 0, b_cnt[j], vb[j]);
+                    }
                 }
             }
             const int slot = k % g.nstage;
@@ -154,9 +194,15 @@ conv_gen_wgrad_tc_kernel(View<const float> S, View<const float> L, float* __rest
             unsigned char* sB = sA + 2 * WGG_A_PART;
 #pragma unroll
             for (int i = 0; i < NA; ++i) split_store_bf(sA + (g0 + WGG_GQ * i) * WGG_GROUP + px * 16, WGG_A_PART, va[i]);
+            if constexpr (!ROWS) {
 #pragma unroll
-            for (int j = 0; j < NB; ++j)
-                if (g0 + WGG_GQ * j < ngB) split_store_bf(sB + (g0 + WGG_GQ * j) * WGG_GROUP + px * 16, g.b_part, vb[j]);
+                for (int j = 0; j < NB; ++j)
+                    if (g0 + WGG_GQ * j < ngB) split_store_bf(sB + (g0 + WGG_GQ * j) * WGG_GROUP + px * 16, g.b_part, vb[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < NBR; ++j)
+                    if (b_cnt[j] >= 0) split_store_bf(sB + r_dst[j], g.b_part, vb[j]);
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[slot])) : "memory");
             // next stage: WGG_KP pixels further along (n, y, x)
@@ -171,7 +217,7 @@ conv_gen_wgrad_tc_kernel(View<const float> S, View<const float> L, float* __rest
         }
     } else if (lane == 0) {
         // ================= issuer =================
-        const uint32_t idesc = umma_idesc_bf16_mn(128, g.nn);
+        const uint32_t idesc = umma_idesc_bf16_mn(128, ROWS ? g.nb : g.nn);
         for (int k = 0; k < nst; ++k) {
             const int slot = k % g.nstage;
             mbar_wait(&bars[slot], (k / g.nstage) & 1);
@@ -180,10 +226,27 @@ conv_gen_wgrad_tc_kernel(View<const float> S, View<const float> L, float* __rest
 #pragma unroll
             for (int t = 0; t < WGG_KP / 16; ++t) {                        // K step: pixels 16t .. 16t+15 = 256 bytes into every group
                 const uint64_t dA1 = umma_desc_mn(sA + t * 256, 128, WGG_GROUP), dA2 = dA1 + (uint64_t)(WGG_A_PART >> 4);
-                const uint64_t dB1 = umma_desc_mn(sB + t * 256, 128, WGG_GROUP), dB2 = dB1 + (uint64_t)(g.b_part >> 4);
-                umma_bf16(tmem, dA1, dB1, idesc, k > 0 || t > 0);
-                umma_bf16(tmem, dA1, dB2, idesc, true);
-                umma_bf16(tmem, dA2, dB1, idesc, true);
+                if constexpr (!ROWS) {
+                    const uint64_t dB1 = umma_desc_mn(sB + t * 256, 128, WGG_GROUP), dB2 = dB1 + (uint64_t)(g.b_part >> 4);
+                    umma_bf16(tmem, dA1, dB1, idesc, k > 0 || t > 0);
+                    umma_bf16(tmem, dA1, dB2, idesc, true);
+                    umma_bf16(tmem, dA2, dB1, idesc, true);
+                } else {
+                    // pixel 16t of the stage sits at (row r, column x) of the segment; tap (ky, kx) reads the row tile of ky
+                    // kx pixels further right (the tile starts `pad` pixels left of the segment).  One MMA reads 4 KB of A and
+                    // 32 * nb bytes of B from shared memory: with all kh * kw taps in one CTA (nb <= 56) the re-reads of A
+                    // bound the kernel (measured: 0.81 vs 0.62 ms on dres2), so a tile holds ONE kernel row and nb up to 160
+                    const int r = (16 * t) / g.seg, x = (16 * t) - r * g.seg;
+                    const uint32_t row0 = sB + (uint32_t)(r * g.bpr + x) * 16;
+                    for (int kyi = 0; kyi < g.kyn; ++kyi)
+                        for (int kx = 0; kx < g.kw; ++kx) {
+                            const uint64_t dB1 = umma_desc_mn(row0 + kyi * 2 * g.b_part + kx * 16, 128, g.bp * 16), dB2 = dB1 + (uint64_t)(g.b_part >> 4);
+                            const uint32_t d = tmem + (uint32_t)((kyi * g.kw + kx) * g.nb);
+                            umma_bf16(d, dA1, dB1, idesc, k > 0 || t > 0);
+                            umma_bf16(d, dA1, dB2, idesc, true);
+                            umma_bf16(d, dA2, dB1, idesc, true);
+                        }
+                }
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[4 + slot])) : "memory");
         }
@@ -279,6 +342,27 @@ static int wgg_setup(WggGeo& g, int n, int ca, int cb, int hs, int ws_, int hl, 
         if (best < 0 || cost < best) best = cost, g.tg = tg, g.nb = nb;
     }
     if (best < 0) { set_error("conv_wgrad: no tiling for %d taps", T); return FFWM_ERR_ARG; }
+    // row mode (stride 1, rows of S in whole 64-pixel stages): a tile is one KERNEL ROW: one [nb channels][segment + kw - 1
+    // pixels] tile of L feeds the kw taps of that row through descriptor offsets, kw * nb <= 512 TMEM columns: L is loaded
+    // once per kernel row instead of once per tap, S once per (b tile, kernel row) with nb up to 160 instead of 200 / tap.
+    // Cost in (8-channel group, pixel) loads per stage, same unit as `best` * 64.
+    g.rows_mode = 0, g.seg = g.rps = g.bpr = g.bp = 0, g.kyn = 1;
+    const int seg = std::min(ws_, 64);
+    if (stride == 1 && kw >= 2 && !opt(OPT_WGRAD_NO_ROWS) && ws_ % 16 == 0 && 64 % seg == 0 && ws_ % seg == 0 && hs % (64 / seg) == 0) {
+        const int rps = 64 / seg, bpr = seg + kw - 1, bp = rps * bpr, kyn = 1;
+        int64_t best_rows = best * 64;
+        // nb >= 96: an MMA re-reads its 4 KB of A for 32 * nb bytes of B; with narrow tiles those re-reads cost more shared-
+        // memory bandwidth than the shared loads save (measured: 64 -> 64 channels 0.135 ms in row mode, 0.117 ms gathered)
+        for (int nb = 96; nb <= 256 && kyn * kw * nb <= 512; nb += 16) {
+            if (nb - 16 >= cb) break;                                      // wider than the channel count rounded up to 16
+            const int nbg = nb / 8;
+            if ((int64_t)kyn * nbg * bp > 4 * WGG_PRODUCERS) continue;     // at most 4 items per producer thread
+            if (2 * (2 * WGG_A_PART + (int64_t)kyn * 2 * nbg * bp * 16) > 227 * 1024 - 256) continue;   // two stages must fit
+            const int64_t nbt = (cb + nb - 1) / nb;
+            const int64_t cost = (kh / kyn) * nbt * (16 * 64 + (int64_t)kyn * nbg * bp);
+            if (cost < best_rows) best_rows = cost, g.rows_mode = 1, g.tg = kyn * kw, g.nb = nb, g.seg = seg, g.rps = rps, g.bpr = bpr, g.bp = bp, g.kyn = kyn;
+        }
+    }
     g.nn = g.tg * g.nb;
     g.nat = (ca + 127) / 128, g.nbt = (cb + g.nb - 1) / g.nb, g.ntg = T / g.tg;
     g.tiles = g.nat * g.nbt * g.ntg;
@@ -299,8 +383,8 @@ static int wgg_setup(WggGeo& g, int n, int ca, int cb, int hs, int ws_, int hl, 
         const double cost = (double)waves * (sps + 6) + 0.5 * (double)sp;
         if (best_cost < 0 || cost < best_cost) best_cost = cost, g.stages_per_split = sps, g.splits = (int)sp;
     }
-    g.b_part = (g.nn / 8) * WGG_GROUP;
-    g.stage_bytes = 2 * WGG_A_PART + 2 * g.b_part;
+    g.b_part = g.rows_mode ? (g.nb / 8) * g.bp * 16 : (g.nn / 8) * WGG_GROUP;
+    g.stage_bytes = 2 * WGG_A_PART + (g.rows_mode ? g.kyn : 1) * 2 * g.b_part;
     g.nstage = std::max(2, std::min(3, (227 * 1024 - 256) / g.stage_bytes));
     g.tmem_cols = 32;
     while (g.tmem_cols < g.nn) g.tmem_cols *= 2;
@@ -346,9 +430,10 @@ extern "C" int ffwm_conv_wgrad(const ffwm_tensor4* small, const ffwm_tensor4* la
     const int64_t need = (int64_t)g.splits * g.tiles * 128 * g.nn * (int64_t)sizeof(float);
     if (!workspace || workspace_bytes < need) { set_error("conv_wgrad: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes, (long long)need); return FFWM_ERR_SHAPE; }
     if (g.splits > 65535) { set_error("conv_wgrad: grid too large"); return FFWM_ERR_TOO_LARGE; }
-    cudaError_t e = cudaFuncSetAttribute(conv_gen_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    auto kern = g.rows_mode ? conv_gen_wgrad_tc_kernel<true> : conv_gen_wgrad_tc_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("conv_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
-    conv_gen_wgrad_tc_kernel<<<dim3(g.tiles, g.splits), WGG_PRODUCERS + 32, g.nstage * g.stage_bytes + 128, st>>>(sv, lv, static_cast<float*>(workspace), g);
+    kern<<<dim3(g.tiles, g.splits), WGG_PRODUCERS + 32, g.nstage * g.stage_bytes + 128, st>>>(sv, lv, static_cast<float*>(workspace), g);
     if ((rc = check_launch("conv_wgrad"))) return rc;
     conv_gen_wgrad_reduce_kernel<<<dim3(g.nat * g.nbt * 128, (g.nb + WGG_RED_BC - 1) / WGG_RED_BC), 128, 0, st>>>(
         static_cast<const float*>(workspace), wv.p, wv.sb, wv.sc, (int64_t)wv.sh, (int64_t)wv.sw, g);

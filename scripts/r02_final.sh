@@ -15,13 +15,28 @@ FFWM_CONV_MATH_FWD=1 timeout 400 python bench.py --no-cpu-baseline --no-warp --n
 timeout 300 python -m benchmarks.conv --out $O/${TAG}_conv.json > $O/${TAG}_conv.txt 2>&1
 timeout 300 python -m benchmarks.conv --gen --out $O/${TAG}_conv_gen.json > $O/${TAG}_conv_gen.txt 2>&1
 timeout 300 python -m benchmarks.conv --wgrad --out $O/${TAG}_conv_wgrad.json > $O/${TAG}_conv_wgrad.txt 2>&1
+timeout 300 python benchmarks/batch_norm.py > $O/${TAG}_batch_norm.txt 2>&1
+for sw in FFWM_FUSED_BN=0 FFWM_FUSED_ADAM=0; do
+    env $sw timeout 400 python bench.py --no-cpu-baseline --no-warp --no-library-baseline --no-e2e > $O/${TAG}_bench_${sw%%=*}_off.json 2> /dev/null; echo "bench $sw rc=$?"
+done
+# compute-sanitizer over the kernels added since the last sanitizer pass (batch norm / channel sum, weight packing, wgrad reduction)
+{
+for tool in memcheck racecheck; do
+    echo "== batch_norm_$tool"
+    timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 20 python -m pytest tests/test_batch_norm_gpu.py -q -x \
+        -k "2-5-7-9 or 3-4-2-2 or 8-195-32-32 or channel_sum or bit_identical" 2>&1 | grep -E "SUMMARY|passed|failed" | tail -2
+done
+echo "== convgen_pack_wgrad_memcheck"
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 20 python -m pytest tests/test_conv_gen_gpu.py -q -x \
+    -k "modules_autograd or deterministic or strided_views" 2>&1 | grep -E "SUMMARY|passed|failed" | tail -2
+} > $O/${TAG}_sanitizer_summary.txt 2>&1; cat $O/${TAG}_sanitizer_summary.txt
 FFWM_BENCH_GRAPH=0 FFWM_BENCH_NCU_RANGE=1 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 40000 --csv --log-file $O/launches_train_$TAG.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-warp --no-library-baseline > $O/ncu_launches_train_$TAG.log 2>&1; echo "ncu train launches rc=$?"
 [[ -f $O/launches_train_$TAG.csv ]] && python scripts/launch_summary.py $O/launches_train_$TAG.csv $O/${TAG}_launches_train_summary.txt --rm
 python - $TAG <<'PY'
 import json, sys
 t = sys.argv[1]
-for f in ("bench", "bench_reference", "bench_warp", "bench_warp_smooth", "bench_flownet", "bench_fwdbf16"):
+for f in ("bench", "bench_reference", "bench_warp", "bench_warp_smooth", "bench_flownet", "bench_fwdbf16", "bench_FFWM_FUSED_BN_off", "bench_FFWM_FUSED_ADAM_off"):
     try:
         d = json.loads(open("gpurun_out/%s_%s.json" % (t, f)).read().strip().splitlines()[-1])
         print(f, round(d["value"], 2), d["unit"], round(d["ms_per_step"], 3), "ms/step", "e2e", d.get("e2e", {}).get("value"))
