@@ -170,8 +170,9 @@ WGRAD_TOL = 4e-5      # of max|ref|; chains are capped at 768 accumulator update
 
 # stride-1 shapes whose rows fill whole 64-pixel stages take the weight gradient's ROW mode (one tile per kernel row shared by
 # its taps): widths 128 / 64 (one or two segments per row), 32 / 16 (two / four rows per stage), 5x5, 2x2, no padding
-ROW_MODE_CASES = [(8, 195, 195, 128, 128, 3, 1, 1), (2, 64, 64, 64, 64, 3, 1, 1), (2, 96, 200, 32, 32, 3, 1, 1), (2, 30, 50, 64, 64, 5, 1, 2),
-                  (2, 24, 40, 18, 18, 3, 1, 0), (1, 16, 24, 17, 33, 2, 1, 0), (3, 8, 136, 16, 16, 3, 1, 1)]
+# (and at least 96 input channels: narrower tiles stay in the gathered mode)
+ROW_MODE_CASES = [(8, 195, 195, 128, 128, 3, 1, 1), (2, 64, 64, 64, 64, 3, 1, 1), (2, 96, 200, 32, 32, 3, 1, 1), (2, 100, 50, 64, 64, 5, 1, 2),
+                  (2, 120, 40, 18, 18, 3, 1, 0), (1, 130, 24, 17, 33, 2, 1, 0), (3, 104, 136, 16, 16, 3, 1, 1), (1, 260, 20, 16, 64, 3, 1, 1)]
 
 
 @pytest.mark.parametrize("b,cin,cout,h,w,k,s,p", CONV_CASES + ROW_MODE_CASES)
