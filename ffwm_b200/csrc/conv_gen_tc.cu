@@ -189,8 +189,11 @@ __global__ void __launch_bounds__(256) conv_gen_pack_kernel(const float* __restr
 }
 
 // ---------------------------------------------------------------- the convolution
-template <bool BF>
-__global__ void __launch_bounds__(GN_PRODUCERS + 32, 1)
+// OCC = CTAs per SM the kernel is compiled for: 2 caps the registers at 56 and is launched with <= 113 KB of shared memory
+// and <= 256 TMEM columns, so that two CTAs share an SM and one's load -> split -> store -> MMA latency chain hides behind
+// the other's (the small-map layers are latency-bound: ncu shows 62 % of cycles without an eligible warp at one CTA per SM).
+template <bool BF, int OCC>
+__global__ void __launch_bounds__(GN_PRODUCERS + 32, OCC)
 conv_gen_tc_kernel(View<const float> x, const unsigned char* __restrict__ packed, const float* __restrict__ bias, View<float> out,
                    const __grid_constant__ GnGeo g) {
     constexpr int CPS = BF ? 8 : 4;                                    // channels per 16-byte slot
@@ -449,9 +452,20 @@ extern "C" int ffwm_conv_forward(const ffwm_tensor4* x, const void* packed, cons
         min_units = std::min(min_units, g.nkb * g.cls[i].ntaps);
     }
     if (max_tiles == 0) return FFWM_OK;
+    // two CTAs per SM (see the kernel), measured per shape (profiles/r02y_conv_gen_occ.txt): a gain where many tiles queue per
+    // SM (one CTA's epilogue overlaps the other's main loop: 1x1 195->195 @128 0.136 -> 0.095 ms) and where one or two tiles
+    // stream a large weight (1024->1024 @2x2: 0.052 -> 0.033 ms); 5 % slower in between (shorter stages, two-deep ring)
+    const int occ_opt = opt(OPT_CONV_OCC2);                            // 0: automatic, 1: never, 2: always
+    const bool occ2 = occ_opt == 2 || (occ_opt == 0 && (ctas >= 2 * (int64_t)sm_count() || max_tiles <= 2));
+    if (occ2) {
+        g.upst = std::max(1, std::min(GN_MAXU, (56 * 1024) / (GN_A_UNIT + g.b_unit)));
+        g.stage_bytes = g.upst * (GN_A_UNIT + g.b_unit);
+        g.nstage = 2;
+    }
     // split the K sequence while the tiles alone leave SMs idle; every split keeps >= 2 stages of the shortest class
     const int min_stages = (min_units + g.upst - 1) / g.upst;
-    g.splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(sm_count() / std::max<int64_t>(ctas, 1), min_stages / 2), 64));
+    const int64_t slots = (int64_t)sm_count() * (occ2 ? 2 : 1);
+    g.splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(slots / std::max<int64_t>(ctas, 1), min_stages / 2), 64));
     if ((int64_t)g.nclass * g.splits > 65535 || g.ncob > 65535) { set_error("conv_forward: grid too large"); return FFWM_ERR_TOO_LARGE; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (g.splits > 1) {
@@ -464,7 +478,7 @@ extern "C" int ffwm_conv_forward(const ffwm_tensor4* x, const void* packed, cons
         }
     }
     const int smem = g.nstage * g.stage_bytes + 128;
-    auto kern = math ? conv_gen_tc_kernel<true> : conv_gen_tc_kernel<false>;
+    auto kern = occ2 ? (math ? conv_gen_tc_kernel<true, 2> : conv_gen_tc_kernel<false, 2>) : (math ? conv_gen_tc_kernel<true, 1> : conv_gen_tc_kernel<false, 1>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("conv_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
     dim3 grid(max_tiles, g.ncob, g.nclass * g.splits);
