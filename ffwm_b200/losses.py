@@ -33,6 +33,8 @@ from .external_function import AffineResidualFunction, BlockExtractor, LocalAttn
 # library ops; FFWM_FUSED_AFFINE=0 / FFWM_FUSED_CORRMAX=0 restore those chains (A/B runs, and what the CPU tests exercise).
 FUSED_AFFINE = os.environ.get("FFWM_FUSED_AFFINE", "1") == "1"
 FUSED_CORRMAX = os.environ.get("FFWM_FUSED_CORRMAX", "1") == "1"
+# PerceptualLoss.many: the L1 terms of all pairs of a resolution in one batched pass per VGG layer (FFWM_BATCHED_L1=0: per pair)
+BATCHED_L1 = os.environ.get("FFWM_BATCHED_L1", "1") == "1"
 
 
 class GANLoss(nn.Module):
@@ -361,10 +363,36 @@ class PerceptualLoss(nn.Module):
             xv = self.vgg(torch.cat([pairs[i][0] for i in idxs]))
             with torch.no_grad():
                 yv = self.vgg(torch.cat([pairs[i][1] for i in idxs]))
+            if BATCHED_L1 and isinstance(self.criterion, nn.L1Loss) and self.criterion.reduction == "mean":
+                # every pair's mean |a - b| per layer from ONE pass over the concatenated features: per-sample means, then a
+                # (samples x pairs) averaging matrix — the samples of a group have equal numel, so the mean of a pair's
+                # per-sample means IS its L1Loss; 5 layers x 7 pairs x (sub, abs, mean, mul, add) and their autograd
+                # mirror become 5 x 4 kernels
+                seg = self._segment_matrix(sizes, xv[self.layers[0]])
+                acc = None
+                for layer, w in zip(self.layers, self.weights):
+                    per = F.l1_loss(xv[layer], yv[layer], reduction="none").flatten(1).mean(1)      # (samples,)
+                    acc = w * (per @ seg) if acc is None else acc + w * (per @ seg)
+                for k, i in enumerate(idxs):
+                    out[i] = out[i] + acc[k]
+                continue
             for layer, w in zip(self.layers, self.weights):
                 for i, a, b in zip(idxs, xv[layer].split(sizes), yv[layer].split(sizes)):
                     out[i] = out[i] + w * self.criterion(a, b)
         return out
+
+    def _segment_matrix(self, sizes, like):
+        device = like.device
+        key = (tuple(sizes), str(device), like.dtype)
+        cache = self.__dict__.setdefault("_seg_cache", {})
+        if key not in cache:
+            m = torch.zeros(sum(sizes), len(sizes), dtype=like.dtype)
+            r = 0
+            for k, n in enumerate(sizes):
+                m[r:r + n, k] = 1.0 / n
+                r += n
+            cache[key] = m.to(device)
+        return cache[key]
 
 
 class PerceptualCorrectness(nn.Module):

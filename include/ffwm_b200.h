@@ -199,6 +199,21 @@ int ffwm_batch_norm_backward(const float* x, const float* grad_out, const float*
                              float* grad_gamma, float* grad_beta, int n, int c, int64_t hw, void* workspace, int64_t workspace_bytes,
                              void* stream);
 
+/* ---- spectral norm of all layers of a network at once (csrc/spectral_norm.cu) --------------------------------------------
+ * Replaces torch.nn.utils.spectral_norm's per-layer pre-forward hooks (models/base_networks.py:204-246, :397-410; one power
+ * iteration, dim 0): v = normalize(W^T u), u = normalize(W v), sigma = u . (W v), weight = W / sigma — three launches for
+ * all layers forward, two backward.  `table` (device memory): `layers` rows of 8 int64 {weight_orig pointer (h x w row-major
+ * fp32), u pointer (h), v pointer (w), h, w, offset of the layer in the flat element buffers, in the flat t / v buffers (sum of
+ * w), in the flat s / u buffers (sum of h)}, then three arrays of layers + 1 int64 block prefix sums with ceil(w / 32),
+ * ceil(h / 8), ceil(h * w / 4096) blocks per layer (blocks1..3 = their totals).
+ * forward: out (sum of h*w) = W / sigma per layer; t, v_saved (sum of w), s, u_saved (sum of h) and sigma (layers) are
+ * scratch / saved for backward; update = 1 runs the power iteration and overwrites u and v, 0 uses them as stored (eval mode).
+ * backward: grad_w (flat, like out) = gradient of sum(grad_out * W / sigma) with u, v constants; partial: blocks3 doubles. */
+int ffwm_spectral_norm_forward(const void* table, int layers, int update, float eps, float* out, float* t, float* s, float* u_saved,
+                               float* v_saved, float* sigma, int blocks1, int blocks2, int blocks3, void* stream);
+int ffwm_spectral_norm_backward(const void* table, int layers, const float* grad_out, const float* u_saved, const float* v_saved,
+                                const float* sigma, float* grad_w, void* partial, int blocks3, void* stream);
+
 /* out[c] = sum over (n, hw) of x (N, C, H*W contiguous fp32): the bias gradient of a convolution (grad_out.sum((0,2,3)) in
  * aten::convolution_backward), two kernels, deterministic.  workspace: ffwm_batch_norm_workspace_bytes(N, C, H*W) bytes. */
 int ffwm_channel_sum(const float* x, float* out, int n, int c, int64_t hw, void* workspace, int64_t workspace_bytes, void* stream);
