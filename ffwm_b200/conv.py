@@ -35,6 +35,8 @@ MATH_BWD = int(os.environ.get("FFWM_CONV_MATH_BWD", ops.L.MATH_BF16X3))
 # The kernel also handles width 16, but there a map is one or two CTAs per (image, channel tile) with a
 # long serial K loop: measured slower than cuDNN inside the train step (98.4 -> 101.8 ms), so it is off.
 WIDTHS = (128, 64, 32)
+if os.environ.get("FFWM_CONV3X3_WIDTHS"):     # A/B: route some widths to the general kernel instead
+    WIDTHS = tuple(int(v) for v in os.environ["FFWM_CONV3X3_WIDTHS"].split(","))
 # experimental, unmeasured: 128 output channels per CTA for the W = 128 layers with more than 64 of them
 NT128 = os.environ.get("FFWM_CONV_NT128", "1") == "1"
 

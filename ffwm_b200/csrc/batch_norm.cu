@@ -265,6 +265,135 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, c
     }
 }
 
+// ---- small maps: one block per channel, the channel in registers, one launch per direction ---------------------------------
+// Up to 8 192 values per channel (N * H*W; most of FlowNet below 32x32, the generator's 16x16 / 32x32 stages): thread t holds
+// the float4 chunks t, t + 256, ... of its channel (R <= 8 of them), so the statistics are an exact two-pass mean / variance
+// and the map crosses HBM once per direction; the two-kernel path above would spend its time in launch latency here.
+constexpr int BN_SMALL_MAX = 8192;
+
+template <int R>
+__device__ __forceinline__ void bn_small_load(const float* __restrict__ p, const BnGeo& g, int c, float4 (&v)[R]) {
+    const int hw4 = g.hw >> 2, total4 = g.n * hw4;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const int e = threadIdx.x + k * BN_THREADS;
+        if (e < total4) {
+            const int n = e / hw4, o = e - n * hw4;
+            v[k] = __ldg(reinterpret_cast<const float4*>(p + ((int64_t)n * g.c + c) * g.hw) + o);
+        } else v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+template <int R>
+__device__ __forceinline__ void bn_small_store(float* __restrict__ p, const BnGeo& g, int c, const float4 (&v)[R]) {
+    const int hw4 = g.hw >> 2, total4 = g.n * hw4;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const int e = threadIdx.x + k * BN_THREADS;
+        if (e < total4) {
+            const int n = e / hw4, o = e - n * hw4;
+            reinterpret_cast<float4*>(p + ((int64_t)n * g.c + c) * g.hw)[o] = v[k];
+        }
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ residual, BnGeo g, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
+                    float* __restrict__ save_mean, float* __restrict__ save_invstd, float* __restrict__ y) {
+    __shared__ double sh[2 * BN_THREADS / 32];
+    const int c = blockIdx.x, total4 = g.n * (g.hw >> 2);
+    float4 v[R];
+    bn_small_load<R>(x, g, c, v);
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < R; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    double a = s, b = 0.0;
+    bn_block_sum2(a, b, sh);
+    const double cnt = (double)g.n * g.hw;
+    const float mean = (float)(a / cnt);
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < R; ++k)
+        if (threadIdx.x + k * BN_THREADS < total4) {
+            const float d0 = v[k].x - mean, d1 = v[k].y - mean, d2 = v[k].z - mean, d3 = v[k].w - mean;
+            q = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, q))));
+        }
+    a = q, b = 0.0;
+    bn_block_sum2(a, b, sh);
+    const double var = a / cnt;
+    const float invstd = (float)(1.0 / sqrt(var + (double)g.eps));
+    if (threadIdx.x == 0) {
+        save_mean[c] = mean;
+        save_invstd[c] = invstd;
+        if (running_mean) running_mean[c] = (1.f - g.momentum) * running_mean[c] + g.momentum * mean;
+        if (running_var) running_var[c] = (1.f - g.momentum) * running_var[c] + g.momentum * (float)(var * (cnt / (cnt - 1.0)));
+    }
+    const float kk = __fmul_rn(__ldg(gamma + c), invstd), bt = __ldg(beta + c), slope = g.slope;
+    float4 r[R];
+    if (residual) bn_small_load<R>(residual, g, c, r);
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        float4 o = make_float4(bn_value(v[k].x, mean, kk, bt), bn_value(v[k].y, mean, kk, bt), bn_value(v[k].z, mean, kk, bt), bn_value(v[k].w, mean, kk, bt));
+        if (residual) o = make_float4(__fadd_rn(o.x, r[k].x), __fadd_rn(o.y, r[k].y), __fadd_rn(o.z, r[k].z), __fadd_rn(o.w, r[k].w));
+        if (slope != 1.f) o = make_float4(bn_act(o.x, slope), bn_act(o.y, slope), bn_act(o.z, slope), bn_act(o.w, slope));
+        v[k] = o;
+    }
+    bn_small_store<R>(y, g, c, v);
+}
+
+template <int R>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ yout, BnGeo g,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ save_mean,
+                    const float* __restrict__ save_invstd, float* __restrict__ grad_x, float* __restrict__ grad_residual,
+                    float* __restrict__ grad_gamma, float* __restrict__ grad_beta) {
+    __shared__ double sh[2 * BN_THREADS / 32];
+    const int c = blockIdx.x;
+    const float mean = __ldg(save_mean + c), invstd = __ldg(save_invstd + c);
+    const float kk = __fmul_rn(__ldg(gamma + c), invstd), bt = __ldg(beta + c), slope = g.slope;
+    const bool have_y = yout != nullptr;
+    float4 v[R], e[R];
+    bn_small_load<R>(x, g, c, v);
+    bn_small_load<R>(dy, g, c, e);                                     // padding chunks: dy = 0 -> ge = 0
+    if (slope != 1.f) {
+        float4 yo[R];
+        if (have_y) bn_small_load<R>(yout, g, c, yo);
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const float4 w = have_y ? yo[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+            e[k] = make_float4(bn_ge(e[k].x, v[k].x, w.x, have_y, mean, kk, bt, slope), bn_ge(e[k].y, v[k].y, w.y, have_y, mean, kk, bt, slope),
+                               bn_ge(e[k].z, v[k].z, w.z, have_y, mean, kk, bt, slope), bn_ge(e[k].w, v[k].w, w.w, have_y, mean, kk, bt, slope));
+        }
+    }
+    if (grad_residual) bn_small_store<R>(grad_residual, g, c, e);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        s1 += (e[k].x + e[k].y) + (e[k].z + e[k].w);
+        s2 = fmaf(e[k].x, v[k].x - mean, fmaf(e[k].y, v[k].y - mean, fmaf(e[k].z, v[k].z - mean, fmaf(e[k].w, v[k].w - mean, s2))));
+    }
+    double a = s1, b = s2;
+    bn_block_sum2(a, b, sh);
+    const double cnt = (double)g.n * g.hw;
+    if (threadIdx.x == 0) {
+        if (grad_gamma) grad_gamma[c] = (float)(b * (double)invstd);
+        if (grad_beta) grad_beta[c] = (float)a;
+    }
+    const float ma = (float)(a / cnt), mb = (float)(b * (double)invstd * (double)invstd / cnt);
+#pragma unroll
+    for (int k = 0; k < R; ++k)
+        v[k] = make_float4(kk * (e[k].x - ma - (v[k].x - mean) * mb), kk * (e[k].y - ma - (v[k].y - mean) * mb),
+                           kk * (e[k].z - ma - (v[k].z - mean) * mb), kk * (e[k].w - ma - (v[k].w - mean) * mb));
+    bn_small_store<R>(grad_x, g, c, v);
+}
+
+static bool bn_small(const BnGeo& g) { return g.vec && (int64_t)g.n * g.hw <= BN_SMALL_MAX && !opt(OPT_BN_NO_SMALL); }
+static int bn_small_r(const BnGeo& g) {
+    const int need = (g.n * (g.hw >> 2) + BN_THREADS - 1) / BN_THREADS;
+    return need <= 1 ? 1 : need <= 2 ? 2 : need <= 4 ? 4 : 8;
+}
+
 // ---- per-channel sum of an (N, C, H*W) map: the bias gradient of a convolution (grad_out.sum((0, 2, 3))) ------------------
 // at::sum gives this reduction C x 4 blocks (64 us for the 102 MB gradients of dres2, 1.6 TB/s); here every (plane, chunk)
 // block writes one double, and one warp per channel adds the N * chunks partials in a fixed order.
@@ -344,6 +473,12 @@ extern "C" int ffwm_batch_norm_forward(const float* x, const float* residual, co
         return FFWM_ERR_ARG;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (bn_small(g)) {
+#define FFWM_BN_SF(R) bn_small_fwd_kernel<R><<<c, BN_THREADS, 0, st>>>(x, residual, g, gamma, beta, running_mean, running_var, save_mean, save_invstd, y)
+        switch (bn_small_r(g)) { case 1: FFWM_BN_SF(1); break; case 2: FFWM_BN_SF(2); break; case 4: FFWM_BN_SF(4); break; default: FFWM_BN_SF(8); }
+#undef FFWM_BN_SF
+        return check_launch("batch_norm_forward (small)");
+    }
     const dim3 grid(n * c, g.chunks);
     double* partial = static_cast<double*>(workspace);
     bn_stats_kernel<<<grid, BN_THREADS, 0, st>>>(x, g, partial);
@@ -373,6 +508,12 @@ extern "C" int ffwm_batch_norm_backward(const float* x, const float* grad_out, c
         return FFWM_ERR_ARG;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (bn_small(g)) {
+#define FFWM_BN_SB(R) bn_small_bwd_kernel<R><<<c, BN_THREADS, 0, st>>>(x, grad_out, y_out, g, gamma, beta, save_mean, save_invstd, grad_x, grad_residual, grad_gamma, grad_beta)
+        switch (bn_small_r(g)) { case 1: FFWM_BN_SB(1); break; case 2: FFWM_BN_SB(2); break; case 4: FFWM_BN_SB(4); break; default: FFWM_BN_SB(8); }
+#undef FFWM_BN_SB
+        return check_launch("batch_norm_backward (small)");
+    }
     const dim3 grid(n * c, g.chunks);
     double* partial = static_cast<double*>(workspace);
     bn_bwd_stats_kernel<<<grid, BN_THREADS, 0, st>>>(x, grad_out, y_out, g, gamma, beta, save_mean, save_invstd, grad_residual, partial);

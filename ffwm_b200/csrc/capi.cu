@@ -91,7 +91,7 @@ int sm_count() {
 
 static const char* const g_opt_names[OPT_COUNT] = {
     "DISABLE_TILED", "FORCE_TILED", "DISABLE_ROLL", "FORCE_ROLL", "SCATTER_TILED", "DISABLE_TILED_GFLOW",
-    "DISABLE_QUAD", "GQ_SCALAR_FILL", "SCATTER_SCALAR_FLUSH", "WGRAD_NO_ROWS", "CONV_OCC2", "WGRAD_CHAIN"};
+    "DISABLE_QUAD", "GQ_SCALAR_FILL", "SCATTER_SCALAR_FLUSH", "WGRAD_NO_ROWS", "BN_NO_SMALL", "CONV_OCC2", "WGRAD_CHAIN"};
 static int g_opts[OPT_COUNT];
 static int g_opts_ready = 0;
 

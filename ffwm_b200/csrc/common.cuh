@@ -77,6 +77,7 @@ enum Opt {
     OPT_GQ_SCALAR_FILL,
     OPT_SCATTER_SCALAR_FLUSH,
     OPT_WGRAD_NO_ROWS,           // conv_wgrad: never use the row mode (one tile per kernel row shared by its taps)
+    OPT_BN_NO_SMALL,             // batch_norm: never the one-block-per-channel kernels for small maps
     OPT_CONV_OCC2,               // conv_forward: 0 two CTAs per SM for small grids (automatic), 1 never, 2 always
     OPT_WGRAD_CHAIN,             // conv_wgrad: longest accumulation chain per CTA in 64-pixel stages (0 = the default, 64)
     OPT_COUNT

@@ -16,6 +16,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .conv import Conv2d
+from .pool import MaxPool2d, max_pool2x2
 
 # max-feature-map as one kernel per direction (csrc/mfm.cu): bit-exact vs torch.max on a B200 (tests/test_mfm_gpu.py), train step
 # 73.4 -> 72.0 ms (profiles/r02b_switches.txt).  FFWM_FUSED_MFM=0 restores the torch ops for A/B runs.
@@ -86,7 +87,7 @@ def _stack(block, count, cin, cout):
 
 
 def _pool():
-    return nn.MaxPool2d(kernel_size=2, stride=2, ceil_mode=True)
+    return MaxPool2d(kernel_size=2, stride=2, ceil_mode=True)
 
 
 class network_9layers(nn.Module):
@@ -160,7 +161,7 @@ class network_29layers_v2(nn.Module):
 
     @staticmethod
     def _mixpool(x):
-        return F.max_pool2d(x, 2) + F.avg_pool2d(x, 2)
+        return max_pool2x2(x) + F.avg_pool2d(x, 2)
 
     def forward(self, x):
         x = self._mixpool(self.conv1(x))

@@ -26,6 +26,7 @@ import torch.nn.functional as F
 
 from . import base_networks, ops
 from .conv import Conv2d
+from .pool import MaxPool2d
 from .external_function import AffineResidualFunction, BlockExtractor, LocalAttnReshape, Resample2d, grid_warp
 
 # the affine regularisation as one kernel per direction (csrc/affine_reg.cu) and the correlation column-max of
@@ -257,7 +258,7 @@ class VGG19(nn.Module):
         layers, cin = [], 3
         for v in self.CFG:
             if v == 'M':
-                layers.append(nn.MaxPool2d(kernel_size=2, stride=2))
+                layers.append(MaxPool2d(kernel_size=2, stride=2))
             else:
                 layers += [Conv2d(cin, v, kernel_size=3, padding=1), nn.ReLU(inplace=True)]
                 cin = v

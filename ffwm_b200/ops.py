@@ -290,3 +290,25 @@ def channel_sum(x):
     out = torch.empty(c, dtype=torch.float32, device=x.device)
     L.call("ffwm_channel_sum", dev, _ptr(x), _ptr(out), n, c, ctypes.c_int64(hw), _ptr(ws), ctypes.c_int64(nbytes))
     return out
+
+
+def max_pool2x2_forward(x, out):
+    """out (N,C,ho,wo) = 2x2 / stride-2 max pooling of a contiguous fp32 CUDA (N,C,h,w) map (csrc/pool.cu)."""
+    import ctypes
+    import torch
+    dev = L.require_cuda(x, out)
+    if not (x.dim() == 4 and x.is_contiguous() and out.is_contiguous() and x.dtype == torch.float32 and out.shape[:2] == x.shape[:2]):
+        raise ValueError("max_pool2x2: contiguous fp32 (N,C,H,W) tensors expected")
+    L.call("ffwm_max_pool2x2_forward", dev, _ptr(x), _ptr(out), ctypes.c_int64(x.size(0) * x.size(1)), int(x.size(2)), int(x.size(3)),
+           int(out.size(2)), int(out.size(3)))
+
+
+def max_pool2x2_backward(x, grad_out, grad_x):
+    import ctypes
+    import torch
+    dev = L.require_cuda(x, grad_out, grad_x)
+    if not (x.dim() == 4 and x.is_contiguous() and grad_out.is_contiguous() and grad_x.is_contiguous() and x.dtype == torch.float32
+            and grad_x.shape == x.shape and grad_out.shape[:2] == x.shape[:2]):
+        raise ValueError("max_pool2x2: contiguous fp32 (N,C,H,W) tensors expected")
+    L.call("ffwm_max_pool2x2_backward", dev, _ptr(x), _ptr(grad_out), _ptr(grad_x), ctypes.c_int64(x.size(0) * x.size(1)), int(x.size(2)),
+           int(x.size(3)), int(grad_out.size(2)), int(grad_out.size(3)))

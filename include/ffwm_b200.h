@@ -199,6 +199,14 @@ int ffwm_batch_norm_backward(const float* x, const float* grad_out, const float*
                              float* grad_gamma, float* grad_beta, int n, int c, int64_t hw, void* workspace, int64_t workspace_bytes,
                              void* stream);
 
+/* ---- 2x2 / stride-2 max pooling (csrc/pool.cu): nn.MaxPool2d(2, 2[, ceil_mode=True]) / F.max_pool2d(x, 2) of LightCNN and VGG19
+ * (lightcnn/light_cnn.py:38-42,96-124, models/losses.py:430-470) without ATen's int64 index map: x (planes, h, w) -> out (planes,
+ * ho, wo), contiguous fp32, ho in {floor(h/2), ceil(h/2)}; backward recomputes the argmax from x (first maximum wins, NaN wins:
+ * ATen's rule) and OVERWRITES grad_x. */
+int ffwm_max_pool2x2_forward(const float* x, float* out, int64_t planes, int h, int w, int ho, int wo, void* stream);
+int ffwm_max_pool2x2_backward(const float* x, const float* grad_out, float* grad_x, int64_t planes, int h, int w, int ho, int wo,
+                              void* stream);
+
 /* ---- spectral norm of all layers of a network at once (csrc/spectral_norm.cu) --------------------------------------------
  * Replaces torch.nn.utils.spectral_norm's per-layer pre-forward hooks (models/base_networks.py:204-246, :397-410; one power
  * iteration, dim 0): v = normalize(W^T u), u = normalize(W v), sigma = u . (W v), weight = W / sigma — three launches for

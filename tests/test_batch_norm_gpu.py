@@ -26,6 +26,9 @@ CASES = [
                                              # pre-activation within 3e-6 of zero is not defined at this conditioning)
     (1, 3, 96, 96, None, True, -3.0),        # several chunks per plane, batch 1
     (8, 64, 128, 128, 0.2, False, 0.5),
+    (2, 6, 16, 16, 0.2, True, 0.0),          # one block per channel (<= 8192 values per channel): 1 chunk per thread
+    (8, 12, 16, 32, None, False, 1.0),       # ... 4 chunks per thread
+    (7, 3, 20, 28, 0.2, False, 0.0),         # ... a ragged number of chunks
 ]
 
 
@@ -72,6 +75,16 @@ def test_forward_backward_match_torch_float64(n, c, h, w, slope, use_res, offset
     close(bs_.grad, bd.grad, 2e-5, "grad_beta")
     if use_res:
         close(rs.grad * safe, rd.grad * safe, 2e-5, "grad_residual")
+
+
+def test_small_maps_also_pass_on_the_two_kernel_path():
+    from ffwm_b200 import _lib
+    old = _lib.set_option("BN_NO_SMALL", 1)
+    try:
+        for case in [c for c in CASES if c[0] * c[2] * c[3] <= 8192]:
+            test_forward_backward_match_torch_float64(*case)
+    finally:
+        _lib.set_option("BN_NO_SMALL", old)
 
 
 def test_module_is_a_drop_in_for_bn_plus_leaky_relu():
