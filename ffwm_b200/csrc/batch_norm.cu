@@ -417,6 +417,22 @@ __global__ void __launch_bounds__(BN_THREADS) channel_sum_partial_kernel(const f
     if (threadIdx.x == 0) partial[(int64_t)k.c * (g.n * g.chunks) + k.n * g.chunks + k.chunk] = a;
 }
 
+// small maps (<= 8192 values per channel): one block per channel, one launch
+__global__ void __launch_bounds__(BN_THREADS) channel_sum_small_kernel(const float* __restrict__ x, BnGeo g, float* __restrict__ out) {
+    __shared__ double sh[2 * BN_THREADS / 32];
+    const int c = blockIdx.x, hw4 = g.hw >> 2, total4 = g.n * hw4;
+    float s1 = 0.f, s2 = 0.f;
+    for (int e = threadIdx.x; e < total4; e += BN_THREADS) {
+        const int n = e / hw4, o = e - n * hw4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + ((int64_t)n * g.c + c) * g.hw) + o);
+        s1 += v.x + v.y;
+        s2 += v.z + v.w;
+    }
+    double a = (double)s1 + (double)s2, b = 0.0;
+    bn_block_sum2(a, b, sh);
+    if (threadIdx.x == 0) out[c] = (float)a;
+}
+
 __global__ void __launch_bounds__(BN_THREADS) channel_sum_final_kernel(const double* __restrict__ partial, int c, int per_channel, float* __restrict__ out) {
     const int ch = blockIdx.x * (BN_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (ch >= c) return;
@@ -539,6 +555,10 @@ extern "C" int ffwm_channel_sum(const float* x, float* out, int n, int c, int64_
         return FFWM_ERR_ARG;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (g.vec && (int64_t)g.n * g.hw <= BN_SMALL_MAX && !opt(OPT_BN_NO_SMALL)) {
+        channel_sum_small_kernel<<<c, BN_THREADS, 0, st>>>(x, g, out);
+        return check_launch("channel_sum (small)");
+    }
     double* partial = static_cast<double*>(workspace);
     channel_sum_partial_kernel<<<dim3(g.n * c, g.chunks), BN_THREADS, 0, st>>>(x, g, partial);
     if ((rc = check_launch("channel_sum (partials)"))) return rc;

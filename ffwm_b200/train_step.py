@@ -22,6 +22,7 @@ import torch.nn.functional as F
 
 from . import base_networks, external_function, losses
 from .light_cnn import LightCNN_29Layers
+from .norm import DeferredCounters
 from .parallel import GradAverager
 
 
@@ -90,6 +91,7 @@ class FFWMTrainer:
         self.optimizer_G = torch.optim.Adam(self.netG.parameters(), lr=0.0004, **adam)
         self.optimizer_D = torch.optim.Adam(self.netD.parameters(), lr=0.0004, **adam)
         self.optimizers = [self.optimizer_G, self.optimizer_F, self.optimizer_D]
+        self._counters = DeferredCounters([self.netG, self.netD, self.flowNetF, self.flowNetB])     # BN call counters: one add per step
         self.optimizers_G = [self.optimizer_G, self.optimizer_F]
         self.optimizers_D = [self.optimizer_D]
 
@@ -223,6 +225,7 @@ class FFWMTrainer:
         if self.avg_G is not None:
             self.avg_G.average()
         self._step(self.optimizers_G)
+        self._counters.flush()
 
     # ------------------------------------------------------------------ CUDA graph
     def enable_cuda_graph(self, example_batch, warmup=3, segmented=None):
@@ -276,6 +279,7 @@ class FFWMTrainer:
                 self.backward_G()
             with torch.cuda.graph(g3, pool=pool):
                 self._step(self.optimizers_G)
+                self._counters.flush()
             self._graphs = [(g1, self.avg_D), (g2, self.avg_G), (g3, None)]
         self.graph_kernel_nodes = _lib.kernel_launches() - n0     # ffwm_b200 kernels recorded in the graph(s)
         self.graph_replays = 0
@@ -370,6 +374,7 @@ class FlowNetTrainer:
             self.Correctness.vgg.load_torchvision(vgg_weights)
         self.Regularization = losses.MultiAffineRegularizationLoss(kz_dic={1: 7, 2: 5, 3: 3})
         self.optimizer = torch.optim.Adam(self.flowNet.parameters(), lr=0.0004, betas=(0.5, 0.999), **_adam_impl(self.device))
+        self._counters = DeferredCounters([self.flowNet])
         self.avg = None
         if distributed is not None:
             distributed.broadcast_module_states([self.flowNet, self.Correctness])
@@ -405,6 +410,7 @@ class FlowNetTrainer:
         if self.avg is not None:
             self.avg.average()
         self.optimizer.step()
+        self._counters.flush()
 
     def get_current_losses(self):
         return {n: float(getattr(self, n).detach()) for n in self.loss_names if hasattr(self, n)}

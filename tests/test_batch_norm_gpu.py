@@ -151,3 +151,17 @@ def test_channel_sum_matches_float64(shape):
     scale = float(x.double().abs().sum((0, 2, 3)).max())
     assert float((got.double() - want).abs().max()) <= 2e-7 * scale
     assert torch.equal(got, ops.channel_sum(x))              # deterministic
+
+
+def test_deferred_counters_on_the_kernel_path():
+    from ffwm_b200.norm import BatchNorm2d, DeferredCounters
+    bn = BatchNorm2d(6).cuda()
+    ctr = DeferredCounters([bn])
+    x = torch.randn(4, 6, 8, 8, device="cuda")
+    for _ in range(3):
+        bn(x)
+    assert int(bn.num_batches_tracked) == 0                  # counted on the host, not yet added
+    ctr.flush()
+    assert int(bn.num_batches_tracked) == 3
+    ctr.flush()
+    assert int(bn.num_batches_tracked) == 3

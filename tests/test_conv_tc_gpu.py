@@ -89,7 +89,7 @@ def test_conv_module_autograd_matches_cudnn_fp64():
     n0 = _lib.kernel_launches()
     out = m(x)
     out.backward(go)
-    assert _lib.kernel_launches() - n0 == 8                  # pack + conv (forward, data gradient); weight gradient + its split-K reduction; bias gradient (2)
+    assert _lib.kernel_launches() - n0 in (7, 8)             # pack + conv (forward, data gradient); weight gradient + its split-K reduction; bias gradient (1 or 2 kernels)
     xr = x.detach().double().requires_grad_(True)
     wr = m.weight.detach().double().requires_grad_(True)
     br = m.bias.detach().double().requires_grad_(True)

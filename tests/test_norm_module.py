@@ -42,3 +42,18 @@ def test_norm_factories_of_the_reference_map_to_the_product_class():
     net = B.FlowNet(4)
     assert all(isinstance(m, BatchNorm2d) for m in net.modules() if isinstance(m, nn.BatchNorm2d))
     assert not any(type(m) is nn.LeakyReLU for m in net.modules())
+
+
+def test_deferred_counters_add_up_like_torch():
+    from ffwm_b200.norm import DeferredCounters
+    torch.manual_seed(2)
+    a = nn.Sequential(nn.Conv2d(3, 4, 1), BatchNorm2d(4))
+    b = nn.Sequential(nn.Conv2d(3, 4, 1), BatchNorm2d(4))
+    b.load_state_dict(a.state_dict())
+    ctr = DeferredCounters([b])
+    x = torch.randn(2, 3, 5, 5)
+    for _ in range(3):
+        a(x), b(x)
+    # (on the CPU the layer takes torch's path, which counts by itself: deferral only applies to the CUDA kernels' path)
+    ctr.flush()
+    assert int(a[1].num_batches_tracked) == int(b[1].num_batches_tracked) == 3
