@@ -104,7 +104,7 @@ _DIAG_FWD_LIB = _DIAG_DGRAD_LIB = False      # scripts/diag_nets.py only: one di
 
 class Conv3x3TCFunction(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, math_fwd=None):
         x = x.contiguous()
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
@@ -112,7 +112,8 @@ class Conv3x3TCFunction(Function):
             return torch.nn.functional.conv2d(x, weight, bias, padding=1)
         out = x.new_empty((x.size(0), weight.size(0), x.size(2), x.size(3)))
         nt = _nt(x.size(3), weight.size(0))
-        ops.conv3x3_forward(x, _packed(weight, False, nt, MATH_FWD), bias, out, nt=nt, math=MATH_FWD)
+        math = MATH_FWD if math_fwd is None else math_fwd
+        ops.conv3x3_forward(x, _packed(weight, False, nt, math), bias, out, nt=nt, math=math)
         return out
 
     @staticmethod
@@ -129,7 +130,7 @@ class Conv3x3TCFunction(Function):
             ops.conv3x3_forward(grad_out, _packed(weight, True, nt, MATH_BWD), None, gx, nt=nt, math=MATH_BWD)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             gw, gb = _wgrad(grad_out, x, weight, ctx.has_bias, 1, 1, False, 0, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
-        return gx, gw, gb
+        return gx, gw, gb, None
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -185,12 +186,13 @@ class ConvGenFunction(Function):
     """conv2d(x, W, b, stride, pad) — forward: conv_forward; grad_input: the transposed mode on the same weights."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, pad):
+    def forward(ctx, x, weight, bias, stride, pad, math_fwd=None):
         ctx.save_for_backward(x, weight)
         ctx.cfg = (bias is not None, stride, pad)
         kh, kw = weight.shape[2:]
         out = x.new_empty((x.size(0), weight.size(0), (x.size(2) + 2 * pad - kh) // stride + 1, (x.size(3) + 2 * pad - kw) // stride + 1))
-        ops.conv_forward(x, _packed_gen(weight, False, stride, pad, False, MATH_FWD), bias, out, kh, kw, stride, pad, False, MATH_FWD)
+        math = MATH_FWD if math_fwd is None else math_fwd
+        ops.conv_forward(x, _packed_gen(weight, False, stride, pad, False, math), bias, out, kh, kw, stride, pad, False, math)
         return out
 
     @staticmethod
@@ -205,7 +207,7 @@ class ConvGenFunction(Function):
             ops.conv_forward(grad_out, _packed_gen(weight, True, stride, pad, True, MATH_BWD), None, gx, kh, kw, stride, pad, True, MATH_BWD)
         if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
             gw, gb = _wgrad(grad_out, x, weight, has_bias, stride, pad, False, 0, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None
 
 
 class ConvTGenFunction(Function):
@@ -247,13 +249,30 @@ def conv2d(x, weight, bias, stride=(1, 1), padding=(0, 0), dilation=(1, 1), grou
 
 
 class Conv2d(nn.Conv2d):
+    math_fwd = None          # operand split of THIS layer's forward pass (None: the module-wide MATH_FWD); see set_forward_math
+
     def _conv_forward(self, input, weight, bias):
         if isinstance(self.padding, tuple):
             if eligible(input, weight, self.stride, self.padding, self.dilation, self.groups, self.padding_mode, bias=bias):
-                return Conv3x3TCFunction.apply(input, weight, bias)
+                return Conv3x3TCFunction.apply(input, weight, bias, self.math_fwd)
             if eligible_general(input, weight, self.stride, self.padding, self.dilation, self.groups, self.padding_mode, bias=bias):
-                return ConvGenFunction.apply(input, weight, bias, _sym(self.stride), _sym(self.padding))
+                return ConvGenFunction.apply(input, weight, bias, _sym(self.stride), _sym(self.padding), self.math_fwd)
         return super()._conv_forward(input, weight, bias)
+
+
+# The frozen feature extractors of the losses (VGG19, LightCNN-29) run their forward passes in the 3xBF16 split: their outputs
+# are as close to float64 as with 3xTF32 (LightCNN fc / pool 1.4e-5 / 2.6e-5 vs 3.2e-5 / 3.7e-5, profiles/r02h_network_accuracy.txt)
+# — what 3xBF16 forwards cost is gradient accuracy of the deep BatchNorm / LeakyReLU stacks being TRAINED (FlowNet 1.3e-2 vs
+# 1.9e-5, the discriminator 7.6e-3 vs 1.2e-5), and those keep 3xTF32.  FFWM_LOSSNET_MATH_FWD=0 puts them back on 3xTF32.
+LOSSNET_MATH_FWD = int(os.environ.get("FFWM_LOSSNET_MATH_FWD", ops.L.MATH_BF16X3))
+
+
+def set_forward_math(net, math):
+    """Operand split of the forward pass of every Conv2d of `net` (ops.L.MATH_TF32X3 / MATH_BF16X3; None = module default)."""
+    for m in net.modules():
+        if isinstance(m, Conv2d):
+            m.math_fwd = math
+    return net
 
 
 class ConvTranspose2d(nn.ConvTranspose2d):

@@ -25,7 +25,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import base_networks, ops
-from .conv import Conv2d
+from .conv import LOSSNET_MATH_FWD, Conv2d, set_forward_math
 from .pool import MaxPool2d
 from .external_function import AffineResidualFunction, BlockExtractor, LocalAttnReshape, Resample2d, grid_warp
 
@@ -121,7 +121,7 @@ class MultiScaleLDLoss(nn.Module):
 class IdentityLoss(nn.Module):
     def __init__(self, lightcnn, crop=False):
         super().__init__()
-        self.lightcnn = lightcnn
+        self.lightcnn = set_forward_math(lightcnn, LOSSNET_MATH_FWD)     # frozen feature extractor (ffwm_b200/conv.py)
         self.criterionL1 = nn.L1Loss()
         self.warpNet = base_networks.WarpNet()
         self.crop = crop
@@ -282,6 +282,7 @@ class VGG19(nn.Module):
             self.load_torchvision(torch.load(weights_path, map_location='cpu'))
         for p in self.parameters():
             p.requires_grad = False
+        set_forward_math(self, LOSSNET_MATH_FWD)                          # frozen feature extractor (ffwm_b200/conv.py)
 
     def load_torchvision(self, state):
         own = {k.split('.', 1)[1]: k for k in self.state_dict()}       # '9.weight' -> 'relu3_1.9.weight'
