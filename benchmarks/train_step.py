@@ -219,17 +219,17 @@ class TrainStepWorkload:
         default for cuDNN, outside the path's 1e-4 parity target).  Reported next to `value`; never fatal."""
         import gc
         import torch.nn.functional as F
-        from ffwm_b200 import conv, external_function as EF, light_cnn, losses, norm
+        from ffwm_b200 import conv, external_function as EF, light_cnn, losses, norm, pool, spectral
         from ffwm_b200.train_step import FFWMTrainer
 
         def lib_warp(images, flow):
             return F.grid_sample(images, flow.permute(0, 2, 3, 1), mode='bilinear', padding_mode='zeros', align_corners=False)
 
-        saved = (conv.ENABLED, EF.grid_warp, losses.grid_warp, EF.FUSED_GF, light_cnn.FUSED_MFM, norm.ENABLED,
+        saved = (conv.ENABLED, EF.grid_warp, losses.grid_warp, EF.FUSED_GF, light_cnn.FUSED_MFM, norm.ENABLED, pool.ENABLED, spectral.FUSED_SN,
                  losses.FUSED_AFFINE, losses.FUSED_CORRMAX, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
         rows = {}
         try:
-            conv.ENABLED, EF.FUSED_GF, light_cnn.FUSED_MFM, norm.ENABLED = False, False, False, False
+            conv.ENABLED, EF.FUSED_GF, light_cnn.FUSED_MFM, norm.ENABLED, pool.ENABLED, spectral.FUSED_SN = False, False, False, False, False, False
             losses.FUSED_AFFINE = losses.FUSED_CORRMAX = False
             EF.grid_warp = losses.grid_warp = lib_warp
             for name, tf32 in (("cudnn_fp32", False), ("cudnn_tf32", True)):
@@ -254,12 +254,12 @@ class TrainStepWorkload:
                 gc.collect()
                 torch.cuda.empty_cache()
             rows["note"] = ("same FFWMTrainer / batch / graph replay with conv.ENABLED=False (cuDNN convolutions), cuDNN batch norm + "
-                            "ATen LeakyReLU, F.grid_sample warps, torch-op guided filter and MFM (ffwm_b200_kernels_in_graph must be 0); "
+                            "ATen LeakyReLU / max pooling, torch-op spectral norm (batched per shape), F.grid_sample warps, torch-op guided filter and MFM (ffwm_b200_kernels_in_graph must be 0); "
                             "host-side restructurings (batched spectral norm / loss networks, torch's fused Adam) unchanged")
         except Exception as e:          # noqa: BLE001 - the bench line must survive
             rows["error"] = repr(e)
         finally:
-            (conv.ENABLED, EF.grid_warp, losses.grid_warp, EF.FUSED_GF, light_cnn.FUSED_MFM, norm.ENABLED,
+            (conv.ENABLED, EF.grid_warp, losses.grid_warp, EF.FUSED_GF, light_cnn.FUSED_MFM, norm.ENABLED, pool.ENABLED, spectral.FUSED_SN,
              losses.FUSED_AFFINE, losses.FUSED_CORRMAX, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32) = saved
         return rows
 

@@ -16,7 +16,7 @@ timeout 300 python -m benchmarks.conv --out $O/${TAG}_conv.json > $O/${TAG}_conv
 timeout 300 python -m benchmarks.conv --gen --out $O/${TAG}_conv_gen.json > $O/${TAG}_conv_gen.txt 2>&1
 timeout 300 python -m benchmarks.conv --wgrad --out $O/${TAG}_conv_wgrad.json > $O/${TAG}_conv_wgrad.txt 2>&1
 timeout 300 python benchmarks/batch_norm.py > $O/${TAG}_batch_norm.txt 2>&1
-for sw in FFWM_FUSED_BN=0 FFWM_FUSED_ADAM=0; do
+for sw in FFWM_FUSED_BN=0 FFWM_FUSED_ADAM=0 FFWM_FUSED_SN=0 FFWM_FUSED_POOL=0 FFWM_BATCHED_L1=0 FFWM_LOSSNET_MATH_FWD=0 FFWM_CONV_OCC2=1 FFWM_WGRAD_NO_ROWS=1; do
     env $sw timeout 400 python bench.py --no-cpu-baseline --no-warp --no-library-baseline --no-e2e > $O/${TAG}_bench_${sw%%=*}_off.json 2> /dev/null; echo "bench $sw rc=$?"
 done
 # compute-sanitizer over the kernels added since the last sanitizer pass (batch norm / channel sum, weight packing, wgrad reduction)
@@ -24,11 +24,16 @@ done
 for tool in memcheck racecheck; do
     echo "== batch_norm_$tool"
     timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 20 python -m pytest tests/test_batch_norm_gpu.py -q -x \
-        -k "2-5-7-9 or 3-4-2-2 or 8-195-32-32 or channel_sum or bit_identical" 2>&1 | grep -E "SUMMARY|passed|failed" | tail -2
+        -k "2-5-7-9 or 3-4-2-2 or 8-195-32-32 or 2-6-16-16 or 7-3-20-28 or channel_sum or bit_identical" 2>&1 | grep -E "SUMMARY|passed|failed" | tail -2
+done
+for tool in memcheck racecheck; do
+    echo "== spectral_pool_$tool"
+    timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 20 python -m pytest tests/test_spectral_gpu.py tests/test_pool_gpu.py -q -x \
+        -k "discriminator or declines or 3-5-7-9 or 2-3-8-8 or modules_use" 2>&1 | grep -E "SUMMARY|passed|failed" | tail -2
 done
 echo "== convgen_pack_wgrad_memcheck"
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 20 python -m pytest tests/test_conv_gen_gpu.py -q -x \
-    -k "modules_autograd or deterministic or strided_views" 2>&1 | grep -E "SUMMARY|passed|failed" | tail -2
+    -k "modules_autograd or deterministic or strided_views or (wgrad and (96-200-32 or 120-40-18 or 130-24-17))" 2>&1 | grep -E "SUMMARY|passed|failed" | tail -2
 } > $O/${TAG}_sanitizer_summary.txt 2>&1; cat $O/${TAG}_sanitizer_summary.txt
 FFWM_BENCH_GRAPH=0 FFWM_BENCH_NCU_RANGE=1 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 40000 --csv --log-file $O/launches_train_$TAG.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-warp --no-library-baseline > $O/ncu_launches_train_$TAG.log 2>&1; echo "ncu train launches rc=$?"
@@ -36,7 +41,8 @@ FFWM_BENCH_GRAPH=0 FFWM_BENCH_NCU_RANGE=1 timeout 1500 ncu --metrics gpu__time_d
 python - $TAG <<'PY'
 import json, sys
 t = sys.argv[1]
-for f in ("bench", "bench_reference", "bench_warp", "bench_warp_smooth", "bench_flownet", "bench_fwdbf16", "bench_FFWM_FUSED_BN_off", "bench_FFWM_FUSED_ADAM_off"):
+for f in ("bench", "bench_reference", "bench_warp", "bench_warp_smooth", "bench_flownet", "bench_fwdbf16", "bench_FFWM_FUSED_BN_off", "bench_FFWM_FUSED_ADAM_off", "bench_FFWM_FUSED_SN_off", "bench_FFWM_FUSED_POOL_off", "bench_FFWM_BATCHED_L1_off",
+          "bench_FFWM_LOSSNET_MATH_FWD_off", "bench_FFWM_CONV_OCC2_off", "bench_FFWM_WGRAD_NO_ROWS_off"):
     try:
         d = json.loads(open("gpurun_out/%s_%s.json" % (t, f)).read().strip().splitlines()[-1])
         print(f, round(d["value"], 2), d["unit"], round(d["ms_per_step"], 3), "ms/step", "e2e", d.get("e2e", {}).get("value"))
