@@ -207,9 +207,52 @@ class TrainStepWorkload:
             rows["note"] = ("timed alone after the step (burst clocks); three MMAs are issued per product for fp32-level accuracy; "
                             "bf16x3 fractions are against the measured dense bf16 burst rate (MEASURED_PEAKS.json), the TF32 rate "
                             "measured in this run is in measured_tensor_peaks")
+            rows.update(self._hbm_kernel_rows(pk))
             return rows
         except Exception as e:          # noqa: BLE001 - the bench line must survive
             return {"error": repr(e)}
+
+    def _hbm_kernel_rows(self, pk):
+        """The HBM-bound hand-written kernels of the step that are not warp ops, on the largest map of the step (netG dres2:
+        8 x 195 x 128 x 128 = 102 MB, two rotating copies: 409 MB of operands, larger than L2): batch norm + LeakyReLU +
+        residual forward (algorithmic 3 reads + 1 write), backward (5 reads + 2 writes incl. the residual's gradient), and the
+        bias-gradient channel sum (1 read), against the measured HBM copy bandwidth."""
+        from ffwm_b200 import ops
+        shape = (BATCH, 195, 128, 128)
+        nbytes = 4 * BATCH * 195 * 128 * 128
+        xs = [torch.randn(shape, device=self.dev) for _ in range(2)]
+        gos = [torch.randn(shape, device=self.dev) for _ in range(2)]
+        res, y, gx, gr = (torch.empty(shape, device=self.dev).normal_() for _ in range(4))
+        c = shape[1]
+        w, b = torch.rand(c, device=self.dev) + 0.5, torch.randn(c, device=self.dev)
+        rm, rv, sm, si, gw, gb = (torch.zeros(c, device=self.dev) for _ in range(6))
+        peak = pk.get("hbm_gbs")
+
+        def timed(fn, iters=10):
+            for i in range(3):
+                fn(i)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(iters):
+                fn(i)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters
+
+        cases = {
+            "batch_norm+lrelu+residual fwd 8x195x128x128": (4, lambda i: ops.batch_norm_forward(xs[i % 2], res, w, b, rm, rv, 0.1, 1e-5, 0.2, y, sm, si)),
+            "batch_norm+lrelu+residual bwd 8x195x128x128": (7, lambda i: ops.batch_norm_backward(xs[i % 2], gos[i % 2], y, w, b, sm, si, 0.2, gx, gr, gw, gb)),
+            "channel_sum (bias gradient) 8x195x128x128": (1, lambda i: ops.channel_sum(gos[i % 2])),
+        }
+        rows = {}
+        for name, (passes, fn) in cases.items():
+            ms = timed(fn)
+            gbps = passes * nbytes / ms / 1e6
+            rows[name] = {"ms": round(ms, 4), "algorithmic_GB": round(passes * nbytes / 1e9, 3), "GB/s": round(gbps, 1)}
+            if peak:
+                rows[name]["frac_hbm"] = round(gbps / peak, 4)
+        return rows
 
     # ------------------------------------------------------------------ same-run GPU library baseline
     def gpu_library_baseline(self, steps=10, warmup=3):
