@@ -55,6 +55,7 @@ SIGNATURES = {
     "ffwm_batch_norm_workspace_bytes": [_I, _I, ctypes.c_int64],
     "ffwm_batch_norm_forward": [_VP] * 6 + [ctypes.c_float] * 3 + [_VP] * 3 + [_I, _I, ctypes.c_int64, _VP, ctypes.c_int64, _VP],
     "ffwm_batch_norm_backward": [_VP] * 7 + [ctypes.c_float] + [_VP] * 4 + [_I, _I, ctypes.c_int64, _VP, ctypes.c_int64, _VP],
+    "ffwm_conv_few": [_T4P, _T4P, _I, _I, _VP, _T4P, _I, _I, _VP],
     "ffwm_max_pool2x2_forward": [_VP, _VP, ctypes.c_int64, _I, _I, _I, _I, _VP],
     "ffwm_max_pool2x2_backward": [_VP, _VP, _VP, ctypes.c_int64, _I, _I, _I, _I, _VP],
     "ffwm_spectral_norm_forward": [_VP, _I, _I, ctypes.c_float] + [_VP] * 6 + [_I, _I, _I, _VP],

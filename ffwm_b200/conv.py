@@ -101,6 +101,35 @@ def eligible(x, weight, stride, padding, dilation, groups, padding_mode="zeros",
 
 _DIAG_FWD_LIB = _DIAG_DGRAD_LIB = False      # scripts/diag_nets.py only: one direction on the library
 
+# Degenerate channel counts (csrc/conv_few.cu): <= 4 input channels, or ONE output channel at stride 1 on maps of at least 32x32
+# with at most 512 input channels, run as direct fp32 FFMA kernels instead of tensor-core tiles that are 75-97 % padding.
+# Measured in the train step (gpurun call 80): the few-input kernel replaces 2.4 ms of tensor-core launches with 1.0 ms, the
+# one-output kernel (LightCNN stem's data gradient) 331 us with 190 us; with 2-4 output channels the direct kernel is
+# instruction-bound and LOSES to the tensor cores (233 vs ~40 us on VGG conv1_1's data gradient), so those stay where they were.
+# FFWM_CONV_FEW=0: tensor cores for everything.
+FEW = os.environ.get("FFWM_CONV_FEW", "1") == "1"
+
+
+def _few_forward(x, weight, bias, out, stride, pad):
+    """conv2d(x, weight, bias, stride, pad) -> out on the direct kernels when the shape qualifies; False otherwise."""
+    if not FEW:
+        return False
+    if weight.size(1) <= 4 or (weight.size(0) == 1 and stride == 1 and weight.size(1) <= 512 and out.size(2) * out.size(3) >= 1024):
+        ops.conv_few(x, weight, False, False, bias, out, stride, pad)
+        return True
+    return False
+
+
+def _few_dgrad(grad_out, weight, gx, stride, pad):
+    """grad_input of conv2d(x, weight, stride 1, pad) -> gx: a convolution of grad_out with the transposed, flipped weight."""
+    kh, kw = weight.shape[2:]
+    if not FEW or stride != 1 or kh != kw or kh - 1 - pad < 0:
+        return False
+    if weight.size(0) <= 4 or (weight.size(1) == 1 and weight.size(0) <= 512 and gx.size(2) * gx.size(3) >= 1024):
+        ops.conv_few(grad_out, weight, True, True, None, gx, 1, kh - 1 - pad)
+        return True
+    return False
+
 
 class Conv3x3TCFunction(Function):
     @staticmethod
@@ -111,6 +140,8 @@ class Conv3x3TCFunction(Function):
         if _DIAG_FWD_LIB:
             return torch.nn.functional.conv2d(x, weight, bias, padding=1)
         out = x.new_empty((x.size(0), weight.size(0), x.size(2), x.size(3)))
+        if _few_forward(x, weight, bias, out, 1, 1):
+            return out
         nt = _nt(x.size(3), weight.size(0))
         math = MATH_FWD if math_fwd is None else math_fwd
         ops.conv3x3_forward(x, _packed(weight, False, nt, math), bias, out, nt=nt, math=math)
@@ -126,8 +157,9 @@ class Conv3x3TCFunction(Function):
             gx = torch.ops.aten.convolution_backward(grad_out, x, weight, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, False, False])[0]
         elif ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
-            nt = _nt(grad_out.size(3), weight.size(1))
-            ops.conv3x3_forward(grad_out, _packed(weight, True, nt, MATH_BWD), None, gx, nt=nt, math=MATH_BWD)
+            if not _few_dgrad(grad_out, weight, gx, 1, 1):
+                nt = _nt(grad_out.size(3), weight.size(1))
+                ops.conv3x3_forward(grad_out, _packed(weight, True, nt, MATH_BWD), None, gx, nt=nt, math=MATH_BWD)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             gw, gb = _wgrad(grad_out, x, weight, ctx.has_bias, 1, 1, False, 0, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         return gx, gw, gb, None
@@ -191,6 +223,8 @@ class ConvGenFunction(Function):
         ctx.cfg = (bias is not None, stride, pad)
         kh, kw = weight.shape[2:]
         out = x.new_empty((x.size(0), weight.size(0), (x.size(2) + 2 * pad - kh) // stride + 1, (x.size(3) + 2 * pad - kw) // stride + 1))
+        if _few_forward(x, weight, bias, out, stride, pad):
+            return out
         math = MATH_FWD if math_fwd is None else math_fwd
         ops.conv_forward(x, _packed_gen(weight, False, stride, pad, False, math), bias, out, kh, kw, stride, pad, False, math)
         return out
@@ -204,7 +238,8 @@ class ConvGenFunction(Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x, memory_format=torch.contiguous_format)
-            ops.conv_forward(grad_out, _packed_gen(weight, True, stride, pad, True, MATH_BWD), None, gx, kh, kw, stride, pad, True, MATH_BWD)
+            if not _few_dgrad(grad_out, weight, gx, stride, pad):
+                ops.conv_forward(grad_out, _packed_gen(weight, True, stride, pad, True, MATH_BWD), None, gx, kh, kw, stride, pad, True, MATH_BWD)
         if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
             gw, gb = _wgrad(grad_out, x, weight, has_bias, stride, pad, False, 0, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         return gx, gw, gb, None, None, None

@@ -312,3 +312,14 @@ def max_pool2x2_backward(x, grad_out, grad_x):
         raise ValueError("max_pool2x2: contiguous fp32 (N,C,H,W) tensors expected")
     L.call("ffwm_max_pool2x2_backward", dev, _ptr(x), _ptr(grad_out), _ptr(grad_x), ctypes.c_int64(x.size(0) * x.size(1)), int(x.size(2)),
            int(x.size(3)), int(grad_out.size(2)), int(grad_out.size(3)))
+
+
+def conv_few(x, weight, in_major, flip, bias, out, stride, pad):
+    """Direct fp32 convolution for <= 4 input channels, or <= 4 output channels at stride 1 (csrc/conv_few.cu); `weight` is read
+    through (in_major, flip), see include/ffwm_b200.h."""
+    import ctypes
+    dev = L.require_cuda(x, weight, out)
+    if bias is not None and not (bias.is_cuda and bias.is_contiguous() and bias.dtype == x.dtype and bias.numel() == out.size(1)):
+        raise ValueError("conv_few: bias must be a contiguous fp32 CUDA tensor of Cout elements")
+    L.call("ffwm_conv_few", dev, L.t4(x), L.t4(weight), int(bool(in_major)), int(bool(flip)),
+           ctypes.c_void_p(bias.data_ptr() if bias is not None else None), L.t4(out), int(stride), int(pad))

@@ -199,6 +199,16 @@ int ffwm_batch_norm_backward(const float* x, const float* grad_out, const float*
                              float* grad_gamma, float* grad_beta, int n, int c, int64_t hw, void* workspace, int64_t workspace_bytes,
                              void* stream);
 
+/* ---- direct fp32 convolution for degenerate channel counts (csrc/conv_few.cu) -----------------------------------------------
+ * out = conv2d(x, W', bias, stride, pad) where W' has at most 4 input channels (LightCNN's 5x5 stem, the 7x7 / 3x3 stems on RGB:
+ * lightcnn/light_cnn.py:96-100, models/base_networks.py:59-75,230,397-399, models/losses.py:430) or at most 4 output channels at
+ * stride 1 (flow heads, reconstructions, the stems' data gradients: models/base_networks.py:45-57,241); FFWM_ERR_ARG otherwise.
+ * W' is `weight` read through (in_major, flip): in_major = 0: W'[o][i] = weight[o][i]; 1: W'[o][i] = weight[i][o]; flip: taps
+ * reversed — the data gradient of a stride-1 convolution is ffwm_conv_few(grad_out, weight, 1, 1, NULL, grad_in, 1, k-1-pad).
+ * Exact fp32 FFMA accumulation; any strides; kernels up to 7x7; stride 1 or 2 (few inputs only); bias may be NULL. */
+int ffwm_conv_few(const ffwm_tensor4* x, const ffwm_tensor4* weight, int in_major, int flip, const float* bias, const ffwm_tensor4* out,
+                  int stride, int pad, void* stream);
+
 /* ---- 2x2 / stride-2 max pooling (csrc/pool.cu): nn.MaxPool2d(2, 2[, ceil_mode=True]) / F.max_pool2d(x, 2) of LightCNN and VGG19
  * (lightcnn/light_cnn.py:38-42,96-124, models/losses.py:430-470) without ATen's int64 index map: x (planes, h, w) -> out (planes,
  * ho, wo), contiguous fp32, ho in {floor(h/2), ceil(h/2)}; backward recomputes the argmax from x (first maximum wins, NaN wins:
