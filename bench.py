@@ -12,9 +12,14 @@ One JSON line on stdout (rank 0).  Workloads live in benchmarks/*.py; each is
                  local_attn_reshape and the bilinear grid-warp, forward+backward, on feature
                  maps far larger than L2
 
-`--impl reference` times the CPU restatement of the same path (oracle/) on the
-host cores — the only place besides tests/ and smoke() that executes oracle/.
-Nothing here reads the reference checkout (absent on the GPU box).
+    flownet      FlowNet pre-training forward+backward (BASELINE config 2; batch 6), CUDA-graph replay
+
+`--impl reference` times the reference's own CPU implementation of the workload on all host cores:
+for train_step the UNMODIFIED `FFWMModel(gpu_ids=[])` at batch 8 from `baseline/_ref` (a byte-identical,
+git-ignored staging of the reference's `models/` + `lightcnn/`, see baseline/stage_ref.py), for flownet
+the reference's `FlowNet(64)`, for warp the reference's formulation (C oracle / torch grid_sample) — the
+only place besides tests/ and smoke() that executes oracle/.  Under torchrun rank 0 alone runs it.
+Nothing here reads /root/reference (absent on the GPU box).
 """
 import argparse
 import json
