@@ -19,7 +19,7 @@ for train_step the UNMODIFIED `FFWMModel(gpu_ids=[])` at batch 8 from `baseline/
 git-ignored staging of the reference's `models/` + `lightcnn/`, see baseline/stage_ref.py), for flownet
 the reference's `FlowNet(64)`, for warp the reference's formulation (C oracle / torch grid_sample) — the
 only place besides tests/ and smoke() that executes oracle/.  Under torchrun rank 0 alone runs it.
-Nothing here reads /root/reference (absent on the GPU box).
+Nothing here reads the reference checkout (absent on the GPU box).
 """
 import argparse
 import json
