@@ -66,3 +66,30 @@ def test_generator_batched_sn_matches_per_layer_hooks_fp32(monkeypatch):
     for pa, pb in zip(ref.parameters(), net.parameters()):
         if pa.grad is not None:
             assert (pa.grad - pb.grad).abs().max() <= 1e-5 * max(1.0, float(pa.grad.abs().max()))
+
+
+def test_fused_plan_table_layout():
+    """Host side of the fused path (ffwm_b200/spectral.py:_Plan): the device table csrc/spectral_norm.cu walks — 8 int64 per
+    layer, then three block-prefix arrays with ceil(w/32), ceil(h/8), ceil(h*w/4096) blocks per layer."""
+    import math
+    from torch.nn.utils import spectral_norm
+    from ffwm_b200.spectral import _Plan
+    torch.manual_seed(0)
+    mods = [spectral_norm(torch.nn.Conv2d(3, 8, 3)), spectral_norm(torch.nn.Conv2d(8, 40, 5)), spectral_norm(torch.nn.Conv2d(40, 4, 1))]
+    plan = _Plan(mods, 1e-12)
+    t = plan.table.tolist()
+    n = len(mods)
+    oe = ot = os_ = 0
+    for i, m in enumerate(mods):
+        h, w = m.weight_orig.shape[0], m.weight_orig[0].numel()
+        assert t[8 * i:8 * i + 8] == [m.weight_orig.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr(), h, w, oe, ot, os_]
+        assert plan.slices[i] == (oe, h * w, tuple(m.weight_orig.shape))
+        oe, ot, os_ = oe + h * w, ot + w, os_ + h
+    assert (plan.total, plan.sum_w, plan.sum_h) == (oe, ot, os_)
+    pre = t[8 * n:]
+    for k, per in enumerate((lambda h, w: math.ceil(w / 32), lambda h, w: math.ceil(h / 8), lambda h, w: math.ceil(h * w / 4096))):
+        want = [0]
+        for m in mods:
+            want.append(want[-1] + per(m.weight_orig.shape[0], m.weight_orig[0].numel()))
+        assert pre[k * (n + 1):(k + 1) * (n + 1)] == want and plan.blocks[k] == want[-1]
+    assert plan.key == _Plan.pointers(mods)
