@@ -37,7 +37,8 @@ MATH_BWD = int(os.environ.get("FFWM_CONV_MATH_BWD", ops.L.MATH_BF16X3))
 WIDTHS = (128, 64, 32)
 if os.environ.get("FFWM_CONV3X3_WIDTHS"):     # A/B: route some widths to the general kernel instead
     WIDTHS = tuple(int(v) for v in os.environ["FFWM_CONV3X3_WIDTHS"].split(","))
-# experimental, unmeasured: 128 output channels per CTA for the W = 128 layers with more than 64 of them
+# 128 output channels per CTA for the W = 128 layers with more than 64 of them (measured: profiles/r02a_conv_nt128.txt;
+# FFWM_CONV_NT128=0 for the A/B)
 NT128 = os.environ.get("FFWM_CONV_NT128", "1") == "1"
 
 
@@ -45,8 +46,8 @@ def _nt(width, n_out):
     return 128 if (NT128 and width == 128 and n_out > 64) else 64
 
 
-# experimental, unmeasured: keep the packed image of FROZEN weights (VGG19, LightCNN: ~280 of the step's 380 packing
-# launches) instead of re-packing on every call.  A weight qualifies while it is a leaf that does not require grad;
+# Keep the packed image of FROZEN weights (VGG19, LightCNN: ~280 of the step's 380 packing launches at the start of round 2)
+# instead of re-packing on every call (default on since round 2: profiles/r02b_switches.txt).  A weight qualifies while it is a leaf that does not require grad;
 # the image is tagged with the tensor's version counter and data pointer, so any in-place update (optimizer step,
 # load_state_dict, .data swap) re-packs.  Spectral-normed weights are new tensors on every call and never qualify.
 CACHE_PACKED = os.environ.get("FFWM_CACHE_PACKED", "1") == "1"

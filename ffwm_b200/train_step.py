@@ -27,8 +27,8 @@ from .parallel import GradAverager
 
 
 # The perceptual losses of one step through 6 VGG19 passes instead of 14 and the identity losses through 2 LightCNN
-# passes instead of 4 (losses.PerceptualLoss.many / IdentityLoss.many: same samples, bigger batches): CPU-verified
-# against the reference goldens, not yet measured on a B200 (written after the round-1 GPU budget was spent).
+# passes instead of 4 (losses.PerceptualLoss.many / IdentityLoss.many: same samples, bigger batches): verified against
+# the reference goldens on the CPU and on a B200, default on since round 2 (profiles/r02a_switches.txt).
 BATCHED_VGG = os.environ.get("FFWM_BATCHED_VGG", "1") == "1"
 FLOW_STREAMS = os.environ.get("FFWM_FLOW_STREAMS", "1") == "1"      # see FFWMTrainer._flownets
 
@@ -126,7 +126,7 @@ class FFWMTrainer:
         convolutions each work on maps of 8x8 and below (a few CTAs on 148 SMs), so FFWM_FLOW_STREAMS=1 runs
         flowNetB on a second stream, forked from and joined back into the current one (legal inside CUDA-graph
         capture; autograd runs each net's backward on the stream its forward used).  Same arithmetic, same order
-        within each net.  Not yet run on a GPU (written after the round-1 GPU budget was spent): off by default."""
+        within each net.  Default on since round 2 (profiles/r02a_switches.txt; FFWM_FLOW_STREAMS=0 for the A/B)."""
         if not (FLOW_STREAMS and self.device.type == "cuda"):
             flows_F = self.flowNetF(self.img_S)
             return flows_F, self.flowNetB(self.img_S)
