@@ -12,6 +12,7 @@ Everything else (eval mode, CPU tensors, other dtypes, affine=False, momentum=No
 absorbed activation applied afterwards, so the module computes the same function everywhere.
 FFWM_FUSED_BN=0 routes training mode through torch as well (the A/B switch).
 """
+import copy
 import functools
 import os
 
@@ -63,6 +64,13 @@ class BatchNorm2d(nn.BatchNorm2d):
         super().__init__(*args, **kwargs)
         self.act_slope = None
         self._deferred = None                           # [pending calls] once a DeferredCounters owns this layer
+
+    def __deepcopy__(self, memo):
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        new.__dict__ = copy.deepcopy(self.__dict__, memo)
+        new._deferred = None            # a copy is not owned by the original's DeferredCounters: it counts by itself again
+        return new
 
     def _fast(self, x):
         return (ENABLED and self.training and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and self.affine

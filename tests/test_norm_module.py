@@ -57,3 +57,15 @@ def test_deferred_counters_add_up_like_torch():
     # (on the CPU the layer takes torch's path, which counts by itself: deferral only applies to the CUDA kernels' path)
     ctr.flush()
     assert int(a[1].num_batches_tracked) == int(b[1].num_batches_tracked) == 3
+
+
+def test_deep_copies_leave_the_deferred_counters():
+    import copy
+    from ffwm_b200.norm import DeferredCounters
+    net = nn.Sequential(nn.Conv2d(3, 4, 1), BatchNorm2d(4))
+    DeferredCounters([net])
+    twin = copy.deepcopy(net)
+    assert net[1]._deferred is not None and twin[1]._deferred is None
+    assert list(twin.state_dict()) == list(net.state_dict()) and twin[1].weight is not net[1].weight
+    twin(torch.randn(2, 3, 4, 4))
+    assert int(twin[1].num_batches_tracked) == 1
